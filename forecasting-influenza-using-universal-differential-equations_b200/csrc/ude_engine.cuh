@@ -1,0 +1,501 @@
+// ude_engine.cuh — device-side building blocks of the fused UDE solve (sm_100a).
+//
+// One CTA owns a tile of TB trajectories for a whole integration.  All per-tile
+// data lives in shared memory as ROWS of TB floats (row stride TBP = TB + 4):
+//   X    [D_p ][TBP]  MLP input u = vec(x), row r*L + l        (lib/models.py:119 Flatten)
+//   ACT_l[n_out_p][TBP] output of every nn.Linear (after ELU where the reference has one)
+//   S_k  [Dn_p][TBP]  solver state rows (y, k_i, adjoints), row r*3 + c
+// so that a trajectory is a COLUMN: threads that walk along a row touch
+// consecutive banks, and the three matrix products of the path
+//   forward   ACT_l = W_l . ACT_{l-1}            (m = trajectory, n = out, k = in)
+//   delta     d_{l-1} = W_l^T . d_l              (m = trajectory, n = in,  k = out)
+//   dW        dW_l += d_l . ACT_{l-1}^T          (m = in, n = out, k = trajectory)
+// are register-tiled FFMA micro-kernels with 128-bit shared-memory operand
+// loads (8x4 lane grid per warp).  The packed weights sit in shared memory too
+// (staged once per CTA with a TMA bulk copy) unless they do not fit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ude_model.h"
+
+namespace ude {
+
+// ----------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ELU(alpha=1) (lib/models.py:122 nn.ELU).  exp via MUFU.EX2: absolute error ~1e-7,
+// far inside the 1e-5 parity budget; the backward uses the SAME value (a + 1).
+__device__ __forceinline__ float elu_f(float h) { return h > 0.f ? h : (__expf(h) - 1.0f); }
+__device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.0f : a + 1.0f; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ----------------------------------------------------------------------------------
+// TMA bulk staging of the packed weights (global -> shared), once per CTA (or per
+// weight-set change).  cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP.
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Stage `n_floats` (multiple of 4) from global to shared with bulk copies of <= 32 KB.
+// Called by ALL threads of the CTA; returns when the data is visible to all of them.
+__device__ __forceinline__ void stage_weights_tma(float* dst, const float* src, int n_floats, uint64_t* bar,
+                                                  uint32_t& phase) {
+    const uint32_t total = static_cast<uint32_t>(n_floats) * 4u;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, total);
+        uint32_t done = 0;
+        while (done < total) {
+            uint32_t chunk = total - done;
+            if (chunk > 32768u) chunk = 32768u;
+            tma_bulk_g2s(reinterpret_cast<char*>(dst) + done, reinterpret_cast<const char*>(src) + done, chunk, bar);
+            done += chunk;
+        }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
+
+// ----------------------------------------------------------------------------------
+// micro-kernels.  Lane grid inside a warp: tx = lane & 7 (8 along m), ty = lane >> 3 (4 along n).
+// ----------------------------------------------------------------------------------
+
+// forward:  out[n][m] = act( bias[n] + sum_k W[n][k] * in[k][m] ),  m-tile = 32 trajectories,
+// n-tile = 4*TN outputs (n = n0 + ty + 4q).  in: rows k (k-major), W: rows n (n-major).
+template <int TN>
+__device__ __forceinline__ void fwd_unit(const LayerP& Lp, const float* __restrict__ Wp, float* __restrict__ smem,
+                                         const int TBP, const int mt, const int nt, const int lane) {
+    const int tx = lane & 7, ty = lane >> 3;
+    const int m_off = mt * 32 + tx * 4;
+    const int n0 = nt * (4 * TN);
+    const float* __restrict__ A = smem + Lp.in_off + m_off;
+    const float* __restrict__ W = Wp + Lp.w_off;
+    int wofs[TN];
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        int n = n0 + ty + 4 * q;
+        n = n < Lp.n_out_p ? n : Lp.n_out_p - 1;
+        wofs[q] = n * Lp.ldw;
+    }
+    float acc[TN][4];
+#pragma unroll
+    for (int q = 0; q < TN; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+
+    const int K = Lp.n_in_p;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        const float4 a0 = ld4(A + (k + 0) * TBP);
+        const float4 a1 = ld4(A + (k + 1) * TBP);
+        const float4 a2 = ld4(A + (k + 2) * TBP);
+        const float4 a3 = ld4(A + (k + 3) * TBP);
+#pragma unroll
+        for (int q = 0; q < TN; ++q) {
+            const float4 w = ld4(W + wofs[q] + k);
+            acc[q][0] = fmaf(a0.x, w.x, acc[q][0]);
+            acc[q][1] = fmaf(a0.y, w.x, acc[q][1]);
+            acc[q][2] = fmaf(a0.z, w.x, acc[q][2]);
+            acc[q][3] = fmaf(a0.w, w.x, acc[q][3]);
+            acc[q][0] = fmaf(a1.x, w.y, acc[q][0]);
+            acc[q][1] = fmaf(a1.y, w.y, acc[q][1]);
+            acc[q][2] = fmaf(a1.z, w.y, acc[q][2]);
+            acc[q][3] = fmaf(a1.w, w.y, acc[q][3]);
+            acc[q][0] = fmaf(a2.x, w.z, acc[q][0]);
+            acc[q][1] = fmaf(a2.y, w.z, acc[q][1]);
+            acc[q][2] = fmaf(a2.z, w.z, acc[q][2]);
+            acc[q][3] = fmaf(a2.w, w.z, acc[q][3]);
+            acc[q][0] = fmaf(a3.x, w.w, acc[q][0]);
+            acc[q][1] = fmaf(a3.y, w.w, acc[q][1]);
+            acc[q][2] = fmaf(a3.z, w.w, acc[q][2]);
+            acc[q][3] = fmaf(a3.w, w.w, acc[q][3]);
+        }
+    }
+    const float* __restrict__ bias = Wp + Lp.b_off;
+    float* __restrict__ out = smem + Lp.act_off + m_off;
+    const bool elu = Lp.elu != 0;
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        const int n = n0 + ty + 4 * q;
+        if (n < Lp.n_out_p) {
+            const float b = bias[n];
+            float4 v = make_float4(acc[q][0] + b, acc[q][1] + b, acc[q][2] + b, acc[q][3] + b);
+            if (elu) {
+                v.x = elu_f(v.x);
+                v.y = elu_f(v.y);
+                v.z = elu_f(v.z);
+                v.w = elu_f(v.w);
+            }
+            st4(out + n * TBP, v);
+        }
+    }
+}
+
+// delta:  d_in[n][m] = elu'(.) * sum_k W[k][n] * d_out[k][m]   (n = input feature, k = output feature)
+// d_out lives in this layer's ACT rows (in place); the result overwrites the PREVIOUS
+// layer's ACT rows (scaled by ELU' read from them) or, for layer 0, goes to the GX rows.
+template <int TN>
+__device__ __forceinline__ void bwd_unit(const LayerP& Lp, const LayerP* prev, const float* __restrict__ Wp,
+                                         float* __restrict__ smem, const int TBP, const int gx_off, const int mt,
+                                         const int nt, const int lane) {
+    static_assert(TN == 4 || TN == 8, "TN");
+    const int tx = lane & 7, ty = lane >> 3;
+    const int m_off = mt * 32 + tx * 4;
+    const int n0 = nt * (4 * TN);
+    const float* __restrict__ Dl = smem + Lp.act_off + m_off;
+    const float* __restrict__ W = Wp + Lp.w_off + n0 + ty * 4;
+    const int ldw = Lp.ldw;
+    float acc[TN][4];
+#pragma unroll
+    for (int q = 0; q < TN; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    const int K = Lp.n_out;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float4 a = ld4(Dl + k * TBP);
+        const float4 w0 = ld4(W + k * ldw);
+        acc[0][0] = fmaf(a.x, w0.x, acc[0][0]); acc[0][1] = fmaf(a.y, w0.x, acc[0][1]);
+        acc[0][2] = fmaf(a.z, w0.x, acc[0][2]); acc[0][3] = fmaf(a.w, w0.x, acc[0][3]);
+        acc[1][0] = fmaf(a.x, w0.y, acc[1][0]); acc[1][1] = fmaf(a.y, w0.y, acc[1][1]);
+        acc[1][2] = fmaf(a.z, w0.y, acc[1][2]); acc[1][3] = fmaf(a.w, w0.y, acc[1][3]);
+        acc[2][0] = fmaf(a.x, w0.z, acc[2][0]); acc[2][1] = fmaf(a.y, w0.z, acc[2][1]);
+        acc[2][2] = fmaf(a.z, w0.z, acc[2][2]); acc[2][3] = fmaf(a.w, w0.z, acc[2][3]);
+        acc[3][0] = fmaf(a.x, w0.w, acc[3][0]); acc[3][1] = fmaf(a.y, w0.w, acc[3][1]);
+        acc[3][2] = fmaf(a.z, w0.w, acc[3][2]); acc[3][3] = fmaf(a.w, w0.w, acc[3][3]);
+        if (TN == 8) {
+            const float4 w1 = ld4(W + k * ldw + 16);
+            acc[TN - 4][0] = fmaf(a.x, w1.x, acc[TN - 4][0]); acc[TN - 4][1] = fmaf(a.y, w1.x, acc[TN - 4][1]);
+            acc[TN - 4][2] = fmaf(a.z, w1.x, acc[TN - 4][2]); acc[TN - 4][3] = fmaf(a.w, w1.x, acc[TN - 4][3]);
+            acc[TN - 3][0] = fmaf(a.x, w1.y, acc[TN - 3][0]); acc[TN - 3][1] = fmaf(a.y, w1.y, acc[TN - 3][1]);
+            acc[TN - 3][2] = fmaf(a.z, w1.y, acc[TN - 3][2]); acc[TN - 3][3] = fmaf(a.w, w1.y, acc[TN - 3][3]);
+            acc[TN - 2][0] = fmaf(a.x, w1.z, acc[TN - 2][0]); acc[TN - 2][1] = fmaf(a.y, w1.z, acc[TN - 2][1]);
+            acc[TN - 2][2] = fmaf(a.z, w1.z, acc[TN - 2][2]); acc[TN - 2][3] = fmaf(a.w, w1.z, acc[TN - 2][3]);
+            acc[TN - 1][0] = fmaf(a.x, w1.w, acc[TN - 1][0]); acc[TN - 1][1] = fmaf(a.y, w1.w, acc[TN - 1][1]);
+            acc[TN - 1][2] = fmaf(a.z, w1.w, acc[TN - 1][2]); acc[TN - 1][3] = fmaf(a.w, w1.w, acc[TN - 1][3]);
+        }
+    }
+    float* __restrict__ dst = smem + (prev ? prev->act_off : gx_off) + m_off;
+    const bool elu = prev && prev->elu;
+    const bool accumulate = prev == nullptr;      // layer 0: GX += W0^T delta0 (GX pre-loaded with the direct term)
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        const int n = n0 + (q >> 2) * 16 + ty * 4 + (q & 3);
+        if (n < Lp.n_in_p) {
+            float4 v = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+            if (elu) {
+                const float4 e = ld4(dst + n * TBP);
+                v.x *= elu_grad_from_out(e.x);
+                v.y *= elu_grad_from_out(e.y);
+                v.z *= elu_grad_from_out(e.z);
+                v.w *= elu_grad_from_out(e.w);
+            } else if (accumulate) {
+                const float4 e = ld4(dst + n * TBP);
+                v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+            }
+            st4(dst + n * TBP, v);
+        }
+    }
+}
+
+// dW:  G[n][m] += sum_b d[n][b] * in[m][b]    (m = input feature, n = output feature, k = trajectory)
+// m = m0 + tx + 8p, n = n0 + ty + 4q.  Each (n, m) is owned by exactly one thread of one
+// unit, so the accumulators are updated with plain read-modify-writes (deterministic).
+template <int TM, int TN>
+__device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restrict__ smem, float* __restrict__ G,
+                                        const int TB, const int TBP, const int mt, const int nt, const int lane) {
+    const int tx = lane & 7, ty = lane >> 3;
+    const int m0 = mt * (8 * TM), n0 = nt * (4 * TN);
+    int aofs[TM], dofs[TN];
+#pragma unroll
+    for (int p = 0; p < TM; ++p) {
+        int m = m0 + tx + 8 * p;
+        m = m < Lp.n_in_p ? m : Lp.n_in_p - 1;
+        aofs[p] = Lp.in_off + m * TBP;
+    }
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        int n = n0 + ty + 4 * q;
+        n = n < Lp.n_out_p ? n : Lp.n_out_p - 1;
+        dofs[q] = Lp.act_off + n * TBP;
+    }
+    float acc[TN][TM];
+#pragma unroll
+    for (int q = 0; q < TN; ++q)
+#pragma unroll
+        for (int p = 0; p < TM; ++p) acc[q][p] = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < TB; k += 4) {
+        float4 av[TM], dv[TN];
+#pragma unroll
+        for (int p = 0; p < TM; ++p) av[p] = ld4(smem + aofs[p] + k);
+#pragma unroll
+        for (int q = 0; q < TN; ++q) dv[q] = ld4(smem + dofs[q] + k);
+#pragma unroll
+        for (int q = 0; q < TN; ++q)
+#pragma unroll
+            for (int p = 0; p < TM; ++p) {
+                acc[q][p] = fmaf(av[p].x, dv[q].x, acc[q][p]);
+                acc[q][p] = fmaf(av[p].y, dv[q].y, acc[q][p]);
+                acc[q][p] = fmaf(av[p].z, dv[q].z, acc[q][p]);
+                acc[q][p] = fmaf(av[p].w, dv[q].w, acc[q][p]);
+            }
+    }
+    float* __restrict__ Gw = G + Lp.w_off;
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        const int n = n0 + ty + 4 * q;
+#pragma unroll
+        for (int p = 0; p < TM; ++p) {
+            const int m = m0 + tx + 8 * p;
+            if (n < Lp.n_out && m < Lp.n_in) Gw[n * Lp.ldw + m] += acc[q][p];
+        }
+    }
+}
+
+// db: G_b[n] += sum_b d[n][b] for 8 consecutive rows starting at n0 (one warp).
+__device__ __forceinline__ void db_unit(const LayerP& Lp, const float* __restrict__ smem, float* __restrict__ G,
+                                        const int TB, const int TBP, const int n0, const int lane) {
+    for (int n = n0; n < n0 + 8 && n < Lp.n_out; ++n) {
+        const float* row = smem + Lp.act_off + n * TBP;
+        float s = 0.f;
+        for (int b = lane; b < TB; b += 32) s += row[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) G[Lp.b_off + n] += s;
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// phases (each ends with __syncthreads())
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ int fwd_units(const LayerP& Lp, int m_tiles) {
+    return m_tiles * ((Lp.n_out_p + 4 * Lp.tn_fwd - 1) / (4 * Lp.tn_fwd));
+}
+__device__ __forceinline__ void fwd_run(const LayerP& Lp, const float* Wp, float* smem, int TBP, int m_tiles, int u,
+                                        int lane) {
+    const int mt = u % m_tiles, nt = u / m_tiles;
+    if (Lp.tn_fwd == 8) fwd_unit<8>(Lp, Wp, smem, TBP, mt, nt, lane);
+    else if (Lp.tn_fwd == 4) fwd_unit<4>(Lp, Wp, smem, TBP, mt, nt, lane);
+    else fwd_unit<1>(Lp, Wp, smem, TBP, mt, nt, lane);
+}
+
+// All nn.Linear layers of both nets, layer index in lockstep.  Pre: X rows ready and
+// synced.  Post: every ACT buffer ready and synced.
+__device__ __forceinline__ void rhs_forward_layers(const ModelP& P, const float* Wp, float* smem, int warp, int lane) {
+    const int m_tiles = P.TB / 32;
+    const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+    for (int li = 0; li < nl; ++li) {
+        const int u0 = li < P.n_rate ? fwd_units(P.rate[li], m_tiles) : 0;
+        const int u1 = li < P.n_aug ? fwd_units(P.aug[li], m_tiles) : 0;
+        for (int u = warp; u < u0 + u1; u += kWarps) {
+            if (u < u0) fwd_run(P.rate[li], Wp, smem, P.TBP, m_tiles, u, lane);
+            else fwd_run(P.aug[li], Wp, smem, P.TBP, m_tiles, u - u0, lane);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ int dw_units(const LayerP& Lp) {
+    const int mt = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
+    const int nt = (Lp.n_out_p + 4 * Lp.tn_dw - 1) / (4 * Lp.tn_dw);
+    return mt * nt;
+}
+__device__ __forceinline__ void dw_run(const LayerP& Lp, const float* smem, float* G, int TB, int TBP, int u, int lane) {
+    const int mtiles = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
+    const int mt = u % mtiles, nt = u / mtiles;
+    if (Lp.tm_dw == 4 && Lp.tn_dw == 4) dw_unit<4, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
+    else if (Lp.tm_dw == 1 && Lp.tn_dw == 4) dw_unit<1, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
+    else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_unit<4, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
+    else dw_unit<1, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
+}
+__device__ __forceinline__ int bwd_units(const LayerP& Lp, int m_tiles) {
+    return m_tiles * ((Lp.n_in_p + 4 * Lp.tn_bwd - 1) / (4 * Lp.tn_bwd));
+}
+__device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, const float* Wp, float* smem, int TBP,
+                                        int gx_off, int m_tiles, int u, int lane) {
+    const int mt = u % m_tiles, nt = u / m_tiles;
+    if (Lp.tn_bwd == 8) bwd_unit<8>(Lp, prev, Wp, smem, TBP, gx_off, mt, nt, lane);
+    else bwd_unit<4>(Lp, prev, Wp, smem, TBP, gx_off, mt, nt, lane);
+}
+
+// Backward through all layers of both nets, depth counted from the heads in
+// lockstep.  Pre: the head ACT rows hold dL/d(head output) (written by the caller),
+// every other ACT row still holds the forward activation, all synced.
+// GX rows pre-loaded with the direct dL/du.  Post: GX += W0^T delta0 of both nets; G accumulated.
+__device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float* Wp, float* smem, float* G, int warp,
+                                                    int lane) {
+    const int m_tiles = P.TB / 32;
+    const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+    for (int s = 0; s < nl; ++s) {
+        const int lr = P.n_rate - 1 - s, la = P.n_aug - 1 - s;
+        const LayerP* Lr = lr >= 0 ? &P.rate[lr] : nullptr;
+        const LayerP* La = la >= 0 ? &P.aug[la] : nullptr;
+        // ---- phase A: weight and bias gradients of this depth
+        {
+            const int w0 = Lr ? dw_units(*Lr) : 0;
+            const int w1 = La ? dw_units(*La) : 0;
+            const int b0 = Lr ? (Lr->n_out + 7) / 8 : 0;
+            const int b1 = La ? (La->n_out + 7) / 8 : 0;
+            const int total = w0 + w1 + b0 + b1;
+            for (int u = warp; u < total; u += kWarps) {
+                if (u < w0) dw_run(*Lr, smem, G, P.TB, P.TBP, u, lane);
+                else if (u < w0 + w1) dw_run(*La, smem, G, P.TB, P.TBP, u - w0, lane);
+                else if (u < w0 + w1 + b0) db_unit(*Lr, smem, G, P.TB, P.TBP, (u - w0 - w1) * 8, lane);
+                else db_unit(*La, smem, G, P.TB, P.TBP, (u - w0 - w1 - b0) * 8, lane);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: cotangent of this depth's inputs (in place over the previous ACT rows;
+        //      layer 0 accumulates into GX, so two layer-0 jobs must not share a phase)
+        {
+            const int u0 = Lr ? bwd_units(*Lr, m_tiles) : 0;
+            const int u1 = La ? bwd_units(*La, m_tiles) : 0;
+            const bool split = (lr == 0 && la == 0);
+            for (int u = warp; u < u0 + (split ? 0 : u1); u += kWarps) {
+                if (u < u0) bwd_run(*Lr, lr > 0 ? &P.rate[lr - 1] : nullptr, Wp, smem, P.TBP, P.off_GX, m_tiles, u, lane);
+                else bwd_run(*La, la > 0 ? &P.aug[la - 1] : nullptr, Wp, smem, P.TBP, P.off_GX, m_tiles, u - u0, lane);
+            }
+            if (split) {
+                __syncthreads();
+                for (int u = warp; u < u1; u += kWarps)
+                    bwd_run(*La, nullptr, Wp, smem, P.TBP, P.off_GX, m_tiles, u, lane);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// element-wise RHS tail for one (region r, trajectory b): SIR terms + correction + clamp
+// (/root/reference/lib/models.py:130-146, 231-251).  Mirrors the reference's operation
+// order with explicitly un-fused multiplies/adds.
+// ----------------------------------------------------------------------------------
+struct SideAcc {
+    double sb, sg, sb2, sg2, sf2;
+    long long rows;
+    __device__ __forceinline__ void clear() { sb = sg = sb2 = sg2 = sf2 = 0.0; rows = 0; }
+};
+
+__device__ __forceinline__ void rhs_tail(const ModelP& P, const float* __restrict__ smem, const int r, const int b,
+                                         const bool valid, SideAcc& side, float (&f)[3]) {
+    const int TBP = P.TBP;
+    const float* X = smem + P.off_X + (r * P.L) * TBP + b;
+    const float x0 = X[0], x1 = X[TBP], x2 = X[2 * TBP];
+    f[0] = f[1] = f[2] = 0.f;
+    if (P.n_rate > 0) {
+        const float* O = smem + P.rate[P.n_rate - 1].act_off + (2 * r) * TBP + b;
+        const float beta = fabsf(O[0]), gamma = fabsf(O[TBP]);
+        const float plus_i = __fmul_rn(__fmul_rn(beta, x0), x1);   // (beta*S)*I   models.py:139
+        const float minus_i = __fmul_rn(gamma, x1);                // gamma*I      models.py:140
+        f[0] = -plus_i;
+        f[1] = __fsub_rn(plus_i, minus_i);
+        f[2] = minus_i;
+        if (valid) {
+            side.sb += beta; side.sg += gamma;
+            side.sb2 += (double)beta * beta; side.sg2 += (double)gamma * gamma;
+        }
+    }
+    if (P.n_aug > 0) {
+        const float* FA = smem + P.aug[P.n_aug - 1].act_off + (3 * r) * TBP + b;
+        const float a0 = FA[0], a1 = FA[TBP], a2 = FA[2 * TBP];
+        if (P.n_rate > 0) {                                         // Fp + Fa_w * Fa  models.py:249
+            f[0] = __fadd_rn(f[0], __fmul_rn(P.fa_w, a0));
+            f[1] = __fadd_rn(f[1], __fmul_rn(P.fa_w, a1));
+            f[2] = __fadd_rn(f[2], __fmul_rn(P.fa_w, a2));
+        } else {                                                    // Fa alone: no Fa_w  models.py:184
+            f[0] = a0; f[1] = a1; f[2] = a2;
+        }
+        if (valid) side.sf2 += (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2;
+    }
+    if (valid) side.rows += 1;
+    if (x0 > 2.f || x0 < -1.f) f[0] = 0.f;                          // res[mask] = 0  models.py:145
+    if (x1 > 2.f || x1 < -1.f) f[1] = 0.f;
+    if (x2 > 2.f || x2 < -1.f) f[2] = 0.f;
+}
+
+// Vector-Jacobian product of the tail for one (r, b): given g = dL/df (3 comps) writes
+// dL/d(head outputs) in place over the head ACT rows and returns the direct dL/dx.
+// gs = dL/d(side sums).
+__device__ __forceinline__ void rhs_tail_vjp(const ModelP& P, float* __restrict__ smem, const int r, const int b,
+                                             const bool valid, const float (&gs)[5], float g0, float g1, float g2,
+                                             float (&xb)[3]) {
+    const int TBP = P.TBP;
+    const float* X = smem + P.off_X + (r * P.L) * TBP + b;
+    const float x0 = X[0], x1 = X[TBP], x2 = X[2 * TBP];
+    if (x0 > 2.f || x0 < -1.f) g0 = 0.f;
+    if (x1 > 2.f || x1 < -1.f) g1 = 0.f;
+    if (x2 > 2.f || x2 < -1.f) g2 = 0.f;
+    xb[0] = xb[1] = xb[2] = 0.f;
+    const float vm = valid ? 1.f : 0.f;
+    if (P.n_rate > 0) {
+        float* O = smem + P.rate[P.n_rate - 1].act_off + (2 * r) * TBP + b;
+        const float o0 = O[0], o1 = O[TBP];
+        const float beta = fabsf(o0), gamma = fabsf(o1);
+        const float gp = g1 - g0;          // cotangent of plusI
+        const float gm = g2 - g1;          // cotangent of minusI
+        float dbeta = gp * x0 * x1 + vm * (gs[0] + 2.f * gs[2] * beta);
+        float dgamma = gm * x1 + vm * (gs[1] + 2.f * gs[3] * gamma);
+        O[0] = (o0 > 0.f ? dbeta : (o0 < 0.f ? -dbeta : 0.f));      // d|o| = sign(o), sign(0) = 0
+        O[TBP] = (o1 > 0.f ? dgamma : (o1 < 0.f ? -dgamma : 0.f));
+        xb[0] = gp * beta * x1;
+        xb[1] = gp * beta * x0 + gm * gamma;
+    }
+    if (P.n_aug > 0) {
+        float* FA = smem + P.aug[P.n_aug - 1].act_off + (3 * r) * TBP + b;
+        const float w = P.n_rate > 0 ? P.fa_w : 1.0f;
+        const float c = vm * 2.f * gs[4];
+        FA[0] = w * g0 + c * FA[0];
+        FA[TBP] = w * g1 + c * FA[TBP];
+        FA[2 * TBP] = w * g2 + c * FA[2 * TBP];
+    }
+}
+
+// Block-wide reduction of the side-channel accumulators into out[0..7] (fp64).
+__device__ __forceinline__ void side_block_reduce(const SideAcc& s, double n_evals, double* scratch /*smem [kWarps*8]*/,
+                                                  double* out) {
+    double v[6] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int w = 0; w < kWarps; ++w) t += scratch[w * 8 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 6) out[6] = n_evals;
+    if (threadIdx.x == 7) out[7] = 0.0;
+    __syncthreads();
+}
+
+}  // namespace ude

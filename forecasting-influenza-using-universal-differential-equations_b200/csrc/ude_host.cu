@@ -1,0 +1,489 @@
+// ude_host.cu — C-ABI entry points (include/ude_b200.h) and host-side planning.
+//
+// Everything here is plain C++/CUDA runtime: no torch, no allocation of persistent
+// memory, no exceptions across the boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/ude_b200.h"
+#include "ude_dopri5.cuh"
+#include "ude_rk4.cuh"
+
+namespace ude {
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+    return UDE_ERR_CUDA;
+}
+#define UDE_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+static inline int round4(int x) { return (x + 3) & ~3; }
+static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------
+// descriptor -> ModelP (layer tables, packed layout).  No GPU needed.
+// ---------------------------------------------------------------------------------
+static int check_desc(const UdeDesc* d) {
+    if (!d) return UDE_ERR_INVALID;
+    if (d->kind < UDE_KIND_FP || d->kind > UDE_KIND_FAFP) return UDE_ERR_INVALID;
+    if (d->n_regions < 1 || d->latent_dim < 3) return UDE_ERR_INVALID;
+    const bool rate = d->kind != UDE_KIND_FA, aug = d->kind != UDE_KIND_FP;
+    if (rate) {
+        if (d->n_rate_layers < 2 || d->n_rate_layers > UDE_MAX_LAYERS) return UDE_ERR_INVALID;
+        if (d->rate_sizes[d->n_rate_layers - 1] != 2 * d->n_regions) return UDE_ERR_INVALID;
+        for (int i = 0; i < d->n_rate_layers; ++i)
+            if (d->rate_sizes[i] < 1) return UDE_ERR_INVALID;
+    } else if (d->n_rate_layers != 0) return UDE_ERR_INVALID;
+    if (aug) {
+        if (d->n_aug_layers < 2 || d->n_aug_layers > UDE_MAX_LAYERS) return UDE_ERR_INVALID;
+        if (d->aug_sizes[d->n_aug_layers - 1] != 3 * d->n_regions) return UDE_ERR_INVALID;
+        for (int i = 0; i < d->n_aug_layers; ++i)
+            if (d->aug_sizes[i] < 1) return UDE_ERR_INVALID;
+    } else if (d->n_aug_layers != 0) return UDE_ERR_INVALID;
+    if (d->n_groups < 1 || d->batch < 1 || d->batch % d->n_groups != 0) return UDE_ERR_INVALID;
+    return UDE_OK;
+}
+
+static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int& th, int& pk) {
+    int n_in = P.D;
+    for (int i = 0; i < n; ++i) {
+        LayerP& Lp = Ls[i];
+        memset(&Lp, 0, sizeof(Lp));
+        Lp.n_in = n_in;
+        Lp.n_out = sizes[i];
+        Lp.n_in_p = round4(Lp.n_in);
+        Lp.n_out_p = round4(Lp.n_out);
+        Lp.ldw = Lp.n_in_p;
+        if (Lp.ldw % 32 == 0) Lp.ldw += 4;     // keep the 4 rows a warp reads at once in distinct banks
+        Lp.th_w = th;
+        th += Lp.n_in * Lp.n_out;
+        Lp.th_b = th;
+        th += Lp.n_out;
+        Lp.w_off = pk;
+        pk += Lp.n_out_p * Lp.ldw;
+        Lp.b_off = pk;
+        pk += Lp.n_out_p;
+        Lp.elu = (i <= n - 3) ? 1 : 0;         // Linear,[ELU,Linear]*,Linear: no ELU before the head
+        n_in = Lp.n_out;
+    }
+}
+
+static void base_model(const UdeDesc* d, ModelP& P) {
+    memset(&P, 0, sizeof(P));
+    P.kind = d->kind;
+    P.R = d->n_regions;
+    P.L = d->latent_dim;
+    P.D = P.R * P.L;
+    P.D_p = round4(P.D);
+    P.Dn = 3 * P.R;
+    P.Dn_p = round4(P.Dn);
+    P.n_rate = d->n_rate_layers;
+    P.n_aug = d->n_aug_layers;
+    P.fa_w = d->fa_w;
+    int th = 0, pk = 0;
+    fill_layers(P, P.rate, P.n_rate, d->rate_sizes, th, pk);
+    fill_layers(P, P.aug, P.n_aug, d->aug_sizes, th, pk);
+    P.n_theta = th;
+    P.n_packed = pk + kPadTail;
+}
+
+// Shared-memory plan for a given tile size; returns the arena size in floats.
+static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, bool bwd) {
+    P.TB = TB;
+    P.TBP = TB + 4;
+    P.w_in_smem = w_smem;
+    P.g_in_smem = g_smem;
+    P.n_state = n_state;
+    int off = 0;
+    P.off_W = off;
+    if (w_smem) off += P.n_packed;
+    P.off_G = off;
+    if (g_smem) off += P.n_packed;
+    P.off_X = off;
+    off += P.D_p * P.TBP;
+    for (int net = 0; net < 2; ++net) {
+        LayerP* Ls = net == 0 ? P.rate : P.aug;
+        const int n = net == 0 ? P.n_rate : P.n_aug;
+        for (int i = 0; i < n; ++i) {
+            Ls[i].in_off = i == 0 ? P.off_X : Ls[i - 1].act_off;
+            Ls[i].act_off = off;
+            off += Ls[i].n_out_p * P.TBP;
+        }
+    }
+    P.off_S = off;
+    off += n_state * P.Dn_p * P.TBP;
+    P.off_GX = off;
+    P.off_CB = off;
+    if (bwd) {
+        off += P.D_p * P.TBP;
+        P.off_CB = off;
+        off += P.D_p * P.TBP;
+    }
+    off += 8;    // slack
+    P.smem_floats = off;
+    // tile shapes: aim at >= kWarps units per phase (both nets run in the same phase)
+    const int nets = (P.n_rate > 0) + (P.n_aug > 0);
+    const int want = kWarps / nets;
+    const int m_tiles = TB / 32;
+    for (int net = 0; net < 2; ++net) {
+        LayerP* Ls = net == 0 ? P.rate : P.aug;
+        const int n = net == 0 ? P.n_rate : P.n_aug;
+        for (int i = 0; i < n; ++i) {
+            LayerP& Lp = Ls[i];
+            if (Lp.n_out_p <= 4) Lp.tn_fwd = 1;
+            else Lp.tn_fwd = (m_tiles * ((Lp.n_out_p + 31) / 32) >= want) ? 8 : 4;
+            Lp.tn_bwd = (m_tiles * ((Lp.n_in_p + 31) / 32) >= want) ? 8 : 4;
+            Lp.tm_dw = Lp.n_in_p > 8 ? 4 : 1;
+            Lp.tn_dw = Lp.n_out_p > 4 ? 4 : 1;
+        }
+    }
+    return off;
+}
+
+static const int kSmemBudgetBytes = 226 * 1024;     // 227 KB per CTA minus the static part
+
+struct DeviceInfo {
+    int ok = 0;
+    int n_sm = 0;
+    int cc_major = 0;
+    int max_smem_optin = 0;
+};
+static DeviceInfo& device_info() {
+    static DeviceInfo info;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+        info.n_sm = prop.multiProcessorCount;
+        info.cc_major = prop.major;
+        info.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        info.ok = 1;
+    });
+    return info;
+}
+
+// Pick (TB, weights in smem, accumulators in smem) for a direction.
+static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, bool bwd) {
+    base_model(d, P);
+    const int budget = kSmemBudgetBytes / 4;
+    const long long tiles64 = (d->batch + 63) / 64;
+    const DeviceInfo& di = device_info();
+    const int n_sm = di.ok ? di.n_sm : 148;
+    // small batches: smaller tiles spread over more SMs
+    const int tb_order[2] = {tiles64 >= n_sm ? 64 : 32, tiles64 >= n_sm ? 32 : 64};
+    struct Cand { int w, g; };
+    const Cand cands_bwd[3] = {{1, 1}, {1, 0}, {0, 0}};
+    const Cand cands_fwd[2] = {{1, 0}, {0, 0}};
+    const Cand* cands = bwd ? cands_bwd : cands_fwd;
+    const int nc = bwd ? 3 : 2;
+    for (int c = 0; c < nc; ++c)
+        for (int t = 0; t < 2; ++t) {
+            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, n_state, bwd) <= budget) return UDE_OK;
+        }
+    return UDE_ERR_UNSUPPORTED;
+}
+
+struct Workspace {
+    float* wpacked;
+    double* side_partial;
+    float* slabs;
+    long long bytes;
+};
+static Workspace carve_workspace(void* base, const ModelP& P, int n_ctas) {
+    Workspace w;
+    long long off = 0;
+    w.wpacked = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)P.n_packed * 4, 256);
+    w.side_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * 8 * 8, 256);
+    w.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * P.n_packed * 4, 256);
+    w.bytes = off;
+    return w;
+}
+
+static int grid_size(const ModelP& P, long long B) {
+    const DeviceInfo& di = device_info();
+    const long long tiles = (B + P.TB - 1) / P.TB;
+    const int n_sm = di.ok ? di.n_sm : 148;
+    return (int)(tiles < n_sm ? tiles : n_sm);
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+    UDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return UDE_OK;
+}
+
+static int n_state_for(int method, bool bwd) {
+    if (method == UDE_METHOD_RK4) return bwd ? B_NSTATE : F_NSTATE;
+    return bwd ? DB_NSTATE : DF_NSTATE;
+}
+
+}  // namespace ude
+
+using namespace ude;
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int ude_abi_version(void) { return UDE_ABI_VERSION; }
+
+const char* ude_strerror(int status) {
+    switch (status) {
+        case UDE_OK: return "ok";
+        case UDE_ERR_INVALID: return "invalid argument or descriptor";
+        case UDE_ERR_UNSUPPORTED: return "configuration not supported by the fused kernels";
+        case UDE_ERR_WORKSPACE: return "workspace or tape too small (see ude_plan)";
+        case UDE_ERR_CUDA: return "CUDA runtime error (see ude_last_cuda_error)";
+        case UDE_ERR_NO_DEVICE: return "no sm_100 CUDA device visible";
+        case UDE_ERR_GRID: return "time points must be strictly increasing and step_size positive";
+        case UDE_ERR_CAPACITY: return "caller-provided table too small";
+        default: return "unknown status";
+    }
+}
+
+const char* ude_last_cuda_error(void) { return g_cuda_err; }
+
+int64_t ude_theta_size(const UdeDesc* desc) {
+    if (check_desc(desc) != UDE_OK) return UDE_ERR_INVALID;
+    ModelP P;
+    base_model(desc, P);
+    return P.n_theta;
+}
+
+int64_t ude_macs_per_eval(const UdeDesc* desc) {
+    if (check_desc(desc) != UDE_OK) return UDE_ERR_INVALID;
+    ModelP P;
+    base_model(desc, P);
+    int64_t macs = 0;
+    for (int i = 0; i < P.n_rate; ++i) macs += (int64_t)P.rate[i].n_in * P.rate[i].n_out;
+    for (int i = 0; i < P.n_aug; ++i) macs += (int64_t)P.aug[i].n_in * P.aug[i].n_out;
+    return macs;
+}
+
+int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
+    int st = check_desc(desc);
+    if (st != UDE_OK || !plan || n_steps < 0) return UDE_ERR_INVALID;
+    if (method != UDE_METHOD_RK4 && method != UDE_METHOD_DOPRI5) return UDE_ERR_INVALID;
+    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    ModelP Pf, Pb;      // pure host arithmetic: works without a GPU (148 SMs assumed then)
+    if ((st = choose_plan(desc, Pf, n_state_for(method, false), false)) != UDE_OK) return st;
+    if ((st = choose_plan(desc, Pb, n_state_for(method, true), true)) != UDE_OK) return st;
+    memset(plan, 0, sizeof(*plan));
+    plan->n_theta = Pf.n_theta;
+    const int ctas_f = grid_size(Pf, desc->batch), ctas_b = grid_size(Pb, desc->batch);
+    const int n_ctas = ctas_f > ctas_b ? ctas_f : ctas_b;
+    Workspace w = carve_workspace(nullptr, Pf, n_ctas);
+    plan->workspace_bytes = w.bytes;
+    const long long stages = method == UDE_METHOD_RK4 ? 4 : kDopriStages;
+    plan->tape_bytes = align_up((long long)n_steps * stages * Pf.Dn * desc->batch * 4, 256);
+    if (method == UDE_METHOD_DOPRI5) plan->tape_bytes += align_up((long long)n_steps * desc->batch * 8 * 2, 256);
+    plan->tile_traj = Pb.TB;
+    plan->n_ctas = n_ctas;
+    plan->smem_bytes_fwd = Pf.smem_floats * 4;
+    plan->smem_bytes_bwd = Pb.smem_floats * 4;
+    plan->weights_in_smem = Pb.w_in_smem;
+    return UDE_OK;
+}
+
+int ude_rk4_grid(const float* t, int32_t n_t, float step_size, int32_t use_step_size, int32_t cap_steps, float* dt,
+                 int32_t* n_steps, int32_t* out_step, int32_t* out_kind, float* out_w) {
+    if (!t || n_t < 2 || !dt || !n_steps || !out_step || !out_kind || !out_w) return UDE_ERR_INVALID;
+    for (int i = 1; i < n_t; ++i)
+        if (!(t[i] > t[i - 1])) return UDE_ERR_GRID;
+    // grid points are generated on the fly: g(i) = fl32(fl32(i * h) + t0), last one overwritten by t[-1]
+    long long niters;
+    volatile float h = step_size;
+    if (use_step_size) {
+        if (!(step_size > 0.f)) return UDE_ERR_GRID;
+        volatile float span = t[n_t - 1] - t[0];
+        volatile float q = span / h;
+        volatile float q1 = q + 1.0f;
+        const float c = ceilf(q1);
+        if (!(c >= 2.f) || c > 1e9f) return UDE_ERR_GRID;
+        niters = (long long)c;
+    } else {
+        niters = n_t;
+    }
+    const long long ns = niters - 1;
+    if (ns > cap_steps) {
+        *n_steps = (int32_t)ns;
+        return UDE_ERR_CAPACITY;
+    }
+    auto grid_at = [&](long long i) -> float {
+        if (i == niters - 1) return t[n_t - 1];
+        if (!use_step_size) return t[i];
+        volatile float fi = (float)i;       // arange(0, niters, dtype=float32)
+        volatile float p = fi * h;          // * step_size
+        volatile float g = p + t[0];        // + start_time
+        return g;
+    };
+    if (grid_at(0) != t[0]) return UDE_ERR_GRID;
+    out_step[0] = -1;
+    out_kind[0] = 0;
+    out_w[0] = 0.f;
+    int j = 1;
+    for (long long n = 0; n < ns; ++n) {
+        const float t0 = grid_at(n), t1 = grid_at(n + 1);
+        volatile float d = t1 - t0;
+        dt[n] = d;
+        while (j < n_t && t1 >= t[j]) {
+            out_step[j] = (int32_t)n;
+            if (t[j] == t0) {
+                out_kind[j] = 0;
+                out_w[j] = 0.f;
+            } else if (t[j] == t1) {
+                out_kind[j] = 1;
+                out_w[j] = 1.f;
+            } else {
+                volatile float num = t[j] - t0;
+                volatile float den = t1 - t0;
+                volatile float s = num / den;
+                out_kind[j] = 2;
+                out_w[j] = s;
+            }
+            ++j;
+        }
+    }
+    if (j != n_t) return UDE_ERR_GRID;
+    *n_steps = (int32_t)ns;
+    return UDE_OK;
+}
+
+static int launch_pack(const ModelP& P, const float* theta, float* wpacked, cudaStream_t s) {
+    pack_theta_kernel<<<P.n_rate + P.n_aug + 1, 256, 0, s>>>(P, theta, wpacked);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, int32_t n_steps, const float* dt,
+                    int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w, float* y_out,
+                    float* tape, double* side, void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_desc(desc);
+    if (st != UDE_OK) return st;
+    if (!theta || !y0 || !dt || !out_step || !out_kind || !out_w || !y_out || !side || !workspace) return UDE_ERR_INVALID;
+    if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
+    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    ModelP P;
+    if ((st = choose_plan(desc, P, F_NSTATE, false)) != UDE_OK) return st;
+    const int n_ctas = grid_size(P, desc->batch);
+    Workspace w = carve_workspace(workspace, P, n_ctas);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
+    Rk4FwdArgs a;
+    a.wpacked = w.wpacked;
+    a.y0 = y0;
+    a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+    a.y_out = y_out;
+    a.tape = tape;
+    a.side_partial = w.side_partial;
+    a.B = desc->batch;
+    const int smem = P.smem_floats * 4;
+    if (P.w_in_smem) {
+        if ((st = set_smem(rk4_fwd_kernel<true>, smem)) != UDE_OK) return st;
+        rk4_fwd_kernel<true><<<n_ctas, kThreads, smem, s>>>(P, a);
+    } else {
+        if ((st = set_smem(rk4_fwd_kernel<false>, smem)) != UDE_OK) return st;
+        rk4_fwd_kernel<false><<<n_ctas, kThreads, smem, s>>>(P, a);
+    }
+    UDE_CUDA(cudaGetLastError());
+    reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, int32_t n_steps, const float* dt,
+                     int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                     const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_theta,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_desc(desc);
+    if (st != UDE_OK) return st;
+    if (!theta || !y0 || !dt || !out_step || !out_kind || !out_w || !tape || !g_out || !g_y0 || !g_theta || !workspace)
+        return UDE_ERR_INVALID;
+    if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
+    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    ModelP P;
+    if ((st = choose_plan(desc, P, B_NSTATE, true)) != UDE_OK) return st;
+    const int n_ctas = grid_size(P, desc->batch);
+    Workspace w = carve_workspace(workspace, P, n_ctas);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
+    Rk4BwdArgs a;
+    a.wpacked = w.wpacked;
+    a.y0 = y0;
+    a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+    a.tape = tape;
+    a.g_out = g_out;
+    a.g_side = g_side;
+    a.g_y0 = g_y0;
+    a.slabs = w.slabs;
+    a.B = desc->batch;
+    const int smem = P.smem_floats * 4;
+#define UDE_LAUNCH_BWD(W, G)                                                              \
+    do {                                                                                  \
+        if ((st = set_smem(rk4_bwd_kernel<W, G>, smem)) != UDE_OK) return st;             \
+        rk4_bwd_kernel<W, G><<<n_ctas, kThreads, smem, s>>>(P, a);                        \
+    } while (0)
+    if (P.w_in_smem && P.g_in_smem) UDE_LAUNCH_BWD(true, true);
+    else if (P.w_in_smem) UDE_LAUNCH_BWD(true, false);
+    else UDE_LAUNCH_BWD(false, false);
+#undef UDE_LAUNCH_BWD
+    UDE_CUDA(cudaGetLastError());
+    reduce_dtheta_kernel<<<(P.n_theta + 255) / 256, 256, 0, s>>>(P, w.slabs, n_ctas, g_theta);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int ude_measure_ffma_tflops(double* tflops, void* stream) {
+    if (!tflops) return UDE_ERR_INVALID;
+    const DeviceInfo& di = device_info();
+    if (!di.ok) return UDE_ERR_NO_DEVICE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    float* out = nullptr;
+    UDE_CUDA(cudaMalloc(&out, 4));
+    cudaEvent_t e0, e1;
+    UDE_CUDA(cudaEventCreate(&e0));
+    UDE_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = di.n_sm * 8, threads = 256;
+    ffma_peak_kernel<<<blocks, threads, 0, s>>>(out, 256, 1.0f);     // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        UDE_CUDA(cudaEventRecord(e0, s));
+        ffma_peak_kernel<<<blocks, threads, 0, s>>>(out, iters, 1.0f);
+        UDE_CUDA(cudaEventRecord(e1, s));
+        UDE_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        UDE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return UDE_OK;
+}
+
+}  // extern "C"
+
+#include "ude_dopri5_host.inl"

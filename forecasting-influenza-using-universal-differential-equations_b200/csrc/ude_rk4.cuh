@@ -1,0 +1,463 @@
+// ude_rk4.cuh — fused fixed-step RK4 (torchdiffeq 'rk4' = 3/8 rule) forward and
+// discrete-adjoint kernels.  One persistent CTA per SM walks over tiles of TB
+// trajectories; a tile runs the WHOLE time grid before the CTA moves on.
+//
+// Replaces the Python loop of torchdiffeq FixedGridODESolver.integrate +
+// rk4_alt_step_func that the reference drives from /root/reference/lib/VAE.py:137,
+// and the autograd replay behind /root/reference/lib/VAE.py:203.
+#pragma once
+#include "ude_engine.cuh"
+
+namespace ude {
+
+struct GridTables {
+    int n_steps;
+    const float* dt;        // [n_steps]
+    int n_out;
+    const int* out_step;    // [n_out]  (-1 for output 0)
+    const int* out_kind;    // [n_out]  0 copy y_n, 1 copy y_{n+1}, 2 lerp
+    const float* out_w;     // [n_out]
+};
+
+struct Rk4FwdArgs {
+    const float* wpacked;   // [n_packed]
+    const float* y0;        // [B,R,L]
+    GridTables g;
+    float* y_out;           // [n_out,B,R,L]
+    float* tape;            // [n_steps,4,Dn,B] or null
+    double* side_partial;   // [gridDim.x, 8]
+    long long B;
+};
+
+struct Rk4BwdArgs {
+    const float* wpacked;
+    const float* y0;
+    GridTables g;
+    const float* tape;
+    const float* g_out;     // [n_out,B,R,L]
+    const float* g_side;    // [5] or null
+    float* g_y0;            // [B,R,L]
+    float* slabs;           // [gridDim.x, n_packed] per-CTA dtheta accumulators
+    long long B;
+};
+
+// ---- state buffer indices ---------------------------------------------------------
+enum { F_Y = 0, F_K1 = 1, F_K2 = 2, F_K3 = 3, F_NSTATE = 4 };
+enum { B_LAM = 0, B_KB1 = 1, B_KB2 = 2, B_KB3 = 3, B_KB4 = 4, B_NSTATE = 5 };
+
+__device__ __forceinline__ void copy_model_to_smem(ModelP* dst, const ModelP& src) {
+    const int* s = reinterpret_cast<const int*>(&src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelP) / sizeof(int)); i += kThreads) d[i] = s[i];
+}
+
+// Load the y0 tile into X (all R*L rows); invalid columns get zeros.
+__device__ __forceinline__ void load_y0_tile(const ModelP& P, float* smem, const float* __restrict__ y0, long long b0,
+                                             int nvalid) {
+    const int TB = P.TB, TBP = P.TBP, L = P.L;
+    for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+        const int r = idx / TB, b = idx - r * TB;
+        float* X = smem + P.off_X + (r * L) * TBP + b;
+        if (b < nvalid) {
+            const float* src = y0 + ((b0 + b) * P.R + r) * (long long)L;
+            if ((L & 3) == 0) {
+                for (int l = 0; l < L; l += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + l));
+                    X[(l + 0) * TBP] = v.x; X[(l + 1) * TBP] = v.y; X[(l + 2) * TBP] = v.z; X[(l + 3) * TBP] = v.w;
+                }
+            } else {
+                for (int l = 0; l < L; ++l) X[l * TBP] = __ldg(src + l);
+            }
+        } else {
+            for (int l = 0; l < L; ++l) X[l * TBP] = 0.f;
+        }
+    }
+}
+
+// Store one output row (r, b): dynamic comps from v[], constants from X.
+__device__ __forceinline__ void store_out_row(const ModelP& P, const float* smem, float* __restrict__ dst, int r, int b,
+                                              const float (&v)[3]) {
+    const int TBP = P.TBP, L = P.L;
+    const float* X = smem + P.off_X + (r * L) * TBP + b;
+    if ((L & 3) == 0) {
+        st4(dst, make_float4(v[0], v[1], v[2], X[3 * TBP]));
+        for (int l = 4; l < L; l += 4)
+            st4(dst + l, make_float4(X[l * TBP], X[(l + 1) * TBP], X[(l + 2) * TBP], X[(l + 3) * TBP]));
+    } else {
+        dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
+        for (int l = 3; l < L; ++l) dst[l] = X[l * TBP];
+    }
+}
+
+// ===================================================================================
+// forward
+// ===================================================================================
+template <bool SMEM_W>
+__global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_constant__ ModelP Pg, const Rk4FwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ ModelP P;
+    __shared__ __align__(8) uint64_t wbar;
+    __shared__ double red[kWarps * 8];
+
+    copy_model_to_smem(&P, Pg);
+    if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn;
+    uint32_t wphase = 0;
+    const float* Wp = a.wpacked;
+    if (SMEM_W) {
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        Wp = smem + P.off_W;
+    }
+    // zero the padding rows of X once (they feed layer 0 with K = D_p)
+    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+
+    float* SY = smem + P.off_S + F_Y * P.Dn_p * TBP;
+    float* SK1 = smem + P.off_S + F_K1 * P.Dn_p * TBP;
+    float* SK2 = smem + P.off_S + F_K2 * P.Dn_p * TBP;
+    float* SK3 = smem + P.off_S + F_K3 * P.Dn_p * TBP;
+
+    SideAcc side;
+    side.clear();
+    const double n_evals = 4.0 * a.g.n_steps;      // RHS evaluations per trajectory
+    const long long B = a.B;
+    const long long n_tiles = (B + TB - 1) / TB;
+    const long long tape_stage = (long long)Dn * B;           // floats per (step, stage)
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long b0 = tile * TB;
+        const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
+        __syncthreads();                                       // previous tile done with X
+        load_y0_tile(P, smem, a.y0, b0, nvalid);
+        __syncthreads();
+        // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
+        for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+            const int r = idx / TB, b = idx - r * TB;
+            const float* X = smem + P.off_X + (r * L) * TBP + b;
+            float v[3] = {X[0], X[TBP], X[2 * TBP]};
+            SY[(3 * r + 0) * TBP + b] = v[0];
+            SY[(3 * r + 1) * TBP + b] = v[1];
+            SY[(3 * r + 2) * TBP + b] = v[2];
+            if (b < nvalid) store_out_row(P, smem, a.y_out + ((b0 + b) * P.R + r) * (long long)L, r, b, v);
+        }
+        // (each thread only re-reads rows it wrote itself below, no sync needed here)
+        int j = 1;
+        for (int n = 0; n < a.g.n_steps; ++n) {
+            const float dt = __ldg(a.g.dt + n);
+            int j_next = j;
+#pragma unroll 1
+            for (int stage = 0; stage < 4; ++stage) {
+                rhs_forward_layers(P, Wp, smem, warp, lane);
+                for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                    const int r = idx / TB, b = idx - r * TB;
+                    const bool valid = b < nvalid;
+                    float f[3];
+                    rhs_tail(P, smem, r, b, valid, side, f);
+                    float* X = smem + P.off_X + (r * L) * TBP + b;
+                    float* tp = a.tape ? a.tape + ((long long)(n * 4 + stage) * tape_stage + (long long)(3 * r) * B + b0 + b) : nullptr;
+                    float xn[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int row = (3 * r + c) * TBP + b;
+                        const float y = SY[row];
+                        if (tp && valid) tp[(long long)c * B] = X[c * TBP];     // stage input x_{stage+1}
+                        if (stage == 0) {
+                            SK1[row] = f[c];
+                            xn[c] = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f[c]), 1.0f / 3.0f));
+                        } else if (stage == 1) {
+                            SK2[row] = f[c];
+                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f[c], __fmul_rn(SK1[row], 1.0f / 3.0f))));
+                        } else if (stage == 2) {
+                            SK3[row] = f[c];
+                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(SK1[row], SK2[row]), f[c])));
+                        } else {
+                            const float s = __fadd_rn(__fadd_rn(SK1[row], __fmul_rn(3.0f, __fadd_rn(SK2[row], SK3[row]))), f[c]);
+                            xn[c] = __fadd_rn(y, __fmul_rn(__fmul_rn(s, dt), 0.125f));
+                        }
+                    }
+                    if (stage == 3) {
+                        // outputs that fall into (t_n, t_{n+1}]  (FixedGridODESolver.integrate)
+                        int jj = j;
+                        while (jj < a.g.n_out && __ldg(a.g.out_step + jj) == n) {
+                            if (valid) {
+                                const int kind = __ldg(a.g.out_kind + jj);
+                                float v[3];
+                                if (kind == 1) {
+                                    v[0] = xn[0]; v[1] = xn[1]; v[2] = xn[2];
+                                } else {
+                                    const float w = __ldg(a.g.out_w + jj);
+#pragma unroll
+                                    for (int c = 0; c < 3; ++c) {
+                                        const float y = SY[(3 * r + c) * TBP + b];
+                                        v[c] = kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(xn[c], y)));
+                                    }
+                                }
+                                store_out_row(P, smem, a.y_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L, r, b, v);
+                            }
+                            ++jj;
+                        }
+                        j_next = jj;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = xn[c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) X[c * TBP] = xn[c];
+                }
+                if (stage == 3) {
+                    // threads with no (r,b) task still need the advanced output cursor
+                    int jj = j;
+                    while (jj < a.g.n_out && __ldg(a.g.out_step + jj) == n) ++jj;
+                    j_next = jj;
+                }
+                __syncthreads();
+            }
+            j = j_next;
+        }
+    }
+    side_block_reduce(side, n_evals, red, a.side_partial + (long long)blockIdx.x * 8);
+}
+
+// ===================================================================================
+// backward (discrete adjoint)
+// ===================================================================================
+template <bool SMEM_W, bool SMEM_G>
+__global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_constant__ ModelP Pg, const Rk4BwdArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ ModelP P;
+    __shared__ __align__(8) uint64_t wbar;
+
+    copy_model_to_smem(&P, Pg);
+    if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn;
+    uint32_t wphase = 0;
+    const float* Wp = a.wpacked;
+    if (SMEM_W) {
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        Wp = smem + P.off_W;
+    }
+    float* G = SMEM_G ? smem + P.off_G : a.slabs + (long long)blockIdx.x * P.n_packed;
+    for (int i = threadIdx.x; i < P.n_packed; i += kThreads) G[i] = 0.f;
+    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+
+    float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.g_side) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
+    }
+
+    const int SS = P.Dn_p * TBP;
+    float* LAM = smem + P.off_S + B_LAM * SS;
+    float* KB = smem + P.off_S + B_KB1 * SS;        // KB[s] = KB + s*SS, s = 0..3
+    float* GX = smem + P.off_GX;
+    float* CB = smem + P.off_CB;
+
+    const long long B = a.B;
+    const long long n_tiles = (B + TB - 1) / TB;
+    const long long tape_stage = (long long)Dn * B;
+    const int n_steps = a.g.n_steps;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long b0 = tile * TB;
+        const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
+        __syncthreads();
+        load_y0_tile(P, smem, a.y0, b0, nvalid);        // constants of X; dynamic rows reloaded per stage
+        for (int i = threadIdx.x; i < SS; i += kThreads) LAM[i] = 0.f;
+        for (int i = threadIdx.x; i < P.D_p * TBP; i += kThreads) { CB[i] = 0.f; GX[i] = 0.f; }
+        __syncthreads();
+
+        int j = a.g.n_out - 1;
+        for (int n = n_steps - 1; n >= 0; --n) {
+            const float dt = __ldg(a.g.dt + n);
+            // ---- outputs tied to step n feed lambda_{n+1} (and, for copies of y_n / lerps, lambda_n)
+            int j_next = j;
+            {
+                int jj = j;
+                while (jj >= 1 && __ldg(a.g.out_step + jj) == n) --jj;
+                j_next = jj;
+            }
+            for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                const int r = idx / TB, b = idx - r * TB;
+                const bool valid = b < nvalid;
+                float lam[3], pend[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) lam[c] = LAM[(3 * r + c) * TBP + b];
+                if (valid) {
+                    for (int jj = j; jj > j_next; --jj) {
+                        const int kind = __ldg(a.g.out_kind + jj);
+                        const float w = __ldg(a.g.out_w + jj);
+                        const float* gp = a.g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
+                        for (int l = 0; l < L; ++l) {
+                            const float g = __ldg(gp + l);
+                            if (l < 3) {
+                                if (kind == 1) lam[l] += g;
+                                else if (kind == 0) pend[l] += g;
+                                else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
+                            } else {
+                                CB[(r * L + l) * TBP + b] += g;
+                            }
+                        }
+                    }
+                }
+                const float c8 = dt * 0.125f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int row = (3 * r + c) * TBP + b;
+                    const float base = lam[c] * c8;
+                    KB[0 * SS + row] = base;
+                    KB[1 * SS + row] = 3.f * base;
+                    KB[2 * SS + row] = 3.f * base;
+                    KB[3 * SS + row] = base;
+                    LAM[row] = lam[c] + pend[c];    // becomes lambda_n once the four stage VJPs are added
+                    // stage input of stage 4
+                    float* X = smem + P.off_X + (r * L + c) * TBP + b;
+                    *X = valid ? __ldg(a.tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                }
+            }
+            j = j_next;
+            __syncthreads();
+#pragma unroll 1
+            for (int stage = 3; stage >= 0; --stage) {
+                rhs_forward_layers(P, Wp, smem, warp, lane);
+                // ---- tail VJP: cotangent KB[stage] -> head cotangents (in place) + direct dx
+                for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                    const int r = idx / TB, b = idx - r * TB;
+                    const int row = (3 * r) * TBP + b;
+                    float xb[3];
+                    rhs_tail_vjp(P, smem, r, b, b < nvalid, gs, KB[stage * SS + row], KB[stage * SS + row + TBP],
+                                 KB[stage * SS + row + 2 * TBP], xb);
+                    float* gx = GX + (r * L) * TBP + b;     // GX := direct term; the layer-0 deltas accumulate on top
+                    gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
+                    for (int l = 3; l < L; ++l) gx[l * TBP] = 0.f;
+                }
+                __syncthreads();
+                rhs_backward_layers(P, Wp, smem, G, warp, lane);
+                // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
+                for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                    const int r = idx / TB, b = idx - r * TB;
+                    const bool valid = b < nvalid;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int row = (3 * r + c) * TBP + b;
+                        const int xrow = (r * L + c) * TBP + b;
+                        const float xb = GX[xrow];
+                        const float u = xb * dt;
+                        if (stage == 3) {            // x4 = y + dt*((k1 - k2) + k3)
+                            KB[2 * SS + row] += u; KB[0 * SS + row] += u; KB[1 * SS + row] -= u;
+                        } else if (stage == 2) {     // x3 = y + dt*(k2 - k1/3)
+                            KB[1 * SS + row] += u; KB[0 * SS + row] -= u * (1.0f / 3.0f);
+                        } else if (stage == 1) {     // x2 = y + (dt*k1)/3
+                            KB[0 * SS + row] += (xb * (1.0f / 3.0f)) * dt;
+                        }
+                        LAM[row] += xb;
+                        // next stage input (stage-1), from the tape
+                        if (stage > 0)
+                            smem[P.off_X + xrow] = valid ? __ldg(a.tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                    }
+                    for (int l = 3; l < L; ++l) {
+                        const int xrow = (r * L + l) * TBP + b;
+                        CB[xrow] += GX[xrow];
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- output 0 (= y0 itself) and the final store of dL/dy0
+        for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+            const int r = idx / TB, b = idx - r * TB;
+            if (b < nvalid) {
+                const float* gp = a.g_out + ((b0 + b) * P.R + r) * (long long)L;
+                float* dst = a.g_y0 + ((b0 + b) * P.R + r) * (long long)L;
+                for (int l = 0; l < L; ++l) {
+                    const float g = __ldg(gp + l);
+                    const float acc = l < 3 ? LAM[(3 * r + l) * TBP + b] : CB[(r * L + l) * TBP + b];
+                    dst[l] = acc + g;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (SMEM_G) {
+        float* slab = a.slabs + (long long)blockIdx.x * P.n_packed;
+        for (int i = threadIdx.x; i < P.n_packed; i += kThreads) slab[i] = G[i];
+    }
+}
+
+// ===================================================================================
+// small utility kernels
+// ===================================================================================
+// theta (PyTorch layout) -> packed blob (padded rows, zero fill).  One block per layer.
+__global__ void pack_theta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ theta, float* __restrict__ packed) {
+    const int li = blockIdx.x;
+    if (li == P.n_rate + P.n_aug) {       // tail padding
+        for (int i = threadIdx.x; i < kPadTail; i += blockDim.x) packed[P.n_packed - kPadTail + i] = 0.f;
+        return;
+    }
+    const LayerP& Lp = li < P.n_rate ? P.rate[li] : P.aug[li - P.n_rate];
+    const int nW = Lp.n_out_p * Lp.ldw;
+    for (int i = threadIdx.x; i < nW; i += blockDim.x) {
+        const int row = i / Lp.ldw, col = i - row * Lp.ldw;
+        packed[Lp.w_off + i] = (row < Lp.n_out && col < Lp.n_in) ? theta[Lp.th_w + row * Lp.n_in + col] : 0.f;
+    }
+    for (int i = threadIdx.x; i < Lp.n_out_p; i += blockDim.x)
+        packed[Lp.b_off + i] = i < Lp.n_out ? theta[Lp.th_b + i] : 0.f;
+}
+
+// g_theta[e] = sum over CTA slabs (fixed order => deterministic) of the packed accumulators.
+__global__ void reduce_dtheta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ slabs, int n_slabs,
+                                     float* __restrict__ g_theta) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.n_theta) return;
+    int pidx = -1;
+    const int nl = P.n_rate + P.n_aug;
+    for (int li = 0; li < nl; ++li) {
+        const LayerP& Lp = li < P.n_rate ? P.rate[li] : P.aug[li - P.n_rate];
+        if (e >= Lp.th_w && e < Lp.th_w + Lp.n_in * Lp.n_out) {
+            const int k = e - Lp.th_w;
+            const int row = k / Lp.n_in, col = k - row * Lp.n_in;
+            pidx = Lp.w_off + row * Lp.ldw + col;
+            break;
+        }
+        if (e >= Lp.th_b && e < Lp.th_b + Lp.n_out) {
+            pidx = Lp.b_off + (e - Lp.th_b);
+            break;
+        }
+    }
+    float s = 0.f;
+    if (pidx >= 0)
+        for (int c = 0; c < n_slabs; ++c) s += slabs[(long long)c * P.n_packed + pidx];
+    g_theta[e] = s;
+}
+
+// side[0..7] = sum over CTA partials (fixed order).
+__global__ void reduce_side_kernel(const double* __restrict__ partial, int n_parts, double* __restrict__ side) {
+    const int i = threadIdx.x;
+    if (i >= 8) return;
+    double s = 0.0;
+    for (int c = 0; c < n_parts; ++c) s += partial[c * 8 + i];
+    if (i == 6) s = partial[6];   // RHS evaluations per trajectory: identical in every CTA
+    side[i] = s;
+}
+
+// Register-resident FFMA chains: the measured fp32 roofline denominator.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i) * 1e-3f;
+    const float m = 0.999f + seed * 1e-6f, c = 1e-4f * seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;       // never true; keeps the chain alive
+}
+
+}  // namespace ude

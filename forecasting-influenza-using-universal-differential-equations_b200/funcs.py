@@ -1,0 +1,228 @@
+"""ODE-func modules with the reference's protocol, and their recognition.
+
+``Fp`` / ``Fa`` / ``FaFp`` mirror the public surface of
+/root/reference/lib/models.py:109-265 — constructor kwargs, ``forward(t, x)``,
+``clear_tracking()``, ``posterior()``, attributes ``params``, ``tracker``,
+``Fa_w``, ``ode_type``, ``uncertainty``, ``n_regions``, ``latent_dim`` and the
+``state_dict`` keys (``Fp_net.{1,3,..}``, ``net.*``/``aug_net.*``) — so that a
+checkpoint written by the reference loads here and vice versa.
+
+The fused solver never calls ``forward``: ``describe_func`` reads the layer
+structure and hands the flat weight vector to the CUDA kernels.  ``forward`` is
+kept because it is part of the ODE-func protocol (``func(t, y)``) that callers
+such as plotting code use directly.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+from torch.distributions import Normal
+
+from . import _lib
+
+
+def _mlp_modules(n_in: int, sizes: Sequence[int], n_head: int, flatten_first: bool) -> nn.ModuleList:
+    """[Flatten?], Linear, (ELU, Linear)*, Linear — index layout as in the reference
+    (lib/models.py:116-124), which is what fixes the state_dict keys."""
+    mods = nn.ModuleList()
+    if flatten_first:
+        mods.append(nn.Flatten())
+    widths = [n_in, *sizes]
+    mods.append(nn.Linear(widths[0], widths[1]))
+    for a, b in zip(widths[1:-1], widths[2:]):
+        mods.append(nn.ELU(inplace=True))
+        mods.append(nn.Linear(a, b))
+    mods.append(nn.Linear(widths[-1], n_head))
+    return mods
+
+
+def _run(mods: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
+    for m in mods:
+        x = m(x)
+    return x
+
+
+class _UdeFunc(nn.Module):
+    """Shared behaviour of the three ODE funcs."""
+    ode_type = "?"
+
+    def __init__(self, n_regions: int, latent_dim: int):
+        super().__init__()
+        self.n_regions = n_regions
+        self.latent_dim = latent_dim
+        self.uncertainty = "none"
+        self.params: list = []
+        self.tracker: list = []
+
+    # -- reference protocol -----------------------------------------------------------
+    def clear_tracking(self):
+        self.params = []
+        self.tracker = []
+
+    def posterior(self) -> Normal:
+        rows = torch.stack(self.params).reshape(-1, 2)
+        self.params = []
+        return Normal(rows.mean(0), rows.std(0))
+
+    # -- shared math ------------------------------------------------------------------
+    def _rates(self, net: nn.ModuleList, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        p = torch.abs(_run(net, x)).reshape(-1, self.n_regions, 2)
+        self.params.append(p)
+        infect = p[..., 0] * x[..., 0] * x[..., 1]
+        recover = p[..., 1] * x[..., 1]
+        return torch.stack([-infect, infect - recover, recover], dim=-1), p
+
+    def _finish(self, dyn: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        out = torch.cat([dyn, torch.zeros_like(x[..., 3:])], -1)
+        out[(x > 2) | (x < -1)] = 0.0
+        return out
+
+
+class Fp(_UdeFunc):
+    """Mechanistic SIR term with MLP-produced (beta, gamma) — lib/models.py:109-156."""
+
+    def __init__(self, n_regions=1, latent_dim=8, net_sizes=[20, 20], **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.ode_type = "Fp"
+        self.Fp_net = _mlp_modules(n_regions * latent_dim, net_sizes, 2 * n_regions, flatten_first=True)
+
+    def forward(self, t, x):
+        dyn, _ = self._rates(self.Fp_net, x)
+        return self._finish(dyn, x)
+
+
+class Fa(_UdeFunc):
+    """Pure MLP correction — lib/models.py:158-197 (Flatten is a separate attribute there)."""
+
+    def __init__(self, n_regions=1, latent_dim=8, net_sizes=[32, 32], aug_net_sizes=[32, 32], nhidden_fa=32, **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.ode_type = "Fa"
+        self.flatten = nn.Flatten()
+        self.aug_net = _mlp_modules(n_regions * latent_dim, aug_net_sizes, 3 * n_regions, flatten_first=False)
+
+    def forward(self, t, x):
+        fa = _run(self.aug_net, self.flatten(x)).reshape(-1, self.n_regions, 3)
+        out = self._finish(fa, x)
+        self.tracker.append(fa)
+        return out
+
+
+class FaFp(_UdeFunc):
+    """SIR term + Fa_w * correction — lib/models.py:199-265."""
+
+    def __init__(self, n_regions=1, latent_dim=8, net_sizes=[20, 20], aug_net_sizes=[32, 32], **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.ode_type = "FaFp"
+        self.net = _mlp_modules(n_regions * latent_dim, net_sizes, 2 * n_regions, flatten_first=True)
+        self.aug_net = _mlp_modules(n_regions * latent_dim, aug_net_sizes, 3 * n_regions, flatten_first=True)
+        self.Fa_w = 1.0
+
+    def forward(self, t, x):
+        dyn, _ = self._rates(self.net, x)
+        fa = _run(self.aug_net, x).reshape(-1, self.n_regions, 3)
+        out = self._finish(dyn + self.Fa_w * fa, x)
+        self.tracker.append(fa)
+        return out
+
+
+# ---------------------------------------------------------------------------------------
+# recognition of a reference-protocol module (ours, lib.models.*, or tuning/tune_node.py:63 Fp)
+# ---------------------------------------------------------------------------------------
+@dataclass
+class FuncInfo:
+    kind: str
+    n_regions: int
+    latent_dim: int
+    rate_layers: List[nn.Linear]
+    aug_layers: List[nn.Linear]
+    fa_w: float
+
+    def desc(self, batch: int, n_groups: int = 1) -> "_lib.UdeDesc":
+        d = _lib.UdeDesc()
+        d.kind = _lib.KIND[self.kind]
+        d.n_regions = self.n_regions
+        d.latent_dim = self.latent_dim
+        d.n_rate_layers = len(self.rate_layers)
+        for i, l in enumerate(self.rate_layers):
+            d.rate_sizes[i] = l.out_features
+        d.n_aug_layers = len(self.aug_layers)
+        for i, l in enumerate(self.aug_layers):
+            d.aug_sizes[i] = l.out_features
+        d.fa_w = float(self.fa_w)
+        d.n_groups = n_groups
+        d.batch = batch
+        return d
+
+    def linears(self) -> List[nn.Linear]:
+        return [*self.rate_layers, *self.aug_layers]
+
+    def theta(self) -> torch.Tensor:
+        """Flat weight vector in the C-ABI layout; differentiable w.r.t. the module parameters."""
+        return torch.cat([p.reshape(-1) for l in self.linears() for p in (l.weight, l.bias)])
+
+
+class UnsupportedFunc(TypeError):
+    pass
+
+
+def _linear_chain(net, what: str) -> List[nn.Linear]:
+    """Validate Linear, (ELU, Linear)*, Linear (an optional leading Flatten is skipped)."""
+    mods = [m for m in net if not isinstance(m, nn.Flatten)]
+    lin: List[nn.Linear] = []
+    expect_linear = True
+    for i, m in enumerate(mods):
+        if isinstance(m, nn.Linear):
+            if m.bias is None:
+                raise UnsupportedFunc(f"{what}: Linear without bias")
+            lin.append(m)
+            expect_linear = False
+        elif isinstance(m, nn.ELU):
+            if expect_linear or m.alpha != 1.0:
+                raise UnsupportedFunc(f"{what}: unexpected ELU at position {i}")
+            expect_linear = True
+        else:
+            raise UnsupportedFunc(f"{what}: unsupported layer {type(m).__name__}")
+    if len(lin) < 2 or len(lin) > _lib.UDE_MAX_LAYERS:
+        raise UnsupportedFunc(f"{what}: needs 2..{_lib.UDE_MAX_LAYERS} Linear layers")
+    # the reference puts an ELU before every hidden Linear except the head: positions must be
+    # Linear, ELU, Linear, ..., ELU, Linear, Linear
+    n_elu = sum(isinstance(m, nn.ELU) for m in mods)
+    if n_elu != len(lin) - 2 or not isinstance(mods[-1], nn.Linear) or not isinstance(mods[-2], nn.Linear):
+        raise UnsupportedFunc(f"{what}: layer pattern is not Linear,(ELU,Linear)*,Linear")
+    for a, b in zip(lin[:-1], lin[1:]):
+        if a.out_features != b.in_features:
+            raise UnsupportedFunc(f"{what}: width mismatch")
+    return lin
+
+
+def describe_func(func) -> FuncInfo:
+    """Duck-type an ODE func following the reference protocol; raise UnsupportedFunc otherwise."""
+    kind = getattr(func, "ode_type", None)
+    if kind is None and type(func).__name__ == "Fp" and hasattr(func, "net"):
+        kind = "Fp"                                    # tuning/tune_node.py:63-104 local Fp
+    if kind not in ("Fp", "Fa", "FaFp"):
+        raise UnsupportedFunc(
+            "the fused UDE solver integrates Fp / Fa / FaFp modules (lib/models.py protocol) only; "
+            f"got {type(func).__name__}.  There is deliberately no generic-callable or CPU fallback.")
+    if getattr(func, "uncertainty", "none") != "none":
+        raise UnsupportedFunc("Bayesian ODE funcs (per-stage weight re-sampling) are not fused yet")
+    R = int(getattr(func, "n_regions", getattr(func, "n_region", 0)))
+    L = int(func.latent_dim)
+    rate: List[nn.Linear] = []
+    aug: List[nn.Linear] = []
+    if kind == "Fp":
+        rate = _linear_chain(func.Fp_net if hasattr(func, "Fp_net") else func.net, "Fp net")
+    elif kind == "FaFp":
+        rate = _linear_chain(func.net, "FaFp.net")
+        aug = _linear_chain(func.aug_net, "FaFp.aug_net")
+    else:
+        aug = _linear_chain(func.aug_net, "Fa.aug_net")
+    for lin, head in ((rate, 2 * R), (aug, 3 * R)):
+        if lin and (lin[0].in_features != R * L or lin[-1].out_features != head):
+            raise UnsupportedFunc("layer widths do not match n_regions * latent_dim / the head size")
+    if L < 3:
+        raise UnsupportedFunc("latent_dim must be >= 3 (S, I, R)")
+    return FuncInfo(kind, R, L, rate, aug, float(getattr(func, "Fa_w", 1.0)))

@@ -1,0 +1,231 @@
+"""``odeint`` — drop-in for ``torchdiffeq.odeint`` on the reference's hot path.
+
+    latent = odeint(self.ode, z, t, method='rk4', options=dict(step_size=h))
+                                                   /root/reference/lib/VAE.py:137
+
+Same signature and return value (``[len(t), *y0.shape]``); ``func`` must be an
+``Fp`` / ``Fa`` / ``FaFp`` module (this package's or the reference's own
+``lib.models`` classes) living on a CUDA device in fp32.  The whole
+integration is ONE fused CUDA kernel launch; ``loss.backward()`` runs ONE fused
+discrete-adjoint kernel and routes ``dL/dtheta`` into the module parameters and
+``dL/dy0`` to whatever produced ``y0`` (the encoder).  Anything else raises —
+there is no CPU path and no generic-callable path.
+
+Side channels (lib/models.py:137,187,238,252): the reference appends beta/gamma
+and Fa of *every* RHS evaluation to python lists that the loss later reduces
+(``posterior()`` -> mean/std, lib/models.py:152-156; ``torch.norm(torch.stack(
+tracker))``, lib/VAE.py:180).  The kernels emit the reductions instead; after a
+solve ``func.params`` / ``func.tracker`` receive small differentiable tensors
+for which those two expressions return exactly the reference's values.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .funcs import FuncInfo, UnsupportedFunc, describe_func
+
+_GRID_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_GRID_CACHE_MAX = 64
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------
+# fixed grid tables (host side, fp32, bit-exact restatement of torchdiffeq — see ude_rk4_grid)
+# ---------------------------------------------------------------------------------------
+def rk4_grid_tables(t_host: np.ndarray, step_size: Optional[float]):
+    """Returns (dt[n_steps] f32, out_step[T] i32, out_kind[T] i32, out_w[T] f32) as numpy arrays."""
+    L = _lib.lib()
+    t_host = np.ascontiguousarray(t_host, dtype=np.float32)
+    T = t_host.shape[0]
+    use = 0 if step_size is None else 1
+    h = 0.0 if step_size is None else float(np.float32(step_size))
+    cap = 1024
+    while True:
+        dt = np.empty(cap, dtype=np.float32)
+        n_steps = C.c_int32(0)
+        out_step = np.empty(T, dtype=np.int32)
+        out_kind = np.empty(T, dtype=np.int32)
+        out_w = np.empty(T, dtype=np.float32)
+        st = L.ude_rk4_grid(t_host.ctypes.data, T, h, use, cap, dt.ctypes.data, C.byref(n_steps),
+                            out_step.ctypes.data, out_kind.ctypes.data, out_w.ctypes.data)
+        if st == _lib.UDE_ERR_CAPACITY:
+            cap = int(n_steps.value)
+            continue
+        _lib.check(st, "ude_rk4_grid")
+        return dt[: n_steps.value].copy(), out_step, out_kind, out_w
+
+
+def _grid_on_device(t: torch.Tensor, step_size, device):
+    t_host = t.detach().to("cpu", torch.float32).numpy()
+    if step_size is None:
+        h = None
+    elif isinstance(step_size, torch.Tensor):
+        h = float(step_size.detach().to("cpu", torch.float32))
+    else:
+        h = float(np.float32(step_size))
+    key = (t_host.tobytes(), h, str(device))
+    hit = _GRID_CACHE.get(key)
+    if hit is not None:
+        _GRID_CACHE.move_to_end(key)
+        return hit
+    dt, out_step, out_kind, out_w = rk4_grid_tables(t_host, h)
+    dev = tuple(torch.from_numpy(a).to(device) for a in (dt, out_step, out_kind, out_w))
+    val = (dev, int(dt.shape[0]))
+    _GRID_CACHE[key] = val
+    if len(_GRID_CACHE) > _GRID_CACHE_MAX:
+        _GRID_CACHE.popitem(last=False)
+    return val
+
+
+# ---------------------------------------------------------------------------------------
+# autograd bridge
+# ---------------------------------------------------------------------------------------
+class _Rk4Solve(torch.autograd.Function):
+    """(theta, y0) -> (y_out [T,B,R,L], side [8] fp64).  One fused launch each way."""
+
+    @staticmethod
+    def forward(ctx, theta, y0, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool):
+        L = _lib.lib()
+        dev = y0.device
+        B, R, Ld = y0.shape
+        desc = info.desc(B)
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
+            theta_c = theta.detach().contiguous()
+            y0_c = y0.detach().contiguous()
+            y_out = torch.empty((n_out, B, R, Ld), dtype=torch.float32, device=dev)
+            side = torch.empty(8, dtype=torch.float64, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            dt, out_step, out_kind, out_w = tables
+            st = L.ude_rk4_forward(C.byref(desc), _ptr(theta_c), _ptr(y0_c), n_steps, _ptr(dt), n_out,
+                                   _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(y_out), _ptr(tape), _ptr(side),
+                                   _ptr(ws), int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out = info, tables, n_steps, n_out
+        ctx.plan_ws = int(plan.workspace_bytes)
+        ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev))
+        ctx.has_tape = tape is not None
+        return y_out, side
+
+    @staticmethod
+    def backward(ctx, g_out, g_side):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_c, y0_c, tape = ctx.saved_tensors
+        info: FuncInfo = ctx.info
+        dev = y0_c.device
+        B = y0_c.shape[0]
+        desc = info.desc(B)
+        with torch.cuda.device(dev):
+            if g_out is None:
+                g_out = torch.zeros((ctx.n_out, *y0_c.shape), dtype=torch.float32, device=dev)
+            g_out = g_out.contiguous().float()
+            gs = None
+            if g_side is not None:
+                gs = g_side[:5].to(torch.float32).contiguous()
+            g_y0 = torch.empty_like(y0_c)
+            g_theta = torch.empty_like(theta_c)
+            ws = torch.empty(ctx.plan_ws, dtype=torch.uint8, device=dev)
+            dt, out_step, out_kind, out_w = ctx.tables
+            st = L.ude_rk4_backward(C.byref(desc), _ptr(theta_c), _ptr(y0_c), ctx.n_steps, _ptr(dt), ctx.n_out,
+                                    _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(tape), _ptr(g_out), _ptr(gs),
+                                    _ptr(g_y0), _ptr(g_theta), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward")
+        return g_theta, g_y0, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------
+# side channels -> the reference's python-list protocol
+# ---------------------------------------------------------------------------------------
+def posterior_rows(side: torch.Tensor) -> torch.Tensor:
+    """A [2, 2] tensor whose column mean / unbiased std equal the mean / std of every
+    (beta, gamma) row the reference would have stacked (lib/models.py:152-156)."""
+    n = side[5]
+    mean = side[0:2] / n
+    var = (side[2:4] - n * mean * mean) / (n - 1.0)
+    std = torch.sqrt(torch.clamp(var, min=0.0))
+    half = std / math.sqrt(2.0)
+    return torch.stack([mean - half, mean + half]).to(torch.float32)
+
+
+def install_side_channels(func, info: FuncInfo, side: torch.Tensor) -> None:
+    if info.rate_layers and isinstance(getattr(func, "params", None), list):
+        func.params.append(posterior_rows(side))
+    if info.aug_layers and isinstance(getattr(func, "tracker", None), list):
+        func.tracker.append(torch.sqrt(side[4]).to(torch.float32))
+
+
+# ---------------------------------------------------------------------------------------
+# public entry point
+# ---------------------------------------------------------------------------------------
+def _check_common(func, y0, t, method, event_fn):
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not on the fused path")
+    if not isinstance(y0, torch.Tensor):
+        raise NotImplementedError("tuple-valued states are not on the fused path")
+    if not torch.is_floating_point(y0):
+        raise TypeError("`y0` must be a floating point Tensor")
+    if not isinstance(t, torch.Tensor) or t.dim() != 1 or not torch.is_floating_point(t):
+        raise ValueError("t must be a one dimensional floating point tensor")
+    if t.numel() < 2:
+        raise ValueError("t must hold at least two time points")
+    info = describe_func(func)
+    if not y0.is_cuda:
+        raise RuntimeError("the fused UDE solver runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+    if y0.dtype != torch.float32:
+        raise TypeError("the fused UDE solver is fp32 (as the reference, run_ode.py:30)")
+    if y0.dim() != 3 or y0.shape[1] != info.n_regions or y0.shape[2] != info.latent_dim:
+        raise ValueError(f"y0 must be [B, {info.n_regions}, {info.latent_dim}], got {tuple(y0.shape)}")
+    for l in info.linears():
+        if l.weight.device != y0.device or l.weight.dtype != torch.float32:
+            raise RuntimeError("ODE func parameters must be fp32 on y0's device")
+    return info
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """torchdiffeq.odeint signature; fused sm_100a implementation for UDE funcs."""
+    if method is None:
+        method = "dopri5"
+    if method not in ("rk4", "dopri5"):
+        raise ValueError(f'Invalid method "{method}". The fused path implements rk4 and dopri5.')
+    info = _check_common(func, y0, t, method, event_fn)
+    options = {} if options is None else dict(options)
+    t_cpu = t.detach().to("cpu")
+    inc = bool((t_cpu[1:] > t_cpu[:-1]).all())
+    if not inc:
+        if bool((t_cpu[1:] < t_cpu[:-1]).all()):
+            raise NotImplementedError("decreasing t is not on the reference's path")
+        raise ValueError("t must be strictly increasing or decreasing")
+    if method == "dopri5":
+        from .dopri5 import dopri5_solve
+        return dopri5_solve(func, info, y0, t_cpu, rtol, atol, options)
+
+    unknown = set(options) - {"step_size", "interp", "perturb", "grid_constructor"}
+    if unknown:
+        raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
+    if options.get("interp", "linear") != "linear" or options.get("perturb", False) or \
+            options.get("grid_constructor", None) is not None:
+        raise NotImplementedError("only step_size grids with linear interpolation are fused")
+    (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
+    theta = info.theta()
+    need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
+    y_out, side = _Rk4Solve.apply(theta, y0, info, tables, n_steps, int(t.numel()), need_tape)
+    install_side_channels(func, info, side)
+    return y_out

@@ -1,0 +1,200 @@
+/*
+ * ude_b200.h — C ABI of the B200-native fused UDE solve.
+ *
+ * This is the drop-in boundary for ONE hot path of
+ * M-Morris-95/Forecasting-Influenza-Using-Universal-Differential-Equations:
+ *
+ *     latent = odeint(self.ode, z, t, method='rk4', options=dict(step_size=h))
+ *                                              /root/reference/lib/VAE.py:137
+ *     loss.backward()                          /root/reference/lib/VAE.py:203
+ *
+ * i.e. the batched integration of the Fp / Fa / FaFp ODE funcs
+ * (/root/reference/lib/models.py:109-265) by torchdiffeq's fixed-grid RK4
+ * (3/8 rule) or adaptive Dopri5, and the discrete adjoint of that integration.
+ * The reference reaches this path through Python (torchdiffeq.odeint +
+ * torch.autograd); a binding is a ctypes/cffi stub over the entry points below
+ * (see INTEGRATION.md).  The Python package in this repo is exactly such a stub.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer marked "dev" is a device pointer
+ *     owned by the caller, everything else is host memory;
+ *   - nothing persistent is allocated; scratch comes in through `workspace`
+ *     (size from ude_plan()); all work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*) and is asynchronous;
+ *   - every function returns 0 (UDE_OK) or a negative UdeStatus, never throws;
+ *   - arithmetic is fp32 (side-channel sums are fp64), as the reference
+ *     (/root/reference/run_ode.py:30).
+ *
+ * Tensor layouts (row-major, innermost last)
+ *   y0, g_y0      [B, R, L]       the reference's flattened batch axis
+ *                                 B = n_samples * batch (lib/models.py:23)
+ *   y_out, g_out  [T, B, R, L]    what odeint returns (lib/VAE.py:137-138)
+ *   theta, g_theta[G, n_theta]    per weight set: for every nn.Linear in
+ *                                 ModuleList order (rate net, then aug net)
+ *                                 W[out,in] row-major, then b[out]
+ *                                 (lib/models.py:118-124, 167-172, 208-223)
+ *   tape          opaque, ude_plan().tape_bytes; written by *_forward,
+ *                 read by *_backward (stage inputs, SoA)
+ *   side          double[8]: sum beta, sum gamma, sum beta^2, sum gamma^2,
+ *                 sum Fa^2, N rows, n RHS evals, reserved — the reductions
+ *                 behind posterior() (lib/models.py:152-156) and the Fa_norm
+ *                 loss (lib/VAE.py:179-183); per group: [G, 8]
+ *   g_side        float[5] per group: dL/d(side[0..4])
+ */
+#ifndef UDE_B200_H
+#define UDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDE_ABI_VERSION 1
+#define UDE_MAX_LAYERS 8          /* nn.Linear layers per net, head included */
+#define UDE_SIDE_LEN 8
+
+typedef enum UdeStatus {
+    UDE_OK = 0,
+    UDE_ERR_INVALID = -1,         /* bad descriptor / null pointer / bad size   */
+    UDE_ERR_UNSUPPORTED = -2,     /* valid request the kernels do not cover     */
+    UDE_ERR_WORKSPACE = -3,       /* workspace / tape smaller than ude_plan()   */
+    UDE_ERR_CUDA = -4,            /* CUDA runtime error (see ude_last_cuda_error) */
+    UDE_ERR_NO_DEVICE = -5,       /* no sm_100 device visible                   */
+    UDE_ERR_GRID = -6,            /* t not strictly increasing / bad step_size  */
+    UDE_ERR_CAPACITY = -7         /* caller-provided table too small            */
+} UdeStatus;
+
+typedef enum UdeKind { UDE_KIND_FP = 0, UDE_KIND_FA = 1, UDE_KIND_FAFP = 2 } UdeKind;
+
+/* Static description of the ODE func (constructor kwargs of
+ * lib/models.py:110,159,200) and of the batch. */
+typedef struct UdeDesc {
+    int32_t kind;                         /* UdeKind                                         */
+    int32_t n_regions;                    /* R                                               */
+    int32_t latent_dim;                   /* L >= 3                                          */
+    int32_t n_rate_layers;                /* Linear layers of the (beta,gamma) net, 0 for Fa */
+    int32_t rate_sizes[UDE_MAX_LAYERS];   /* out width of each; last must be 2R              */
+    int32_t n_aug_layers;                 /* Linear layers of the Fa net, 0 for Fp           */
+    int32_t aug_sizes[UDE_MAX_LAYERS];    /* out width of each; last must be 3R              */
+    float   fa_w;                         /* FaFp.Fa_w (lib/models.py:225,249); runtime      */
+    int32_t n_groups;                     /* G independent weight sets (tuning sweeps); >= 1 */
+    int64_t batch;                        /* B, all groups together; B % G == 0              */
+} UdeDesc;
+
+typedef enum UdeMethod { UDE_METHOD_RK4 = 0, UDE_METHOD_DOPRI5 = 1 } UdeMethod;
+
+/* Sizes the caller must provide (bytes). */
+typedef struct UdePlan {
+    int64_t n_theta;            /* floats per weight set                          */
+    int64_t workspace_bytes;    /* scratch for either direction                   */
+    int64_t tape_bytes;         /* for n_steps steps (rk4) / max_steps (dopri5)   */
+    int32_t tile_traj;          /* trajectories per CTA tile                      */
+    int32_t n_ctas;             /* persistent grid size                           */
+    int32_t smem_bytes_fwd;     /* dynamic shared memory per CTA                  */
+    int32_t smem_bytes_bwd;
+    int32_t weights_in_smem;    /* 1: staged once per CTA with a TMA bulk copy    */
+    int32_t reserved;
+} UdePlan;
+
+int         ude_abi_version(void);
+const char* ude_strerror(int status);
+const char* ude_last_cuda_error(void);
+
+/* Number of floats in one weight set for `desc` (host only, no GPU needed). */
+int64_t ude_theta_size(const UdeDesc* desc);
+
+/* Algorithmic multiply-accumulates of one RHS evaluation of one trajectory. */
+int64_t ude_macs_per_eval(const UdeDesc* desc);
+
+/* Sizes for a solve of `n_steps` grid steps (rk4) or at most `n_steps`
+ * accepted steps per trajectory (dopri5).  Host arithmetic only (assumes 148 SMs
+ * when no GPU is visible). */
+int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan);
+
+/*
+ * Fixed-grid construction, host only (no GPU needed).  Restates
+ * torchdiffeq FixedGridODESolver._grid_constructor_from_step_size + the output
+ * loop of FixedGridODESolver.integrate in fp32, bit for bit:
+ *   niters = ceil((t[-1]-t[0])/step_size + 1); grid = arange(niters)*step_size + t[0];
+ *   grid[-1] = t[-1];  outputs emitted while t1 >= t[j].
+ * use_step_size == 0 -> the grid is t itself.
+ *   dt[n]        = grid[n+1] - grid[n]                      n < *n_steps
+ *   out_step[j]  = grid step whose end first reaches t[j]   (-1 for j == 0)
+ *   out_kind[j]  = 0: copy y_n (t[j]==t0)  1: copy y_{n+1} (t[j]==t1)  2: lerp
+ *   out_w[j]     = (t[j]-t0)/(t1-t0)  for kind 2
+ * `cap_steps` is the capacity of dt[]; the per-output tables hold n_t entries.
+ */
+int ude_rk4_grid(const float* t, int32_t n_t, float step_size, int32_t use_step_size,
+                 int32_t cap_steps, float* dt, int32_t* n_steps,
+                 int32_t* out_step, int32_t* out_kind, float* out_w);
+
+/*
+ * Fixed-step RK4 (torchdiffeq 'rk4' = 3/8 rule) forward over the whole grid.
+ * Replaces  odeint(func, y0, t, method='rk4', options={'step_size': h})
+ * (/root/reference/lib/VAE.py:137).  `tape` may be NULL (no backward wanted).
+ */
+int ude_rk4_forward(const UdeDesc* desc,
+                    const float* theta /*dev*/, const float* y0 /*dev*/,
+                    int32_t n_steps, const float* dt /*dev [n_steps]*/,
+                    int32_t n_out, const int32_t* out_step /*dev*/,
+                    const int32_t* out_kind /*dev*/, const float* out_w /*dev*/,
+                    float* y_out /*dev [n_out,B,R,L]*/, float* tape /*dev | NULL*/,
+                    double* side /*dev [G,8]*/,
+                    void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+/*
+ * Discrete adjoint of ude_rk4_forward = what torch.autograd computes for
+ * loss.backward() through the solver (/root/reference/lib/VAE.py:203).
+ */
+int ude_rk4_backward(const UdeDesc* desc,
+                     const float* theta /*dev*/, const float* y0 /*dev*/,
+                     int32_t n_steps, const float* dt /*dev*/,
+                     int32_t n_out, const int32_t* out_step /*dev*/,
+                     const int32_t* out_kind /*dev*/, const float* out_w /*dev*/,
+                     const float* tape /*dev*/,
+                     const float* g_out /*dev [n_out,B,R,L]*/, const float* g_side /*dev [G,5] | NULL*/,
+                     float* g_y0 /*dev [B,R,L]*/, float* g_theta /*dev [G,n_theta]*/,
+                     void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+/* Controller options of torchdiffeq's RKAdaptiveStepsizeODESolver. */
+typedef struct UdeDopri5Opts {
+    double  rtol, atol;
+    double  first_step;          /* <= 0: torchdiffeq's _select_initial_step      */
+    double  safety, ifactor, dfactor;   /* 0.9, 10, 0.2                            */
+    int32_t max_steps;           /* cap on ACCEPTED steps per trajectory (tape)   */
+    int32_t max_attempts;        /* cap on attempted steps per trajectory         */
+} UdeDopri5Opts;
+
+/*
+ * Adaptive Dopri5 forward, one controller PER TRAJECTORY (= torchdiffeq called
+ * with B == 1 for each row; DESIGN.md "Dopri5 batch semantics").
+ *   t_out   dev [n_out] fp64 output times, increasing; y_out[0] = y0
+ *   counts  dev [B,4] int32: accepted, rejected, status (0 ok, 1 max_steps,
+ *           2 max_attempts, 3 dt underflow / non-finite), reserved
+ *   steps   dev [max_steps,B] fp64 pairs are inside `tape`.
+ */
+int ude_dopri5_forward(const UdeDesc* desc, const UdeDopri5Opts* opts,
+                       const float* theta /*dev*/, const float* y0 /*dev*/,
+                       int32_t n_out, const double* t_out /*dev*/,
+                       float* y_out /*dev*/, float* tape /*dev | NULL*/,
+                       int32_t* counts /*dev [B,4]*/, double* side /*dev [G,8]*/,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+int ude_dopri5_backward(const UdeDesc* desc, const UdeDopri5Opts* opts,
+                        const float* theta /*dev*/, const float* y0 /*dev*/,
+                        int32_t n_out, const double* t_out /*dev*/,
+                        const float* tape /*dev*/, const int32_t* counts /*dev*/,
+                        const float* g_out /*dev*/, const float* g_side /*dev | NULL*/,
+                        float* g_y0 /*dev*/, float* g_theta /*dev*/,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Sustained fp32 FFMA throughput of the device in TFLOP/s (2 flops per FMA),
+ * measured with a register-resident FMA chain kernel: the roofline denominator
+ * bench.py reports against.  Synchronous. */
+int ude_measure_ffma_tflops(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDE_B200_H */
