@@ -13,7 +13,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libude_b200.so")
+SO_PATH = os.environ.get("UDE_B200_LIB") or os.path.join(CSRC, "libude_b200.so")   # env override: kernel experiments
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 UDE_MAX_LAYERS = 8

@@ -12,7 +12,10 @@
 
 namespace ude {
 
-constexpr int kThreads = 256;     // threads per CTA
+#ifndef UDE_THREADS
+#define UDE_THREADS 256
+#endif
+constexpr int kThreads = UDE_THREADS;     // threads per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxLayers = 8;     // == UDE_MAX_LAYERS
 constexpr int kPadTail = 64;      // floats of zero padding after the packed weights

@@ -1,0 +1,115 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/ude_b200.h
+declares, and its host-only entry points (grid construction, sizes, planning, error codes) agree
+with the oracle.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import odeint_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "ude_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ude_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(built_lib, name), f"{name} declared in the header but not exported"
+    import ude_b200._lib as L
+    assert declared == set(L.EXPORTS)
+    assert built_lib.ude_abi_version() == 1
+    assert built_lib.ude_strerror(0) == b"ok" and b"workspace" in built_lib.ude_strerror(-3)
+
+
+GRIDS = [
+    (torch.arange(9.), 1.0), (torch.arange(57.) / 7, None), (torch.arange(37.) / 7, None),
+    (torch.arange(44.) / 7, None), (torch.arange(86.) / 7, None), (torch.linspace(1, 56, 56) / 7, 1.0),
+    (torch.arange(4.), 0.5), (torch.tensor([0.0, 0.3, 0.9, 2.0]), 0.7), (torch.tensor([0.0, 1e-3, 5.0]), 2.0),
+]
+
+
+@pytest.mark.parametrize("case", range(len(GRIDS)))
+def test_host_grid_is_bit_exact_vs_oracle(built_lib, case):
+    """ude_rk4_grid == torchdiffeq's fp32 grid constructor + output rule (as restated by the oracle)."""
+    import ude_b200
+    t, h = GRIDS[case]
+    hh = (t[1] - t[0]) if h is None else h
+    dt, out_step, out_kind, out_w = ude_b200.rk4_grid_tables(t.numpy(), float(hh))
+    grid = odeint_ref.rk4_grid(t, hh)
+    assert np.array_equal(dt, (grid[1:] - grid[:-1]).numpy())
+    # replay the oracle's output loop
+    j = 1
+    for n, (t0, t1) in enumerate(zip(grid[:-1], grid[1:])):
+        while j < len(t) and t1 >= t[j]:
+            assert out_step[j] == n
+            if t[j] == t0:
+                assert out_kind[j] == 0
+            elif t[j] == t1:
+                assert out_kind[j] == 1
+            else:
+                assert out_kind[j] == 2
+                assert np.float32(out_w[j]) == ((t[j] - t0) / (t1 - t0)).numpy()
+            j += 1
+    assert j == len(t) and out_step[0] == -1
+
+
+def test_grid_without_step_size_is_t_itself(built_lib):
+    import ude_b200
+    t = torch.tensor([0.0, 0.5, 1.5, 4.0])
+    dt, out_step, out_kind, _ = ude_b200.rk4_grid_tables(t.numpy(), None)
+    assert np.array_equal(dt, (t[1:] - t[:-1]).numpy())
+    assert list(out_step) == [-1, 0, 1, 2] and list(out_kind[1:]) == [1, 1, 1]
+
+
+def test_grid_errors(built_lib):
+    import ude_b200
+    with pytest.raises(ude_b200.UdeError):
+        ude_b200.rk4_grid_tables(np.array([0.0, 1.0, 1.0], dtype=np.float32), 0.5)     # not increasing
+    with pytest.raises(ude_b200.UdeError):
+        ude_b200.rk4_grid_tables(np.array([0.0, 1.0], dtype=np.float32), -1.0)         # bad step
+
+
+def _desc(kind, R, L, rate, aug, B=2048):
+    from ude_b200 import _lib
+    d = _lib.UdeDesc()
+    d.kind, d.n_regions, d.latent_dim = _lib.KIND[kind], R, L
+    d.n_rate_layers = len(rate)
+    for i, s in enumerate(rate):
+        d.rate_sizes[i] = s
+    d.n_aug_layers = len(aug)
+    for i, s in enumerate(aug):
+        d.aug_sizes[i] = s
+    d.fa_w, d.n_groups, d.batch = 1.0, 1, B
+    return d
+
+
+def test_sizes_match_reference_parameter_counts(built_lib):
+    """params 6 882 / 4 931 / 11 813 (R=1), 34 626 / 38 867 / 73 493 (R=49)."""
+    cases = [("Fp", 1, [64, 64, 32, 2], [], 6882, 6720), ("Fa", 1, [], [64, 64, 3], 4931, 4800),
+             ("FaFp", 1, [64, 64, 32, 2], [64, 64, 3], 11813, 11520),
+             ("Fp", 49, [64, 64, 32, 98], [], 34626, 34368), ("FaFp", 49, [64, 64, 32, 98], [64, 64, 147], 73493, 72960)]
+    for kind, R, rate, aug, n_theta, macs in cases:
+        d = _desc(kind, R, 8, rate, aug)
+        assert built_lib.ude_theta_size(C.byref(d)) == n_theta
+        assert built_lib.ude_macs_per_eval(C.byref(d)) == macs
+
+
+def test_descriptor_validation_and_plan(built_lib):
+    from ude_b200 import _lib
+    bad = _desc("FaFp", 1, 8, [64, 3], [64, 3])          # rate head must be 2R
+    assert built_lib.ude_theta_size(C.byref(bad)) == -1
+    bad = _desc("Fp", 1, 2, [8, 2], [])                  # latent_dim < 3
+    assert built_lib.ude_theta_size(C.byref(bad)) == -1
+    d = _desc("FaFp", 1, 8, [64, 64, 32, 2], [64, 64, 3], B=1 << 20)
+    plan = _lib.UdePlan()
+    assert built_lib.ude_plan(C.byref(d), 0, 8, C.byref(plan)) == 0
+    assert plan.n_theta == 11813 and plan.weights_in_smem == 1
+    assert plan.tape_bytes >= (1 << 20) * 8 * 4 * 3 * 4
+    assert plan.smem_bytes_bwd <= 227 * 1024 and plan.smem_bytes_fwd <= 227 * 1024
+    assert built_lib.ude_plan(None, 0, 8, C.byref(plan)) == -1
