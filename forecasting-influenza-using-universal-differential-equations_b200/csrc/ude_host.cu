@@ -87,6 +87,7 @@ static void base_model(const UdeDesc* d, ModelP& P) {
     P.D_p = round4(P.D);
     P.Dn = 3 * P.R;
     P.Dn_p = round4(P.Dn);
+    P.R_p = round4(P.R);
     P.n_rate = d->n_rate_layers;
     P.n_aug = d->n_aug_layers;
     P.fa_w = d->fa_w;
@@ -98,7 +99,7 @@ static void base_model(const UdeDesc* d, ModelP& P) {
 }
 
 // Shared-memory plan for a given tile size; returns the arena size in floats.
-static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, bool bwd) {
+static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, int n_rbuf, bool bwd) {
     P.TB = TB;
     P.TBP = TB + 4;
     P.w_in_smem = w_smem;
@@ -122,6 +123,9 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, b
     }
     P.off_S = off;
     off += n_state * P.Dn_p * P.TBP;
+    P.off_RB = off;
+    P.n_rbuf = n_rbuf;
+    off += n_rbuf * P.R_p * P.TBP;
     P.off_GX = off;
     P.off_CB = off;
     if (bwd) {
@@ -150,7 +154,7 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, b
     return off;
 }
 
-static const int kSmemBudgetBytes = 226 * 1024;     // 227 KB per CTA minus the static part
+static const int kSmemBudgetBytes = 220 * 1024;     // 227 KB per CTA minus the static part (<= 5.4 KB)
 
 struct DeviceInfo {
     int ok = 0;
@@ -175,7 +179,7 @@ static DeviceInfo& device_info() {
 }
 
 // Pick (TB, weights in smem, accumulators in smem) for a direction.
-static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, bool bwd) {
+static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, int n_rbuf, bool bwd) {
     base_model(d, P);
     const int budget = kSmemBudgetBytes / 4;
     const long long tiles64 = (d->batch + 63) / 64;
@@ -190,7 +194,7 @@ static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, bool bwd) {
     const int nc = bwd ? 3 : 2;
     for (int c = 0; c < nc; ++c)
         for (int t = 0; t < 2; ++t) {
-            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, n_state, bwd) <= budget) return UDE_OK;
+            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, n_state, n_rbuf, bwd) <= budget) return UDE_OK;
         }
     return UDE_ERR_UNSUPPORTED;
 }
@@ -227,10 +231,15 @@ static int set_smem(K kernel, int bytes) {
     return UDE_OK;
 }
 
-static int n_state_for(int method, bool bwd) {
-    if (method == UDE_METHOD_RK4) return bwd ? B_NSTATE : F_NSTATE;
-    return bwd ? DB_NSTATE : DF_NSTATE;
+static long long dopri_tape_x_bytes(const ModelP& P, long long B, int max_steps) {
+    return align_up((long long)(max_steps + 1) * kDopriStages * P.Dn * B * 4, 256);
 }
+
+static int n_state_for(int method, bool bwd) {
+    if (method == UDE_METHOD_RK4) return bwd ? (int)B_NSTATE : (int)F_NSTATE;
+    return bwd ? (int)DB_NSTATE : (int)DF_NSTATE;
+}
+static int n_rbuf_for(int method, bool bwd) { return (method == UDE_METHOD_DOPRI5 && !bwd) ? (int)DF_NRB : 0; }
 
 }  // namespace ude
 
@@ -282,17 +291,16 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     if (method != UDE_METHOD_RK4 && method != UDE_METHOD_DOPRI5) return UDE_ERR_INVALID;
     if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     ModelP Pf, Pb;      // pure host arithmetic: works without a GPU (148 SMs assumed then)
-    if ((st = choose_plan(desc, Pf, n_state_for(method, false), false)) != UDE_OK) return st;
-    if ((st = choose_plan(desc, Pb, n_state_for(method, true), true)) != UDE_OK) return st;
+    if ((st = choose_plan(desc, Pf, n_state_for(method, false), n_rbuf_for(method, false), false)) != UDE_OK) return st;
+    if ((st = choose_plan(desc, Pb, n_state_for(method, true), n_rbuf_for(method, true), true)) != UDE_OK) return st;
     memset(plan, 0, sizeof(*plan));
     plan->n_theta = Pf.n_theta;
     const int ctas_f = grid_size(Pf, desc->batch), ctas_b = grid_size(Pb, desc->batch);
     const int n_ctas = ctas_f > ctas_b ? ctas_f : ctas_b;
     Workspace w = carve_workspace(nullptr, Pf, n_ctas);
     plan->workspace_bytes = w.bytes;
-    const long long stages = method == UDE_METHOD_RK4 ? 4 : kDopriStages;
-    plan->tape_bytes = align_up((long long)n_steps * stages * Pf.Dn * desc->batch * 4, 256);
-    if (method == UDE_METHOD_DOPRI5) plan->tape_bytes += align_up((long long)n_steps * desc->batch * 8 * 2, 256);
+    if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up((long long)n_steps * 4 * Pf.Dn * desc->batch * 4, 256);
+    else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
     plan->tile_traj = Pb.TB;
     plan->n_ctas = n_ctas;
     plan->smem_bytes_fwd = Pf.smem_floats * 4;
@@ -381,7 +389,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     ModelP P;
-    if ((st = choose_plan(desc, P, F_NSTATE, false)) != UDE_OK) return st;
+    if ((st = choose_plan(desc, P, F_NSTATE, 0, false)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);
     Workspace w = carve_workspace(workspace, P, n_ctas);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
@@ -421,7 +429,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     ModelP P;
-    if ((st = choose_plan(desc, P, B_NSTATE, true)) != UDE_OK) return st;
+    if ((st = choose_plan(desc, P, B_NSTATE, 0, true)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);
     Workspace w = carve_workspace(workspace, P, n_ctas);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;

@@ -40,6 +40,7 @@ struct ModelP {
     int R, L;
     int D, D_p;             // R*L and padded to 4  : rows of X (MLP input, row = r*L + l)
     int Dn, Dn_p;           // 3R and padded to 4   : rows of the dynamic state (row = r*3 + c)
+    int R_p;                // R padded to 4        : rows of per-region scratch
     int n_rate, n_aug;
     LayerP rate[kMaxLayers];
     LayerP aug[kMaxLayers];
@@ -56,6 +57,7 @@ struct ModelP {
     int off_GX;             // (bwd) dL/du of one RHS evaluation, [D_p][TBP]
     int off_CB;             // (bwd) running cotangent of the constant inputs, [D_p][TBP]
     int n_state;
+    int off_RB, n_rbuf;     // per-region scratch: n_rbuf buffers of [R_p][TBP] (dopri5)
     int smem_floats;        // total arena size
 };
 

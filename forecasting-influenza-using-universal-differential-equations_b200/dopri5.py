@@ -1,6 +1,121 @@
-"""Adaptive Dopri5 front end (per-trajectory controller) — see csrc/ude_dopri5.cuh."""
+"""Adaptive Dopri5 front end — ``odeint(func, y0, t, rtol=, atol=)`` with torchdiffeq's default
+method (the one the reference reaches at /root/reference/lib/train_functions.py:190).
+
+Batch semantics: torchdiffeq uses ONE step size for the whole batch (RMS error norm over the
+entire tensor).  The fused kernels run one controller PER TRAJECTORY, i.e. exactly what
+torchdiffeq computes when called on each row alone (B == 1); see DESIGN.md.  Side channels
+cover accepted stages only (1 + 6 * n_accept evaluations per trajectory).
+
+Extra (fused-path only) options: ``max_accepted_steps`` (tape capacity, default 256) and
+``return_stats=True`` -> ``(y, stats)`` with per-trajectory accepted / rejected counts.
+"""
 from __future__ import annotations
 
+import ctypes as C
 
-def dopri5_solve(func, info, y0, t_cpu, rtol, atol, options):
-    raise NotImplementedError("fused dopri5 is not built yet")
+import torch
+
+from . import _lib
+from .funcs import FuncInfo
+from .odeint import _ptr, _stream_ptr, install_side_channels
+
+STATUS_TEXT = {1: "max_accepted_steps exceeded (raise options['max_accepted_steps'])",
+               2: "max_num_steps exceeded", 3: "underflow in dt / non-finite state"}
+
+
+def _opts(rtol, atol, options) -> "_lib.UdeDopri5Opts":
+    known = {"first_step", "safety", "ifactor", "dfactor", "max_num_steps", "max_accepted_steps", "return_stats",
+             "per_trajectory", "dtype"}
+    unknown = set(options) - known
+    if unknown:
+        raise ValueError(f"unexpected dopri5 options {sorted(unknown)}")
+    if options.get("per_trajectory", True) is False:
+        raise NotImplementedError("the fused Dopri5 runs one controller per trajectory (see DESIGN.md); "
+                                  "shared-step batch control is not fused")
+    o = _lib.UdeDopri5Opts()
+    o.rtol = float(rtol)
+    o.atol = float(atol)
+    fs = options.get("first_step", None)
+    o.first_step = float(fs) if fs is not None else -1.0
+    o.safety = float(options.get("safety", 0.9))
+    o.ifactor = float(options.get("ifactor", 10.0))
+    o.dfactor = float(options.get("dfactor", 0.2))
+    o.max_steps = int(options.get("max_accepted_steps", 256))
+    o.max_attempts = int(min(options.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
+    return o
+
+
+class _Dopri5Solve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, y0, info: FuncInfo, t_dev, opts, need_tape: bool):
+        L = _lib.lib()
+        dev = y0.device
+        B, R, Ld = y0.shape
+        n_out = int(t_dev.numel())
+        desc = info.desc(B)
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["dopri5"], opts.max_steps, C.byref(plan)), "ude_plan")
+            theta_c = theta.detach().contiguous()
+            y0_c = y0.detach().contiguous()
+            y_out = torch.empty((n_out, B, R, Ld), dtype=torch.float32, device=dev)
+            side = torch.empty(8, dtype=torch.float64, device=dev)
+            counts = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            st = L.ude_dopri5_forward(C.byref(desc), C.byref(opts), _ptr(theta_c), _ptr(y0_c), n_out, _ptr(t_dev),
+                                      _ptr(y_out), _ptr(tape), _ptr(counts), _ptr(side), _ptr(ws),
+                                      int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_dopri5_forward")
+        ctx.info, ctx.opts, ctx.t_dev = info, opts, t_dev
+        ctx.plan_ws = int(plan.workspace_bytes)
+        ctx.has_tape = tape is not None
+        ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev), counts)
+        ctx.mark_non_differentiable(counts)
+        return y_out, side, counts
+
+    @staticmethod
+    def backward(ctx, g_out, g_side, _g_counts):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_c, y0_c, tape, counts = ctx.saved_tensors
+        dev = y0_c.device
+        desc = ctx.info.desc(y0_c.shape[0])
+        n_out = int(ctx.t_dev.numel())
+        with torch.cuda.device(dev):
+            g_out = g_out.contiguous().float()
+            gs = g_side[:5].to(torch.float32).contiguous() if g_side is not None else None
+            g_y0 = torch.empty_like(y0_c)
+            g_theta = torch.empty_like(theta_c)
+            ws = torch.empty(ctx.plan_ws, dtype=torch.uint8, device=dev)
+            st = L.ude_dopri5_backward(C.byref(desc), C.byref(ctx.opts), _ptr(theta_c), _ptr(y0_c), n_out,
+                                       _ptr(ctx.t_dev), _ptr(tape), _ptr(counts), _ptr(g_out), _ptr(gs), _ptr(g_y0),
+                                       _ptr(g_theta), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_dopri5_backward")
+        return g_theta, g_y0, None, None, None, None
+
+
+class Dopri5Stats:
+    """Per-trajectory controller statistics of the last fused solve."""
+
+    def __init__(self, counts: torch.Tensor):
+        self.n_accept = counts[:, 0]
+        self.n_reject = counts[:, 1]
+        self.status = counts[:, 2]
+        self.n_attempts = counts[:, 3]
+
+
+def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
+    opts = _opts(rtol, atol, options)
+    t_dev = t_cpu.to(torch.float64).to(y0.device)
+    theta = info.theta()
+    need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
+    y_out, side, counts = _Dopri5Solve.apply(theta, y0, info, t_dev, opts, need_tape)
+    worst = int(counts[:, 2].max())          # torchdiffeq asserts on these conditions; so do we
+    if worst != 0:
+        raise _lib.UdeError("fused dopri5: " + STATUS_TEXT.get(worst, f"status {worst}"))
+    install_side_channels(func, info, side)
+    if options.get("return_stats", False):
+        return y_out, Dopri5Stats(counts)
+    return y_out
