@@ -53,6 +53,7 @@ struct DopriFwdArgs {
     double* tape_t;         // [max_steps, B, 2]
     int* counts;            // [B,4]
     double* side_partial;
+    float* cold;
     long long B;
     DopriOpts o;
 };
@@ -69,6 +70,7 @@ struct DopriBwdArgs {
     const float* g_side;
     float* g_y0;
     float* slabs;
+    float* cold;
     long long B;
     DopriOpts o;
 };
@@ -96,7 +98,7 @@ __device__ __forceinline__ float rk_combine(const float* __restrict__ K, int SS,
 // ===================================================================================
 // forward
 // ===================================================================================
-template <bool SMEM_W>
+template <bool SMEM_W, bool COLD>
 __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_constant__ ModelP Pg, const DopriFwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
@@ -120,12 +122,13 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
 
     const int SS = P.Dn_p * TBP;
-    float* SY = smem + P.off_S + DF_Y * SS;
-    float* SK = smem + P.off_S + DF_K1 * SS;        // SK + i*SS = k_{i+1}
-    float* CO = smem + P.off_S + DF_COEF * SS;      // e, d, c, b, a
+    float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;
+    float* SY = SB + P.off_S + DF_Y * SS;
+    float* SK = SB + P.off_S + DF_K1 * SS;          // SK + i*SS = k_{i+1}
+    float* CO = SB + P.off_S + DF_COEF * SS;        // e, d, c, b, a
     const int RS = P.R_p * TBP;
-    float* PART = smem + P.off_RB + DF_RB_PART * RS;
-    float* SA = smem + P.off_RB + DF_RB_SA * RS;     // 5 x [R_p][TBP]
+    float* PART = SB + P.off_RB + DF_RB_PART * RS;
+    float* SA = SB + P.off_RB + DF_RB_SA * RS;       // 5 x [R_p][TBP]
 
     SideAcc side;
     side.clear();
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
 // ===================================================================================
 // backward: discrete adjoint over each trajectory's accepted-step tape
 // ===================================================================================
-template <bool SMEM_W, bool SMEM_G>
+template <bool SMEM_W, bool SMEM_G, bool COLD>
 __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_constant__ ModelP Pg, const DopriBwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
@@ -453,11 +456,12 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
     const int SS = P.Dn_p * TBP;
-    float* LAM1 = smem + P.off_S + DB_LAM1 * SS;
-    float* Y0B = smem + P.off_S + DB_Y0B * SS;
-    float* KB = smem + P.off_S + DB_KB1 * SS;        // KB + i*SS = kbar_{i+1}
+    float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;
+    float* LAM1 = SB + P.off_S + DB_LAM1 * SS;
+    float* Y0B = SB + P.off_S + DB_Y0B * SS;
+    float* KB = SB + P.off_S + DB_KB1 * SS;          // KB + i*SS = kbar_{i+1}
     float* GX = smem + P.off_GX;
-    float* CB = smem + P.off_CB;
+    float* CB = SB + P.off_CB;
     const long long B = a.B;
     const long long n_tiles = (B + TB - 1) / TB;
     const long long stage_sz = (long long)Dn * B;
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         __syncthreads();
         load_y0_tile(P, smem, a.y0, b0, nvalid);
-        for (int i = threadIdx.x; i < DB_NSTATE * SS; i += kThreads) smem[P.off_S + i] = 0.f;
+        for (int i = threadIdx.x; i < DB_NSTATE * SS; i += kThreads) SB[P.off_S + i] = 0.f;
         for (int i = threadIdx.x; i < P.D_p * TBP; i += kThreads) { CB[i] = 0.f; GX[i] = 0.f; }
         if (threadIdx.x == 0) s_max = 0;
         __syncthreads();

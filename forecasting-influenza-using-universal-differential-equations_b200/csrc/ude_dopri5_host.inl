@@ -31,7 +31,7 @@ int ude_dopri5_forward(const UdeDesc* desc, const UdeDopri5Opts* opts, const flo
     if ((st = choose_plan(desc, P, DF_NSTATE, DF_NRB, false)) != UDE_OK) return st;
     if (P.TB > kMaxTB) return UDE_ERR_UNSUPPORTED;
     const int n_ctas = grid_size(P, desc->batch);
-    Workspace w = carve_workspace(workspace, P, n_ctas);
+    Workspace w = carve_workspace(workspace, P, n_ctas, P.cold_global ? P.cold_floats : 0);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
@@ -46,16 +46,19 @@ int ude_dopri5_forward(const UdeDesc* desc, const UdeDopri5Opts* opts, const flo
                     : nullptr;
     a.counts = counts;
     a.side_partial = w.side_partial;
+    a.cold = w.cold;
     a.B = desc->batch;
     a.o = o;
     const int smem = P.smem_floats * 4;
-    if (P.w_in_smem) {
-        if ((st = set_smem(dopri5_fwd_kernel<true>, smem)) != UDE_OK) return st;
-        dopri5_fwd_kernel<true><<<n_ctas, kThreads, smem, s>>>(P, a);
-    } else {
-        if ((st = set_smem(dopri5_fwd_kernel<false>, smem)) != UDE_OK) return st;
-        dopri5_fwd_kernel<false><<<n_ctas, kThreads, smem, s>>>(P, a);
-    }
+#define UDE_LAUNCH_DFWD(W, C)                                                             \
+    do {                                                                                  \
+        if ((st = set_smem(dopri5_fwd_kernel<W, C>, smem)) != UDE_OK) return st;          \
+        dopri5_fwd_kernel<W, C><<<n_ctas, kThreads, smem, s>>>(P, a);                     \
+    } while (0)
+    if (P.cold_global) UDE_LAUNCH_DFWD(false, true);
+    else if (P.w_in_smem) UDE_LAUNCH_DFWD(true, false);
+    else UDE_LAUNCH_DFWD(false, false);
+#undef UDE_LAUNCH_DFWD
     UDE_CUDA(cudaGetLastError());
     reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
     UDE_CUDA(cudaGetLastError());
@@ -78,7 +81,7 @@ int ude_dopri5_backward(const UdeDesc* desc, const UdeDopri5Opts* opts, const fl
     if ((st = choose_plan(desc, P, DB_NSTATE, 0, true)) != UDE_OK) return st;
     if (P.TB > kMaxTB) return UDE_ERR_UNSUPPORTED;
     const int n_ctas = grid_size(P, desc->batch);
-    Workspace w = carve_workspace(workspace, P, n_ctas);
+    Workspace w = carve_workspace(workspace, P, n_ctas, P.cold_global ? P.cold_floats : 0);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
@@ -94,17 +97,19 @@ int ude_dopri5_backward(const UdeDesc* desc, const UdeDopri5Opts* opts, const fl
     a.g_side = g_side;
     a.g_y0 = g_y0;
     a.slabs = w.slabs;
+    a.cold = w.cold;
     a.B = desc->batch;
     a.o = o;
     const int smem = P.smem_floats * 4;
-#define UDE_LAUNCH_DBWD(W, G)                                                             \
+#define UDE_LAUNCH_DBWD(W, G, C)                                                          \
     do {                                                                                  \
-        if ((st = set_smem(dopri5_bwd_kernel<W, G>, smem)) != UDE_OK) return st;          \
-        dopri5_bwd_kernel<W, G><<<n_ctas, kThreads, smem, s>>>(P, a);                     \
+        if ((st = set_smem(dopri5_bwd_kernel<W, G, C>, smem)) != UDE_OK) return st;       \
+        dopri5_bwd_kernel<W, G, C><<<n_ctas, kThreads, smem, s>>>(P, a);                  \
     } while (0)
-    if (P.w_in_smem && P.g_in_smem) UDE_LAUNCH_DBWD(true, true);
-    else if (P.w_in_smem) UDE_LAUNCH_DBWD(true, false);
-    else UDE_LAUNCH_DBWD(false, false);
+    if (P.cold_global) UDE_LAUNCH_DBWD(false, false, true);
+    else if (P.w_in_smem && P.g_in_smem) UDE_LAUNCH_DBWD(true, true, false);
+    else if (P.w_in_smem) UDE_LAUNCH_DBWD(true, false, false);
+    else UDE_LAUNCH_DBWD(false, false, false);
 #undef UDE_LAUNCH_DBWD
     UDE_CUDA(cudaGetLastError());
     reduce_dtheta_kernel<<<(P.n_theta + 255) / 256, 256, 0, s>>>(P, w.slabs, n_ctas, g_theta);

@@ -99,7 +99,7 @@ static void base_model(const UdeDesc* d, ModelP& P) {
 }
 
 // Shared-memory plan for a given tile size; returns the arena size in floats.
-static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, int n_rbuf, bool bwd) {
+static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int n_state, int n_rbuf, bool bwd) {
     P.TB = TB;
     P.TBP = TB + 4;
     P.w_in_smem = w_smem;
@@ -121,18 +121,20 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, int n_state, i
             off += Ls[i].n_out_p * P.TBP;
         }
     }
-    P.off_S = off;
-    off += n_state * P.Dn_p * P.TBP;
-    P.off_RB = off;
+    // solver-state rows: in shared memory, or (large R) in a per-CTA global scratch ("cold")
+    int coff = 0;
+    int& soff = cold ? coff : off;
+    P.cold_global = cold;
+    P.off_S = soff;
+    soff += n_state * P.Dn_p * P.TBP;
+    P.off_RB = soff;
     P.n_rbuf = n_rbuf;
-    off += n_rbuf * P.R_p * P.TBP;
+    soff += n_rbuf * P.R_p * P.TBP;
+    P.off_CB = soff;
+    if (bwd) soff += P.D_p * P.TBP;
+    P.cold_floats = coff + 8;
     P.off_GX = off;
-    P.off_CB = off;
-    if (bwd) {
-        off += P.D_p * P.TBP;
-        P.off_CB = off;
-        off += P.D_p * P.TBP;
-    }
+    if (bwd) off += P.D_p * P.TBP;
     off += 8;    // slack
     P.smem_floats = off;
     // tile shapes: aim at >= kWarps units per phase (both nets run in the same phase)
@@ -187,14 +189,15 @@ static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, int n_rbuf, boo
     const int n_sm = di.ok ? di.n_sm : 148;
     // small batches: smaller tiles spread over more SMs
     const int tb_order[2] = {tiles64 >= n_sm ? 64 : 32, tiles64 >= n_sm ? 32 : 64};
-    struct Cand { int w, g; };
-    const Cand cands_bwd[3] = {{1, 1}, {1, 0}, {0, 0}};
-    const Cand cands_fwd[2] = {{1, 0}, {0, 0}};
+    struct Cand { int w, g, cold; };
+    const Cand cands_bwd[4] = {{1, 1, 0}, {1, 0, 0}, {0, 0, 0}, {0, 0, 1}};
+    const Cand cands_fwd[3] = {{1, 0, 0}, {0, 0, 0}, {0, 0, 1}};
     const Cand* cands = bwd ? cands_bwd : cands_fwd;
-    const int nc = bwd ? 3 : 2;
+    const int nc = bwd ? 4 : 3;
     for (int c = 0; c < nc; ++c)
         for (int t = 0; t < 2; ++t) {
-            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, n_state, n_rbuf, bwd) <= budget) return UDE_OK;
+            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, cands[c].cold, n_state, n_rbuf, bwd) <= budget)
+                return UDE_OK;
         }
     return UDE_ERR_UNSUPPORTED;
 }
@@ -203,9 +206,10 @@ struct Workspace {
     float* wpacked;
     double* side_partial;
     float* slabs;
+    float* cold;
     long long bytes;
 };
-static Workspace carve_workspace(void* base, const ModelP& P, int n_ctas) {
+static Workspace carve_workspace(void* base, const ModelP& P, int n_ctas, int cold_floats) {
     Workspace w;
     long long off = 0;
     w.wpacked = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
@@ -214,6 +218,8 @@ static Workspace carve_workspace(void* base, const ModelP& P, int n_ctas) {
     off = align_up(off + (long long)n_ctas * 8 * 8, 256);
     w.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
     off = align_up(off + (long long)n_ctas * P.n_packed * 4, 256);
+    w.cold = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * cold_floats * 4, 256);
     w.bytes = off;
     return w;
 }
@@ -297,7 +303,8 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     plan->n_theta = Pf.n_theta;
     const int ctas_f = grid_size(Pf, desc->batch), ctas_b = grid_size(Pb, desc->batch);
     const int n_ctas = ctas_f > ctas_b ? ctas_f : ctas_b;
-    Workspace w = carve_workspace(nullptr, Pf, n_ctas);
+    const int cold_max = Pf.cold_floats > Pb.cold_floats ? Pf.cold_floats : Pb.cold_floats;
+    Workspace w = carve_workspace(nullptr, Pf, n_ctas, cold_max);
     plan->workspace_bytes = w.bytes;
     if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up((long long)n_steps * 4 * Pf.Dn * desc->batch * 4, 256);
     else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
@@ -391,7 +398,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     ModelP P;
     if ((st = choose_plan(desc, P, F_NSTATE, 0, false)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);
-    Workspace w = carve_workspace(workspace, P, n_ctas);
+    Workspace w = carve_workspace(workspace, P, n_ctas, P.cold_global ? P.cold_floats : 0);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
@@ -402,15 +409,18 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     a.y_out = y_out;
     a.tape = tape;
     a.side_partial = w.side_partial;
+    a.cold = w.cold;
     a.B = desc->batch;
     const int smem = P.smem_floats * 4;
-    if (P.w_in_smem) {
-        if ((st = set_smem(rk4_fwd_kernel<true>, smem)) != UDE_OK) return st;
-        rk4_fwd_kernel<true><<<n_ctas, kThreads, smem, s>>>(P, a);
-    } else {
-        if ((st = set_smem(rk4_fwd_kernel<false>, smem)) != UDE_OK) return st;
-        rk4_fwd_kernel<false><<<n_ctas, kThreads, smem, s>>>(P, a);
-    }
+#define UDE_LAUNCH_FWD(W, C)                                                              \
+    do {                                                                                  \
+        if ((st = set_smem(rk4_fwd_kernel<W, C>, smem)) != UDE_OK) return st;             \
+        rk4_fwd_kernel<W, C><<<n_ctas, kThreads, smem, s>>>(P, a);                        \
+    } while (0)
+    if (P.cold_global) UDE_LAUNCH_FWD(false, true);
+    else if (P.w_in_smem) UDE_LAUNCH_FWD(true, false);
+    else UDE_LAUNCH_FWD(false, false);
+#undef UDE_LAUNCH_FWD
     UDE_CUDA(cudaGetLastError());
     reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
     UDE_CUDA(cudaGetLastError());
@@ -431,7 +441,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     ModelP P;
     if ((st = choose_plan(desc, P, B_NSTATE, 0, true)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);
-    Workspace w = carve_workspace(workspace, P, n_ctas);
+    Workspace w = carve_workspace(workspace, P, n_ctas, P.cold_global ? P.cold_floats : 0);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
@@ -444,16 +454,18 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     a.g_side = g_side;
     a.g_y0 = g_y0;
     a.slabs = w.slabs;
+    a.cold = w.cold;
     a.B = desc->batch;
     const int smem = P.smem_floats * 4;
-#define UDE_LAUNCH_BWD(W, G)                                                              \
+#define UDE_LAUNCH_BWD(W, G, C)                                                           \
     do {                                                                                  \
-        if ((st = set_smem(rk4_bwd_kernel<W, G>, smem)) != UDE_OK) return st;             \
-        rk4_bwd_kernel<W, G><<<n_ctas, kThreads, smem, s>>>(P, a);                        \
+        if ((st = set_smem(rk4_bwd_kernel<W, G, C>, smem)) != UDE_OK) return st;          \
+        rk4_bwd_kernel<W, G, C><<<n_ctas, kThreads, smem, s>>>(P, a);                     \
     } while (0)
-    if (P.w_in_smem && P.g_in_smem) UDE_LAUNCH_BWD(true, true);
-    else if (P.w_in_smem) UDE_LAUNCH_BWD(true, false);
-    else UDE_LAUNCH_BWD(false, false);
+    if (P.cold_global) UDE_LAUNCH_BWD(false, false, true);
+    else if (P.w_in_smem && P.g_in_smem) UDE_LAUNCH_BWD(true, true, false);
+    else if (P.w_in_smem) UDE_LAUNCH_BWD(true, false, false);
+    else UDE_LAUNCH_BWD(false, false, false);
 #undef UDE_LAUNCH_BWD
     UDE_CUDA(cudaGetLastError());
     reduce_dtheta_kernel<<<(P.n_theta + 255) / 256, 256, 0, s>>>(P, w.slabs, n_ctas, g_theta);

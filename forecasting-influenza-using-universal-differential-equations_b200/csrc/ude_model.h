@@ -58,6 +58,8 @@ struct ModelP {
     int off_CB;             // (bwd) running cotangent of the constant inputs, [D_p][TBP]
     int n_state;
     int off_RB, n_rbuf;     // per-region scratch: n_rbuf buffers of [R_p][TBP] (dopri5)
+    int cold_global;        // solver-state rows (off_S, off_RB, off_CB) live in a per-CTA global scratch
+    int cold_floats;        // size of that scratch per CTA
     int smem_floats;        // total arena size
 };
 

@@ -26,6 +26,7 @@ struct Rk4FwdArgs {
     float* y_out;           // [n_out,B,R,L]
     float* tape;            // [n_steps,4,Dn,B] or null
     double* side_partial;   // [gridDim.x, 8]
+    float* cold;            // [gridDim.x, cold_floats] when the plan spills the state rows
     long long B;
 };
 
@@ -38,6 +39,7 @@ struct Rk4BwdArgs {
     const float* g_side;    // [5] or null
     float* g_y0;            // [B,R,L]
     float* slabs;           // [gridDim.x, n_packed] per-CTA dtheta accumulators
+    float* cold;
     long long B;
 };
 
@@ -92,7 +94,7 @@ __device__ __forceinline__ void store_out_row(const ModelP& P, const float* smem
 // ===================================================================================
 // forward
 // ===================================================================================
-template <bool SMEM_W>
+template <bool SMEM_W, bool COLD>
 __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_constant__ ModelP Pg, const Rk4FwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
@@ -113,10 +115,11 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
     // zero the padding rows of X once (they feed layer 0 with K = D_p)
     for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
 
-    float* SY = smem + P.off_S + F_Y * P.Dn_p * TBP;
-    float* SK1 = smem + P.off_S + F_K1 * P.Dn_p * TBP;
-    float* SK2 = smem + P.off_S + F_K2 * P.Dn_p * TBP;
-    float* SK3 = smem + P.off_S + F_K3 * P.Dn_p * TBP;
+    float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;    // base of the state rows
+    float* SY = SB + P.off_S + F_Y * P.Dn_p * TBP;
+    float* SK1 = SB + P.off_S + F_K1 * P.Dn_p * TBP;
+    float* SK2 = SB + P.off_S + F_K2 * P.Dn_p * TBP;
+    float* SK3 = SB + P.off_S + F_K3 * P.Dn_p * TBP;
 
     SideAcc side;
     side.clear();
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
 // ===================================================================================
 // backward (discrete adjoint)
 // ===================================================================================
-template <bool SMEM_W, bool SMEM_G>
+template <bool SMEM_W, bool SMEM_G, bool COLD>
 __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_constant__ ModelP Pg, const Rk4BwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
@@ -249,10 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     }
 
     const int SS = P.Dn_p * TBP;
-    float* LAM = smem + P.off_S + B_LAM * SS;
-    float* KB = smem + P.off_S + B_KB1 * SS;        // KB[s] = KB + s*SS, s = 0..3
+    float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;
+    float* LAM = SB + P.off_S + B_LAM * SS;
+    float* KB = SB + P.off_S + B_KB1 * SS;          // KB[s] = KB + s*SS, s = 0..3
     float* GX = smem + P.off_GX;
-    float* CB = smem + P.off_CB;
+    float* CB = SB + P.off_CB;
 
     const long long B = a.B;
     const long long n_tiles = (B + TB - 1) / TB;

@@ -90,6 +90,7 @@ def run_case(name, mod, y0, t, method, options, rtol=1e-7, atol=1e-9, seed=0):
         y=y.detach().numpy(), G=G.numpy(), c_side=C_SIDE.numpy(),
         side=side.detach().numpy(), dy0=grads[0].numpy(), dtheta=dtheta.numpy(),
     )
+    out["first_step"] = np.float64(opts.get("first_step", -1.0) or -1.0)
     if stats is not None:
         out["n_accept"] = stats.n_accept.numpy()
         out["n_reject"] = stats.n_reject.numpy()
@@ -139,6 +140,15 @@ def main():
     m = build("Fp", 3, 8, 9, net_sizes=[32, 32])
     run_case("dopri5_fp_r3", m, synth_y0(4, 3, 8, seed=19), torch.arange(0., 4.5, 0.5), "dopri5",
              dict(per_trajectory=True), rtol=1e-6, atol=1e-8, seed=9)
+    # 10/11. the same machinery with a DETERMINISTIC controller: tolerance so loose that every step
+    # is accepted and grows by ifactor exactly, so fp32 round-off in the error norm cannot change the
+    # step sequence (at tight tolerances it does, in any two fp32 implementations)
+    m = build("FaFp", 1, 8, 10, **big)
+    run_case("dopri5det_fafp_r1", m, synth_y0(70, 1, 8, seed=20), torch.arange(9.), "dopri5",
+             dict(per_trajectory=True, first_step=0.01), rtol=1e-1, atol=1e-1, seed=10)
+    m = build("FaFp", 3, 8, 11, fa_w=0.5, net_sizes=[32, 32], aug_net_sizes=[20])
+    run_case("dopri5det_fafp_r3", m, synth_y0(5, 3, 8, seed=21), torch.arange(0., 4.5, 0.5), "dopri5",
+             dict(per_trajectory=True, first_step=0.05), rtol=1e-1, atol=1e-1, seed=11)
 
 
 if __name__ == "__main__":

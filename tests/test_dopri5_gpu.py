@@ -13,26 +13,48 @@ def _solve(g, **extra):
     mod = module_from_spec(g["spec"], torch.from_numpy(g["theta"]), g["fa_w"], "cuda")
     y0 = torch.from_numpy(g["y0"]).cuda().requires_grad_(True)
     mod.clear_tracking()
+    if float(g["first_step"]) > 0:
+        extra.setdefault("first_step", float(g["first_step"]))
     y, stats = ude_b200.odeint(mod, y0, torch.from_numpy(g["t"]), rtol=float(g["rtol"]), atol=float(g["atol"]),
                                options=dict(return_stats=True, **extra))
     return mod, y0, y, stats
 
 
+@pytest.mark.parametrize("name", golden_names("dopri5det_"))
+def test_golden_forward_deterministic_controller(name):
+    """Same step sequence on both sides -> bit-level machinery parity: 1e-5 on everything."""
+    g = load_golden(name)
+    mod, y0, y, stats = _solve(g)
+    err = rel_err(y, torch.from_numpy(g["y"]))
+    acc, rej = stats.n_accept.cpu().numpy(), stats.n_reject.cpu().numpy()
+    print(f"{name}: forward rel err {err:.3e}")
+    assert np.array_equal(acc, g["n_accept"]) and np.array_equal(rej, g["n_reject"])
+    assert err <= RTOL_PARITY
+    side = torch.from_numpy(g["side"])
+    if g["spec"].has_rate:
+        post = mod.posterior()
+        assert rel_err(post.mean, side[0:2] / side[5]) <= RTOL_PARITY
+    if g["spec"].has_aug:
+        assert rel_err(torch.norm(torch.stack(mod.tracker)), torch.sqrt(side[4])) <= RTOL_PARITY
+
+
 @pytest.mark.parametrize("name", golden_names("dopri5_"))
-def test_golden_forward_and_step_counts(name):
+def test_golden_forward_tight_tolerance(name):
+    """rtol 1e-5 / 1e-6: fp32 round-off in the error norm may flip a borderline accept decision, so
+    the step SEQUENCE may differ; the solution agrees far below the controller tolerance and the
+    accepted-step counts match."""
     g = load_golden(name)
     mod, y0, y, stats = _solve(g)
     err = rel_err(y, torch.from_numpy(g["y"]))
     acc, rej = stats.n_accept.cpu().numpy(), stats.n_reject.cpu().numpy()
     print(f"{name}: forward rel err {err:.3e}; accepted {acc.tolist()} vs {g['n_accept'].tolist()}; "
           f"rejected {rej.tolist()} vs {g['n_reject'].tolist()}")
-    # solver tolerance is rtol: two fp32 realisations of the same controller agree far below it
     assert err <= 10 * float(g["rtol"])
-    assert np.array_equal(acc, g["n_accept"]) and np.array_equal(rej, g["n_reject"])
-    assert err <= RTOL_PARITY            # identical step sequences -> the RK4-grade tolerance holds
+    assert np.array_equal(acc, g["n_accept"])
+    assert np.abs(rej - g["n_reject"]).max() <= 1
 
 
-@pytest.mark.parametrize("name", golden_names("dopri5_"))
+@pytest.mark.parametrize("name", golden_names("dopri5det_"))
 def test_golden_backward(name):
     g = load_golden(name)
     mod, y0, y, stats = _solve(g)
@@ -59,9 +81,6 @@ def test_side_channels_cover_accepted_stages():
     mod, y0, y, stats = _solve(g)
     n_rows = int((1 + 6 * stats.n_accept.cpu().long()).sum()) * g["spec"].n_regions
     assert n_rows == int(g["side"][5])
-    post = mod.posterior()
-    side = torch.from_numpy(g["side"])
-    assert rel_err(post.mean, side[0:2] / side[5]) <= RTOL_PARITY
 
 
 def test_step_count_agreement_large_batch():

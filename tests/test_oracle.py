@@ -35,13 +35,16 @@ def test_oracle_reproduces_rk4_golden(name):
     assert rel_err(f.theta.grad, torch.from_numpy(g["dtheta"])) < 1e-6
 
 
-@pytest.mark.parametrize("name", golden_names("dopri5_"))
+@pytest.mark.parametrize("name", golden_names("dopri5"))
 def test_oracle_reproduces_dopri5_golden(name):
     g = load_golden(name)
     f = OracleFunc(g["spec"], torch.from_numpy(g["theta"]), g["fa_w"])
     stats = odeint_ref.Dopri5Stats()
+    opts = dict(per_trajectory=True, stats=stats)
+    if float(g["first_step"]) > 0:
+        opts["first_step"] = float(g["first_step"])
     y = odeint_ref.odeint(f, torch.from_numpy(g["y0"]), torch.from_numpy(g["t"]), rtol=float(g["rtol"]),
-                          atol=float(g["atol"]), options=dict(per_trajectory=True, stats=stats))
+                          atol=float(g["atol"]), options=opts)
     assert torch.equal(y.detach(), torch.from_numpy(g["y"]))
     assert np.array_equal(stats.n_accept.numpy(), g["n_accept"])
     assert np.array_equal(stats.n_reject.numpy(), g["n_reject"])
