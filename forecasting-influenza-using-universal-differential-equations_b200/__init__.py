@@ -14,6 +14,7 @@ importable alias of this package.
 """
 from ._lib import UdeError, build, lib  # noqa: F401
 from .funcs import Fa, FaFp, Fp, FuncInfo, UnsupportedFunc, describe_func  # noqa: F401
+from . import dist  # noqa: F401
 from .odeint import odeint, posterior_rows, rk4_grid_tables  # noqa: F401
 
 odeint_adjoint = odeint   # torchdiffeq exports both; the fused backward IS the discrete adjoint

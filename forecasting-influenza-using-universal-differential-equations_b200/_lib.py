@@ -34,6 +34,7 @@ class UdeDesc(C.Structure):
         ("aug_sizes", C.c_int32 * UDE_MAX_LAYERS),
         ("fa_w", C.c_float),
         ("n_groups", C.c_int32),
+        ("flags", C.c_int32),
         ("batch", C.c_int64),
     ]
 

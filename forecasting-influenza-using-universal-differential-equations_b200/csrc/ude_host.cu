@@ -54,7 +54,7 @@ static int check_desc(const UdeDesc* d) {
     return UDE_OK;
 }
 
-static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int& th, int& pk) {
+static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int head_elu, int& th, int& pk) {
     int n_in = P.D;
     for (int i = 0; i < n; ++i) {
         LayerP& Lp = Ls[i];
@@ -73,7 +73,7 @@ static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int&
         pk += Lp.n_out_p * Lp.ldw;
         Lp.b_off = pk;
         pk += Lp.n_out_p;
-        Lp.elu = (i <= n - 3) ? 1 : 0;         // Linear,[ELU,Linear]*,Linear: no ELU before the head
+        Lp.elu = (i <= n - 3 + (head_elu ? 1 : 0)) ? 1 : 0;   // lib/models.py: no ELU before the head
         n_in = Lp.n_out;
     }
 }
@@ -92,8 +92,8 @@ static void base_model(const UdeDesc* d, ModelP& P) {
     P.n_aug = d->n_aug_layers;
     P.fa_w = d->fa_w;
     int th = 0, pk = 0;
-    fill_layers(P, P.rate, P.n_rate, d->rate_sizes, th, pk);
-    fill_layers(P, P.aug, P.n_aug, d->aug_sizes, th, pk);
+    fill_layers(P, P.rate, P.n_rate, d->rate_sizes, d->flags & UDE_FLAG_RATE_HEAD_ELU, th, pk);
+    fill_layers(P, P.aug, P.n_aug, d->aug_sizes, d->flags & UDE_FLAG_AUG_HEAD_ELU, th, pk);
     P.n_theta = th;
     P.n_packed = pk + kPadTail;
 }

@@ -25,7 +25,7 @@ STATUS_TEXT = {1: "max_accepted_steps exceeded (raise options['max_accepted_step
 
 def _opts(rtol, atol, options) -> "_lib.UdeDopri5Opts":
     known = {"first_step", "safety", "ifactor", "dfactor", "max_num_steps", "max_accepted_steps", "return_stats",
-             "per_trajectory", "dtype"}
+             "per_trajectory", "dtype", "process_group"}
     unknown = set(options) - known
     if unknown:
         raise ValueError(f"unexpected dopri5 options {sorted(unknown)}")
@@ -115,6 +115,10 @@ def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
     worst = int(counts[:, 2].max())          # torchdiffeq asserts on these conditions; so do we
     if worst != 0:
         raise _lib.UdeError("fused dopri5: " + STATUS_TEXT.get(worst, f"status {worst}"))
+    group = options.get("process_group", None)
+    if group is not None:
+        from .dist import all_reduce_side
+        side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
     if options.get("return_stats", False):
         return y_out, Dopri5Stats(counts)

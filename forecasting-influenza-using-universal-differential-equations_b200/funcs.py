@@ -139,6 +139,8 @@ class FuncInfo:
     rate_layers: List[nn.Linear]
     aug_layers: List[nn.Linear]
     fa_w: float
+    rate_head_elu: bool = False      # ELU between the last hidden layer and the head (tune_node.py Fp)
+    aug_head_elu: bool = False
 
     def desc(self, batch: int, n_groups: int = 1) -> "_lib.UdeDesc":
         d = _lib.UdeDesc()
@@ -153,6 +155,7 @@ class FuncInfo:
             d.aug_sizes[i] = l.out_features
         d.fa_w = float(self.fa_w)
         d.n_groups = n_groups
+        d.flags = (1 if self.rate_head_elu else 0) | (2 if self.aug_head_elu else 0)
         d.batch = batch
         return d
 
@@ -168,8 +171,9 @@ class UnsupportedFunc(TypeError):
     pass
 
 
-def _linear_chain(net, what: str) -> List[nn.Linear]:
-    """Validate Linear, (ELU, Linear)*, Linear (an optional leading Flatten is skipped)."""
+def _linear_chain(net, what: str):
+    """Validate Linear, (ELU, Linear)*, [ELU,] Linear (an optional leading Flatten is skipped).
+    Returns (linears, elu_before_head)."""
     mods = [m for m in net if not isinstance(m, nn.Flatten)]
     lin: List[nn.Linear] = []
     expect_linear = True
@@ -190,12 +194,15 @@ def _linear_chain(net, what: str) -> List[nn.Linear]:
     # the reference puts an ELU before every hidden Linear except the head: positions must be
     # Linear, ELU, Linear, ..., ELU, Linear, Linear
     n_elu = sum(isinstance(m, nn.ELU) for m in mods)
-    if n_elu != len(lin) - 2 or not isinstance(mods[-1], nn.Linear) or not isinstance(mods[-2], nn.Linear):
-        raise UnsupportedFunc(f"{what}: layer pattern is not Linear,(ELU,Linear)*,Linear")
+    if not isinstance(mods[-1], nn.Linear):
+        raise UnsupportedFunc(f"{what}: the last layer must be Linear")
+    head_elu = isinstance(mods[-2], nn.ELU)                  # nn.Sequential style (tuning/tune_node.py:68-75)
+    if n_elu != len(lin) - (1 if head_elu else 2):
+        raise UnsupportedFunc(f"{what}: layer pattern is not Linear,(ELU,Linear)*,[ELU,]Linear")
     for a, b in zip(lin[:-1], lin[1:]):
         if a.out_features != b.in_features:
             raise UnsupportedFunc(f"{what}: width mismatch")
-    return lin
+    return lin, head_elu
 
 
 def describe_func(func) -> FuncInfo:
@@ -213,16 +220,17 @@ def describe_func(func) -> FuncInfo:
     L = int(func.latent_dim)
     rate: List[nn.Linear] = []
     aug: List[nn.Linear] = []
+    r_elu = a_elu = False
     if kind == "Fp":
-        rate = _linear_chain(func.Fp_net if hasattr(func, "Fp_net") else func.net, "Fp net")
+        rate, r_elu = _linear_chain(func.Fp_net if hasattr(func, "Fp_net") else func.net, "Fp net")
     elif kind == "FaFp":
-        rate = _linear_chain(func.net, "FaFp.net")
-        aug = _linear_chain(func.aug_net, "FaFp.aug_net")
+        rate, r_elu = _linear_chain(func.net, "FaFp.net")
+        aug, a_elu = _linear_chain(func.aug_net, "FaFp.aug_net")
     else:
-        aug = _linear_chain(func.aug_net, "Fa.aug_net")
+        aug, a_elu = _linear_chain(func.aug_net, "Fa.aug_net")
     for lin, head in ((rate, 2 * R), (aug, 3 * R)):
         if lin and (lin[0].in_features != R * L or lin[-1].out_features != head):
             raise UnsupportedFunc("layer widths do not match n_regions * latent_dim / the head size")
     if L < 3:
         raise UnsupportedFunc("latent_dim must be >= 3 (S, I, R)")
-    return FuncInfo(kind, R, L, rate, aug, float(getattr(func, "Fa_w", 1.0)))
+    return FuncInfo(kind, R, L, rate, aug, float(getattr(func, "Fa_w", 1.0)), r_elu, a_elu)

@@ -217,6 +217,7 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         from .dopri5 import dopri5_solve
         return dopri5_solve(func, info, y0, t_cpu, rtol, atol, options)
 
+    group = options.pop("process_group", None)        # fused-path extra: all-reduce the side sums over this group
     unknown = set(options) - {"step_size", "interp", "perturb", "grid_constructor"}
     if unknown:
         raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
@@ -227,5 +228,8 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     theta = info.theta()
     need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
     y_out, side = _Rk4Solve.apply(theta, y0, info, tables, n_steps, int(t.numel()), need_tape)
+    if group is not None:
+        from .dist import all_reduce_side
+        side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
     return y_out

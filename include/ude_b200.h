@@ -79,8 +79,15 @@ typedef struct UdeDesc {
     int32_t aug_sizes[UDE_MAX_LAYERS];    /* out width of each; last must be 3R              */
     float   fa_w;                         /* FaFp.Fa_w (lib/models.py:225,249); runtime      */
     int32_t n_groups;                     /* G independent weight sets (tuning sweeps); >= 1 */
+    int32_t flags;                        /* UDE_FLAG_*                                      */
     int64_t batch;                        /* B, all groups together; B % G == 0              */
 } UdeDesc;
+
+/* lib/models.py puts NO activation between the last hidden Linear and the head
+ * (Linear,[ELU,Linear]*,Linear, :118-124); the local Fp of tuning/tune_node.py:63-76 is an
+ * nn.Sequential with an ELU before the head as well.  These flags select the latter. */
+#define UDE_FLAG_RATE_HEAD_ELU 1
+#define UDE_FLAG_AUG_HEAD_ELU 2
 
 typedef enum UdeMethod { UDE_METHOD_RK4 = 0, UDE_METHOD_DOPRI5 = 1 } UdeMethod;
 

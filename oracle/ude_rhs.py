@@ -28,6 +28,7 @@ class UdeSpec:
     latent_dim: int
     net_sizes: Tuple[int, ...] = ()      # hidden widths of the rate net (beta, gamma head)
     aug_sizes: Tuple[int, ...] = ()      # hidden widths of the augmentation net (Fa head)
+    head_elu: bool = False               # ELU also before the heads (tuning/tune_node.py:63-76 Fp)
 
     def __post_init__(self):
         assert self.kind in ("Fp", "Fa", "FaFp")
@@ -74,12 +75,14 @@ def split_theta(spec: UdeSpec, theta: torch.Tensor):
     return nets
 
 
-def _mlp(layers, u: torch.Tensor) -> torch.Tensor:
+def _mlp(layers, u: torch.Tensor, head_elu: bool = False) -> torch.Tensor:
     """Linear -> [ELU -> Linear]* -> Linear : NO ELU before the head
-    (/root/reference/lib/models.py:118-124)."""
+    (/root/reference/lib/models.py:118-124) unless head_elu (tuning/tune_node.py:68-75)."""
     h = F.linear(u, *layers[0])
     for W, b in layers[1:-1]:
         h = F.linear(F.elu(h), W, b)
+    if head_elu:
+        h = F.elu(h)
     return F.linear(h, *layers[-1])
 
 
@@ -97,12 +100,12 @@ def ude_rhs(spec: UdeSpec, theta: torch.Tensor, x: torch.Tensor, fa_w: float = 1
     dyn = torch.zeros(B, R, 3, dtype=x.dtype, device=x.device)
     p = fa = None
     if spec.has_rate:
-        p = torch.abs(_mlp(nets["rate"], u)).reshape(B, R, 2)   # models.py:135
+        p = torch.abs(_mlp(nets["rate"], u, spec.head_elu)).reshape(B, R, 2)   # models.py:135
         plus_i = p[..., 0] * x[..., 0] * x[..., 1]              # (beta*S)*I, left assoc. (:139)
         minus_i = p[..., 1] * x[..., 1]
         dyn = torch.stack([-plus_i, plus_i - minus_i, minus_i], dim=-1)
     if spec.has_aug:
-        fa = _mlp(nets["aug"], u).reshape(B, R, 3)
+        fa = _mlp(nets["aug"], u, spec.head_elu).reshape(B, R, 3)
         if spec.kind == "Fa":
             dyn = fa                                            # models.py:184 (no Fa_w)
         else:

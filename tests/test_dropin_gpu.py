@@ -1,0 +1,125 @@
+"""Drop-in at the call surface, GPU part: the reference caller's idioms (lib/VAE.py:118-223)
+restated around ``odeint`` — step_size as a 0-dim tensor, t[eval_pts], clear_tracking(),
+posterior() -> kl_p, torch.norm(torch.stack(tracker)), reg_loss over the whole trajectory,
+loss.backward(), optimizer over the ODE-func parameters — once with the fused CUDA path and once
+with the oracle driving the same module class on the CPU; the two must agree."""
+import pytest
+import torch
+from torch.distributions import Normal, kl_divergence
+
+from tests.util import RTOL_PARITY, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _vae_style_step(odeint, ode, mean, std, eps, t, eval_pts, y_true, dec_w, device):
+    """lib/VAE.py:118-140 (__call__) + :142-198 (calc_loss) without the GRU encoder."""
+    n_samples, batch = eps.shape[0], eps.shape[1]
+    ode.clear_tracking()                                                          # VAE.py:121
+    tt = t[eval_pts]
+    step_size = tt[1] - tt[0]                                                     # VAE.py:126 (0-dim tensor)
+    z = eps * std + mean                                                          # models.py:16-24 reparam
+    z = torch.cat([z[..., :2].abs(), (1 - z[..., :2].abs().sum(-1)).unsqueeze(-1), z[..., 2:]], -1)
+    z = z.reshape((n_samples * batch,) + z.shape[2:]) + 1e-5                      # VAE.py:130
+    latent = odeint(ode, z.to(device), tt, method='rk4', options=dict(step_size=step_size))   # VAE.py:137
+    y_pred = (latent[..., :3].reshape(len(eval_pts), n_samples * batch, -1) @ dec_w.to(device))   # Decoder
+    y_pred = y_pred.reshape(-1, n_samples, batch, 1).permute(2, 1, 0, 3)
+    y_std, y_mean = y_pred.std(1), y_pred.mean(1)                                 # train_functions.py:81-90
+    nll = (-Normal(y_mean, y_std).log_prob(y_true.to(device))).mean()
+    prior = Normal(torch.tensor([0.8, 0.55], device=device), torch.tensor([0.2, 0.2], device=device))
+    kl_p = kl_divergence(prior, ode.posterior()).mean()                           # VAE.py:172-177
+    fa_norm = 0.1 * torch.norm(torch.stack(ode.tracker))                          # VAE.py:179-183
+    x = latent[..., :3]                                                           # VAE.py:186
+    reg = 0.1 * (torch.where(x < 0, x.abs(), torch.zeros_like(x)) +
+                 torch.where(x > 1, (1 - x).abs(), torch.zeros_like(x))).sum()
+    loss = nll + kl_p + fa_norm + reg
+    return loss, latent
+
+
+def test_vae_style_training_step_matches_oracle():
+    import ude_b200
+    from oracle import odeint_ref
+    torch.manual_seed(0)
+    R, L, n_samples, batch = 1, 8, 16, 6
+    ref = ude_b200.FaFp(R, L, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    with torch.no_grad():
+        ref.aug_net[-1].weight.mul_(0.05)
+        ref.aug_net[-1].bias.mul_(0.05)
+    fused = ude_b200.FaFp(R, L, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    fused.load_state_dict(ref.state_dict())
+    fused.cuda()
+    mean = torch.tensor([0.9, 0.02, 0, 0, 0, 0, 0.]).expand(batch, R, L - 1).clone()
+    mean = (mean + 0.01 * torch.randn_like(mean))
+    std = torch.tensor([0.1, 0.05, 1, 1, 1, 1, 1.]).expand(batch, R, L - 1) * 0.3
+    eps = torch.randn(n_samples, batch, R, L - 1)
+    t = torch.arange(57, dtype=torch.float32) / 7
+    eval_pts = list(range(0, 57, 7))                       # weekly points of the daily axis (run_ode.py:147-151)
+    y_true = torch.rand(batch, len(eval_pts), 1) * 0.3
+    dec_w = torch.randn(3, 1) * 0.3
+
+    mean_r = mean.clone().requires_grad_(True)
+    loss_r, lat_r = _vae_style_step(odeint_ref.odeint, ref, mean_r, std, eps, t, eval_pts, y_true, dec_w, "cpu")
+    loss_r.backward()
+    mean_f = mean.clone().requires_grad_(True)
+    loss_f, lat_f = _vae_style_step(ude_b200.odeint, fused, mean_f, std, eps, t, eval_pts, y_true, dec_w, "cuda")
+    loss_f.backward()
+
+    assert rel_err(lat_f, lat_r) <= RTOL_PARITY
+    assert abs(float(loss_f) - float(loss_r)) <= 1e-5 * max(1.0, abs(float(loss_r)))
+    assert rel_err(mean_f.grad, mean_r.grad) <= 1e-4       # dL/d(encoder output) through |.| and the sample std
+    for (n, pf), (_, pr) in zip(fused.named_parameters(), ref.named_parameters()):
+        assert rel_err(pf.grad, pr.grad) <= 1e-4, n
+    # an optimizer step over the ODE-func parameters works as in VAE.setup_training (VAE.py:112-116)
+    opt = torch.optim.Adam(fused.parameters(), lr=1e-3)
+    opt.step()
+
+
+def test_tuning_style_interpolated_outputs():
+    """tuning/tune_node.py:192,204: t = linspace(1, tmax, tmax)/7 with step_size=1.0 -> every output
+    is a linear interpolation between weekly grid states; the local Fp class of that script
+    (nn.Sequential `net`, attribute n_region) is recognised by duck typing."""
+    import ude_b200
+    from oracle import odeint_ref
+
+    class Fp(torch.nn.Module):                              # shape of tuning/tune_node.py:63-104
+        def __init__(self, n_region=1, latent_dim=8, nhidden=20):
+            super().__init__()
+            self.n_region, self.latent_dim = n_region, latent_dim
+            self.net = torch.nn.Sequential(
+                torch.nn.Flatten(), torch.nn.Linear(n_region * latent_dim, nhidden), torch.nn.ELU(inplace=True),
+                torch.nn.Linear(nhidden, nhidden), torch.nn.ELU(inplace=True), torch.nn.Linear(nhidden, 2 * n_region))
+            self.params = []
+
+        def forward(self, t, x):
+            mask = (x > 2) | (x < -1)
+            out = torch.abs(self.net(x)).reshape(-1, self.n_region, 2)
+            self.params.append(out)
+            plus, minus = out[..., 0] * x[..., 0] * x[..., 1], out[..., 1] * x[..., 1]
+            res = torch.cat([torch.stack([-plus, plus - minus, minus], -1), torch.zeros_like(x[..., 3:])], -1)
+            res[mask] = 0.0
+            return res
+
+        def clear_tracking(self):
+            self.params = []
+
+    torch.manual_seed(1)
+    ref = Fp(1, 8, 32)
+    info = ude_b200.describe_func(ref)
+    assert info.kind == "Fp" and info.rate_head_elu and [l.out_features for l in info.rate_layers] == [32, 32, 2]
+    fused = Fp(1, 8, 32)
+    fused.load_state_dict(ref.state_dict())
+    fused.cuda()
+    from oracle.ude_rhs import synth_y0
+    z = synth_y0(100, 1, 8, seed=3)
+    t = torch.linspace(1, 56, 56) / 7
+    zr = z.clone().requires_grad_(True)
+    lat_r = odeint_ref.odeint(ref, zr, t, method='rk4', options=dict(step_size=1.0))
+    (lat_r[..., :3] ** 2).sum().backward()
+    zf = z.cuda().requires_grad_(True)
+    lat_f = ude_b200.odeint(fused, zf, t, method='rk4', options=dict(step_size=1.0))
+    (lat_f[..., :3] ** 2).sum().backward()
+    assert lat_f.shape == (56, 100, 1, 8)
+    assert rel_err(lat_f, lat_r) <= RTOL_PARITY
+    assert rel_err(zf.grad, zr.grad) <= RTOL_PARITY
+    for pf, pr in zip(fused.parameters(), ref.parameters()):
+        assert rel_err(pf.grad, pr.grad) <= RTOL_PARITY
