@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     auto eval_into = [&](float* Kdst, int record, int nvalid) {
         rhs_forward_layers(P, Wp, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const bool valid = b < nvalid;
             float f[3];
             SideAcc tmp;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const float* X = smem + P.off_X + (r * L) * TBP + b;
             float v[3] = {X[0], X[TBP], X[2 * TBP]};
             for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = v[c];
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         if (!(a.o.first_step > 0.0)) {
             // ---- torchdiffeq _select_initial_step (order p = 4), per trajectory
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const float* X = smem + P.off_X + (r * L) * TBP + b;
                 float s0 = 0.f, s1 = 0.f;
                 for (int l = 0; l < L; ++l) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             }
             __syncthreads();
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 for (int c = 0; c < 3; ++c)
                     smem[P.off_X + (r * L + c) * TBP + b] =
                         __fadd_rn(SY[(3 * r + c) * TBP + b], __fmul_rn(s_h0[b], SK[(3 * r + c) * TBP + b]));
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             __syncthreads();
             eval_into(SK + 1 * SS, 0, nvalid);                      // f1 = func(t0 + h0, y0 + h0 f0): probe, not tracked
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 float s2 = 0.f;
                 for (int c = 0; c < 3; ++c) {
                     const float y = SY[(3 * r + c) * TBP + b];
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         while (true) {
             // (1) outputs t_out[j] <= t1  (torchdiffeq _advance: step only while next_t > t1)
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 if (b >= nvalid) continue;
                 int jj = s_j[b];
                 const double t0 = s_t0[b], t1 = s_t1[b];
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             // (2) one attempt for every trajectory of the tile (finished ones are masked)
             for (int st = 1; st <= 6; ++st) {
                 for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                    const int r = idx / TB, b = idx - r * TB;
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const float dt = (float)s_dt[b];
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             }
             // (3) error norm, per trajectory
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const float dt = (float)s_dt[b];
                 float s = 0.f;
                 for (int c = 0; c < 3; ++c) {
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             __syncthreads();
             // (4) commit accepted steps: interpolant, tape, FSAL, side channels
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const int o = r * TBP + b;
                 if (s_acc[b]) {
                     const float dt = s_dtold[b];
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         }
         if (a.tape_x) {
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 if (b >= nvalid) continue;
                 for (int c = 0; c < 3; ++c)
                     a.tape_x[((long long)s_nacc[b] * kDopriStages) * stage_sz + (long long)(3 * r + c) * B + b0 + b] =
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     auto vjp_at_x = [&](int ki, int nvalid) {
         rhs_forward_layers(P, Wp, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const int row = (3 * r) * TBP + b;
             float xb[3];
             rhs_tail_vjp(P, smem, r, b, (b < nvalid) && s_act[b], gs, KB[ki * SS + row], KB[ki * SS + row + TBP],
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             __syncthreads();
             // ---- outputs interpolated inside step s: cotangents of the five coefficients
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const bool act = s_act[b] != 0;
                 float ce[3] = {0, 0, 0}, cd[3] = {0, 0, 0}, cc[3] = {0, 0, 0}, cbv[3] = {0, 0, 0}, ca[3] = {0, 0, 0};
                 const float dt = act ? s_dt[b] : 0.f;
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             for (int st = 6; st >= 1; --st) {
                 vjp_at_x(st, nvalid);
                 for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-                    const int r = idx / TB, b = idx - r * TB;
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const bool act = s_act[b] != 0;
                     const float dt = act ? s_dt[b] : 0.f;
                     for (int c = 0; c < 3; ++c) {
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         // ---- the very first evaluation f0 = f(y0): VJP with the carried kbar_1 of step 0
         if (threadIdx.x < TB) s_act[threadIdx.x] = s_nacc[threadIdx.x] > 0;
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             for (int c = 0; c < 3; ++c)
                 smem[P.off_X + (r * L + c) * TBP + b] =
                     (b < nvalid) ? __ldg(a.y0 + ((b0 + b) * R + r) * (long long)L + c) : 0.f;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         __syncthreads();
         vjp_at_x(0, nvalid);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
                 const float* gp = a.g_out + ((b0 + b) * R + r) * (long long)L;
                 float* dst = a.g_y0 + ((b0 + b) * R + r) * (long long)L;

@@ -242,10 +242,14 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
         dofs[q] = Lp.act_off + n * TBP;
     }
     float acc[TN][TM];
+    float accb[TN];                       // bias gradient: sum_b d[n][b] (kept by the units of m-tile 0)
 #pragma unroll
-    for (int q = 0; q < TN; ++q)
+    for (int q = 0; q < TN; ++q) {
+        accb[q] = 0.f;
 #pragma unroll
         for (int p = 0; p < TM; ++p) acc[q][p] = 0.f;
+    }
+    const bool with_bias = mt == 0;       // warp-uniform
 #pragma unroll 2
     for (int k = 0; k < TB; k += 4) {
         float4 av[TM], dv[TN];
@@ -254,14 +258,32 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
 #pragma unroll
         for (int q = 0; q < TN; ++q) dv[q] = ld4(smem + dofs[q] + k);
 #pragma unroll
-        for (int q = 0; q < TN; ++q)
+        for (int p = 0; p < TM; ++p)
 #pragma unroll
-            for (int p = 0; p < TM; ++p) {
-                acc[q][p] = fmaf(av[p].x, dv[q].x, acc[q][p]);
-                acc[q][p] = fmaf(av[p].y, dv[q].y, acc[q][p]);
-                acc[q][p] = fmaf(av[p].z, dv[q].z, acc[q][p]);
-                acc[q][p] = fmaf(av[p].w, dv[q].w, acc[q][p]);
-            }
+            for (int q = 0; q < TN; ++q) acc[q][p] = fmaf(av[p].x, dv[q].x, acc[q][p]);
+#pragma unroll
+        for (int p = 0; p < TM; ++p)
+#pragma unroll
+            for (int q = 0; q < TN; ++q) acc[q][p] = fmaf(av[p].y, dv[q].y, acc[q][p]);
+#pragma unroll
+        for (int p = 0; p < TM; ++p)
+#pragma unroll
+            for (int q = 0; q < TN; ++q) acc[q][p] = fmaf(av[p].z, dv[q].z, acc[q][p]);
+#pragma unroll
+        for (int p = 0; p < TM; ++p)
+#pragma unroll
+            for (int q = 0; q < TN; ++q) acc[q][p] = fmaf(av[p].w, dv[q].w, acc[q][p]);
+        if (with_bias) {
+#pragma unroll
+            for (int q = 0; q < TN; ++q) accb[q] += (dv[q].x + dv[q].y) + (dv[q].z + dv[q].w);
+        }
+    }
+    if (with_bias && tx == 0) {
+#pragma unroll
+        for (int q = 0; q < TN; ++q) {
+            const int n = n0 + ty + 4 * q;
+            if (n < Lp.n_out) G[Lp.b_off + n] += accb[q];
+        }
     }
     float* __restrict__ Gw = G + Lp.w_off;
 #pragma unroll
@@ -289,14 +311,40 @@ __device__ __forceinline__ void db_unit(const LayerP& Lp, const float* __restric
 }
 
 // ----------------------------------------------------------------------------------
+// optional per-phase cycle accounting (-DUDE_PROFILE): block 0, lane 0 of every warp adds
+// (work, wait-at-barrier) cycles per phase id into g_prof[warp][phase][2]
+// ----------------------------------------------------------------------------------
+#ifdef UDE_PROFILE
+__device__ unsigned long long g_prof[kWarps * 32 * 2];
+#define UDE_PROF_DECL long long pr_t0 = clock64(), pr_t1 = 0
+#define UDE_PROF_WORK_DONE() pr_t1 = clock64()
+#define UDE_PROF_PHASE_END(id)                                                                  \
+    do {                                                                                        \
+        long long pr_t2 = clock64();                                                            \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {                                       \
+            g_prof[((threadIdx.x >> 5) * 32 + (id)) * 2 + 0] += (unsigned long long)(pr_t1 - pr_t0); \
+            g_prof[((threadIdx.x >> 5) * 32 + (id)) * 2 + 1] += (unsigned long long)(pr_t2 - pr_t1); \
+        }                                                                                       \
+        pr_t0 = pr_t2;                                                                          \
+    } while (0)
+#define UDE_PROF_RESTART() pr_t0 = clock64()
+#else
+#define UDE_PROF_DECL
+#define UDE_PROF_WORK_DONE()
+#define UDE_PROF_PHASE_END(id)
+#define UDE_PROF_RESTART()
+#endif
+
+// ----------------------------------------------------------------------------------
 // phases (each ends with __syncthreads())
 // ----------------------------------------------------------------------------------
-__device__ __forceinline__ int fwd_units(const LayerP& Lp, int m_tiles) {
-    return m_tiles * ((Lp.n_out_p + 4 * Lp.tn_fwd - 1) / (4 * Lp.tn_fwd));
-}
-__device__ __forceinline__ void fwd_run(const LayerP& Lp, const float* Wp, float* smem, int TBP, int m_tiles, int u,
+// NOTE: no integer divisions on the device: m-tiles per layer are 1 or 2 (mt_shift), the n-tile
+// counts come precomputed from the host (a division is a ~200-cycle dependent chain at the head of
+// every phase of every warp).
+__device__ __forceinline__ int fwd_units(const LayerP& Lp, int mt_shift) { return Lp.fwd_nt << mt_shift; }
+__device__ __forceinline__ void fwd_run(const LayerP& Lp, const float* Wp, float* smem, int TBP, int mt_shift, int u,
                                         int lane) {
-    const int mt = u % m_tiles, nt = u / m_tiles;
+    const int mt = u & ((1 << mt_shift) - 1), nt = u >> mt_shift;
     if (Lp.tn_fwd == 8) fwd_unit<8>(Lp, Wp, smem, TBP, mt, nt, lane);
     else if (Lp.tn_fwd == 4) fwd_unit<4>(Lp, Wp, smem, TBP, mt, nt, lane);
     else fwd_unit<1>(Lp, Wp, smem, TBP, mt, nt, lane);
@@ -305,8 +353,9 @@ __device__ __forceinline__ void fwd_run(const LayerP& Lp, const float* Wp, float
 // All nn.Linear layers of both nets, layer index in lockstep.  Pre: X rows ready and
 // synced.  Post: every ACT buffer ready and synced.
 __device__ __forceinline__ void rhs_forward_layers(const ModelP& P, const float* Wp, float* smem, int warp, int lane) {
-    const int m_tiles = P.TB / 32;
+    const int m_tiles = P.mt_shift;
     const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+    UDE_PROF_DECL;
     for (int li = 0; li < nl; ++li) {
         const int u0 = li < P.n_rate ? fwd_units(P.rate[li], m_tiles) : 0;
         const int u1 = li < P.n_aug ? fwd_units(P.aug[li], m_tiles) : 0;
@@ -314,29 +363,25 @@ __device__ __forceinline__ void rhs_forward_layers(const ModelP& P, const float*
             if (u < u0) fwd_run(P.rate[li], Wp, smem, P.TBP, m_tiles, u, lane);
             else fwd_run(P.aug[li], Wp, smem, P.TBP, m_tiles, u - u0, lane);
         }
+        UDE_PROF_WORK_DONE();
         __syncthreads();
+        UDE_PROF_PHASE_END(li);
     }
 }
 
-__device__ __forceinline__ int dw_units(const LayerP& Lp) {
-    const int mt = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
-    const int nt = (Lp.n_out_p + 4 * Lp.tn_dw - 1) / (4 * Lp.tn_dw);
-    return mt * nt;
-}
+__device__ __forceinline__ int dw_units(const LayerP& Lp) { return Lp.dw_mt * Lp.dw_nt; }
 __device__ __forceinline__ void dw_run(const LayerP& Lp, const float* smem, float* G, int TB, int TBP, int u, int lane) {
-    const int mtiles = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
-    const int mt = u % mtiles, nt = u / mtiles;
+    int mt = u, nt = 0;                                  // u -> (mt, nt) without a division (dw_mt is tiny)
+    while (mt >= Lp.dw_mt) { mt -= Lp.dw_mt; ++nt; }
     if (Lp.tm_dw == 4 && Lp.tn_dw == 4) dw_unit<4, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
     else if (Lp.tm_dw == 1 && Lp.tn_dw == 4) dw_unit<1, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
     else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_unit<4, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
     else dw_unit<1, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
 }
-__device__ __forceinline__ int bwd_units(const LayerP& Lp, int m_tiles) {
-    return m_tiles * ((Lp.n_in_p + 4 * Lp.tn_bwd - 1) / (4 * Lp.tn_bwd));
-}
+__device__ __forceinline__ int bwd_units(const LayerP& Lp, int mt_shift) { return Lp.bwd_nt << mt_shift; }
 __device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, const float* Wp, float* smem, int TBP,
-                                        int gx_off, int m_tiles, int u, int lane) {
-    const int mt = u % m_tiles, nt = u / m_tiles;
+                                        int gx_off, int mt_shift, int u, int lane) {
+    const int mt = u & ((1 << mt_shift) - 1), nt = u >> mt_shift;
     if (Lp.tn_bwd == 8) bwd_unit<8>(Lp, prev, Wp, smem, TBP, gx_off, mt, nt, lane);
     else bwd_unit<4>(Lp, prev, Wp, smem, TBP, gx_off, mt, nt, lane);
 }
@@ -347,8 +392,9 @@ __device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, co
 // GX rows pre-loaded with the direct dL/du.  Post: GX += W0^T delta0 of both nets; G accumulated.
 __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float* Wp, float* smem, float* G, int warp,
                                                     int lane) {
-    const int m_tiles = P.TB / 32;
+    const int m_tiles = P.mt_shift;
     const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+    UDE_PROF_DECL;
     for (int s = 0; s < nl; ++s) {
         const int lr = P.n_rate - 1 - s, la = P.n_aug - 1 - s;
         const LayerP* Lr = lr >= 0 ? &P.rate[lr] : nullptr;
@@ -357,17 +403,14 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
         {
             const int w0 = Lr ? dw_units(*Lr) : 0;
             const int w1 = La ? dw_units(*La) : 0;
-            const int b0 = Lr ? (Lr->n_out + 7) / 8 : 0;
-            const int b1 = La ? (La->n_out + 7) / 8 : 0;
-            const int total = w0 + w1 + b0 + b1;
-            for (int u = warp; u < total; u += kWarps) {
+            for (int u = warp; u < w0 + w1; u += kWarps) {
                 if (u < w0) dw_run(*Lr, smem, G, P.TB, P.TBP, u, lane);
-                else if (u < w0 + w1) dw_run(*La, smem, G, P.TB, P.TBP, u - w0, lane);
-                else if (u < w0 + w1 + b0) db_unit(*Lr, smem, G, P.TB, P.TBP, (u - w0 - w1) * 8, lane);
-                else db_unit(*La, smem, G, P.TB, P.TBP, (u - w0 - w1 - b0) * 8, lane);
+                else dw_run(*La, smem, G, P.TB, P.TBP, u - w0, lane);
             }
         }
+        UDE_PROF_WORK_DONE();
         __syncthreads();
+        UDE_PROF_PHASE_END(8 + 2 * s);
         // ---- phase B: cotangent of this depth's inputs (in place over the previous ACT rows;
         //      layer 0 accumulates into GX, so two layer-0 jobs must not share a phase)
         {
@@ -384,7 +427,9 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
                     bwd_run(*La, nullptr, Wp, smem, P.TBP, P.off_GX, m_tiles, u, lane);
             }
         }
+        UDE_PROF_WORK_DONE();
         __syncthreads();
+        UDE_PROF_PHASE_END(9 + 2 * s);
     }
 }
 

@@ -102,6 +102,8 @@ static void base_model(const UdeDesc* d, ModelP& P) {
 static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int n_state, int n_rbuf, bool bwd) {
     P.TB = TB;
     P.TBP = TB + 4;
+    P.tb_shift = TB == 64 ? 6 : 5;
+    P.mt_shift = TB == 64 ? 1 : 0;
     P.w_in_smem = w_smem;
     P.g_in_smem = g_smem;
     P.n_state = n_state;
@@ -151,6 +153,10 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
             Lp.tn_bwd = (m_tiles * ((Lp.n_in_p + 31) / 32) >= want) ? 8 : 4;
             Lp.tm_dw = Lp.n_in_p > 8 ? 4 : 1;
             Lp.tn_dw = Lp.n_out_p > 4 ? 4 : 1;
+            Lp.fwd_nt = (Lp.n_out_p + 4 * Lp.tn_fwd - 1) / (4 * Lp.tn_fwd);
+            Lp.bwd_nt = (Lp.n_in_p + 4 * Lp.tn_bwd - 1) / (4 * Lp.tn_bwd);
+            Lp.dw_mt = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
+            Lp.dw_nt = (Lp.n_out_p + 4 * Lp.tn_dw - 1) / (4 * Lp.tn_dw);
         }
     }
     return off;
@@ -472,6 +478,17 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     UDE_CUDA(cudaGetLastError());
     return UDE_OK;
 }
+
+#ifdef UDE_PROFILE
+/* debug builds only: read and clear the per-phase cycle counters of CTA 0 */
+int ude_debug_read_prof(unsigned long long* out /*[kWarps*32*2]*/) {
+    UDE_CUDA(cudaDeviceSynchronize());
+    UDE_CUDA(cudaMemcpyFromSymbol(out, g_prof, sizeof(unsigned long long) * kWarps * 32 * 2));
+    static unsigned long long zeros[kWarps * 32 * 2];
+    UDE_CUDA(cudaMemcpyToSymbol(g_prof, zeros, sizeof(zeros)));
+    return UDE_OK;
+}
+#endif
 
 int ude_measure_ffma_tflops(double* tflops, void* stream) {
     if (!tflops) return UDE_ERR_INVALID;

@@ -32,7 +32,8 @@ struct LayerP {
     int tn_fwd;             // n-tile shape of the forward micro-kernel: 8 | 4 | 1 outputs per thread
     int tn_bwd;             // 8 | 4 inputs per thread in the delta micro-kernel
     int tm_dw, tn_dw;       // 4 | 1 each, weight-gradient micro-kernel
-    int pad_;
+    int fwd_nt, bwd_nt;     // n-tiles of the forward / delta micro-kernels (host-computed: no device divisions)
+    int dw_mt, dw_nt;       // m- / n-tiles of the weight-gradient micro-kernel
 };
 
 struct ModelP {
@@ -48,7 +49,9 @@ struct ModelP {
     int n_packed;           // floats of the packed blob incl. kPadTail
     float fa_w;
     // ---- shared-memory plan (float offsets into the dynamic smem arena) ----
-    int TB, TBP;            // trajectories per tile, padded row stride (TB + 4)
+    int TB, TBP;            // trajectories per tile (32 | 64), padded row stride (TB + 4)
+    int tb_shift;           // log2(TB)
+    int mt_shift;           // log2(TB / 32): m-tiles per layer are a power of two
     int w_in_smem;          // packed weights resident in smem
     int g_in_smem;          // (bwd) dtheta accumulators resident in smem
     int off_W, off_G;       // valid when the flags above are set

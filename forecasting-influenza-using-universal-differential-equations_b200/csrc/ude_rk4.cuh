@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_y0_tile(const ModelP& P, float* smem, const
                                              int nvalid) {
     const int TB = P.TB, TBP = P.TBP, L = P.L;
     for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-        const int r = idx / TB, b = idx - r * TB;
+        const int r = idx >> P.tb_shift, b = idx & (TB - 1);
         float* X = smem + P.off_X + (r * L) * TBP + b;
         if (b < nvalid) {
             const float* src = y0 + ((b0 + b) * P.R + r) * (long long)L;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
         __syncthreads();
         // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const float* X = smem + P.off_X + (r * L) * TBP + b;
             float v[3] = {X[0], X[TBP], X[2 * TBP]};
             SY[(3 * r + 0) * TBP + b] = v[0];
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
 #pragma unroll 1
             for (int stage = 0; stage < 4; ++stage) {
                 rhs_forward_layers(P, Wp, smem, warp, lane);
+                UDE_PROF_DECL;
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-                    const int r = idx / TB, b = idx - r * TB;
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const bool valid = b < nvalid;
                     float f[3];
                     rhs_tail(P, smem, r, b, valid, side, f);
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
                     while (jj < a.g.n_out && __ldg(a.g.out_step + jj) == n) ++jj;
                     j_next = jj;
                 }
+                UDE_PROF_WORK_DONE();
                 __syncthreads();
+                UDE_PROF_PHASE_END(6);
             }
             j = j_next;
         }
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                 j_next = jj;
             }
             for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-                const int r = idx / TB, b = idx - r * TB;
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const bool valid = b < nvalid;
                 float lam[3], pend[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -325,9 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
 #pragma unroll 1
             for (int stage = 3; stage >= 0; --stage) {
                 rhs_forward_layers(P, Wp, smem, warp, lane);
+                UDE_PROF_DECL;
                 // ---- tail VJP: cotangent KB[stage] -> head cotangents (in place) + direct dx
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-                    const int r = idx / TB, b = idx - r * TB;
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const int row = (3 * r) * TBP + b;
                     float xb[3];
                     rhs_tail_vjp(P, smem, r, b, b < nvalid, gs, KB[stage * SS + row], KB[stage * SS + row + TBP],
@@ -336,11 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                     gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
                     for (int l = 3; l < L; ++l) gx[l * TBP] = 0.f;
                 }
+                UDE_PROF_WORK_DONE();
                 __syncthreads();
+                UDE_PROF_PHASE_END(20);
                 rhs_backward_layers(P, Wp, smem, G, warp, lane);
+                UDE_PROF_RESTART();
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-                    const int r = idx / TB, b = idx - r * TB;
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const bool valid = b < nvalid;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -365,12 +372,14 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                         CB[xrow] += GX[xrow];
                     }
                 }
+                UDE_PROF_WORK_DONE();
                 __syncthreads();
+                UDE_PROF_PHASE_END(21);
             }
         }
         // ---- output 0 (= y0 itself) and the final store of dL/dy0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
-            const int r = idx / TB, b = idx - r * TB;
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
                 const float* gp = a.g_out + ((b0 + b) * P.R + r) * (long long)L;
                 float* dst = a.g_y0 + ((b0 + b) * P.R + r) * (long long)L;
