@@ -66,10 +66,17 @@ class UdeDopri5Opts(C.Structure):
     ]
 
 
-_SOURCES = ["ude_host.cu", "ude_engine.cuh", "ude_rk4.cuh", "ude_dopri5.cuh", "ude_dopri5_host.inl", "ude_model.h"]
+# translation units (compiled in parallel, linked into one .so) and what each one includes
+_UNIT_DEPS = {
+    "ude_host.cu": ["ude_engine.cuh", "ude_rk4.cuh", "ude_dopri5.cuh", "ude_dopri5_host.inl", "ude_model.h",
+                    "ude_host_common.h", "ude_tc_model.h"],
+    "ude_tc_host.cu": ["ude_engine.cuh", "ude_model.h", "ude_host_common.h", "ude_tc.cuh", "ude_tc_model.h"],
+}
+_UNITS = list(_UNIT_DEPS)
+_SOURCES = _UNITS + sorted({d for deps in _UNIT_DEPS.values() for d in deps})
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off",
 ]
 
 
@@ -81,21 +88,36 @@ def _stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > so_m for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     """Compile csrc/ for sm_100a with nvcc into csrc/libude_b200.so (in-tree)."""
     if not force and not _stale():
         return SO_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO_PATH, os.path.join(CSRC, "ude_host.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    objdir = os.path.join(os.path.dirname(_HERE), "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs, objs = [], []
+    for unit in _UNITS:
+        obj = os.path.join(objdir, unit.replace(".cu", ".o"))
+        deps = [os.path.join(CSRC, d) for d in [unit, *_UNIT_DEPS[unit]]] + [os.path.join(INCLUDE, "ude_b200.h")]
+        if not force and os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+            objs.append(obj)        # object still current (objects live in build/, which is not tracked)
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", "-o", obj, os.path.join(CSRC, unit)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        procs.append((obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + out)
+        if verbose:
+            print(out)
+        objs.append(obj)
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH, *objs],
+                         cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return SO_PATH
 
 
@@ -105,7 +127,7 @@ _lock = threading.Lock()
 EXPORTS = [
     "ude_abi_version", "ude_strerror", "ude_last_cuda_error", "ude_theta_size", "ude_macs_per_eval", "ude_plan",
     "ude_rk4_grid", "ude_rk4_forward", "ude_rk4_backward", "ude_dopri5_forward", "ude_dopri5_backward",
-    "ude_measure_ffma_tflops",
+    "ude_measure_ffma_tflops", "ude_rk4_path",
 ]
 
 
@@ -146,6 +168,8 @@ def lib() -> C.CDLL:
         L.ude_dopri5_backward.restype = C.c_int
         L.ude_dopri5_backward.argtypes = [C.POINTER(UdeDesc), C.POINTER(UdeDopri5Opts), vp, vp, i32, vp, vp, vp, vp, vp,
                                           vp, vp, vp, i64, vp]
+        L.ude_rk4_path.restype = C.c_int
+        L.ude_rk4_path.argtypes = [C.POINTER(UdeDesc)]
         L.ude_measure_ffma_tflops.restype = C.c_int
         L.ude_measure_ffma_tflops.argtypes = [C.POINTER(C.c_double), vp]
         if L.ude_abi_version() != 1:

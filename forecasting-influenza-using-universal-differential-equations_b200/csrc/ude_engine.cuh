@@ -21,6 +21,16 @@
 
 namespace ude {
 
+// fixed time grid + output map of one RK4 solve (built on the host by ude_rk4_grid)
+struct GridTables {
+    int n_steps;
+    const float* dt;        // [n_steps]
+    int n_out;
+    const int* out_step;    // [n_out]  (-1 for output 0)
+    const int* out_kind;    // [n_out]  0 copy y_n, 1 copy y_{n+1}, 2 lerp
+    const float* out_w;     // [n_out]
+};
+
 // ----------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------

@@ -2,33 +2,12 @@
 //
 // Everything here is plain C++/CUDA runtime: no torch, no allocation of persistent
 // memory, no exceptions across the boundary.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <mutex>
-
-#include "../../include/ude_b200.h"
+#include "ude_host_common.h"
 #include "ude_dopri5.cuh"
 #include "ude_rk4.cuh"
+#include "ude_tc_model.h"
 
 namespace ude {
-
-static thread_local char g_cuda_err[256] = "";
-
-static int cuda_fail(cudaError_t e, const char* where) {
-    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
-    return UDE_ERR_CUDA;
-}
-#define UDE_CUDA(call)                                  \
-    do {                                                \
-        cudaError_t e__ = (call);                       \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-    } while (0)
-
-static inline int round4(int x) { return (x + 3) & ~3; }
-static inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------
 // descriptor -> ModelP (layer tables, packed layout).  No GPU needed.
@@ -164,28 +143,6 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
 
 static const int kSmemBudgetBytes = 220 * 1024;     // 227 KB per CTA minus the static part (<= 5.4 KB)
 
-struct DeviceInfo {
-    int ok = 0;
-    int n_sm = 0;
-    int cc_major = 0;
-    int max_smem_optin = 0;
-};
-static DeviceInfo& device_info() {
-    static DeviceInfo info;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return;
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
-        info.n_sm = prop.multiProcessorCount;
-        info.cc_major = prop.major;
-        info.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-        info.ok = 1;
-    });
-    return info;
-}
-
 // Pick (TB, weights in smem, accumulators in smem) for a direction.
 static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, int n_rbuf, bool bwd) {
     base_model(d, P);
@@ -237,12 +194,6 @@ static int grid_size(const ModelP& P, long long B) {
     return (int)(tiles < n_sm ? tiles : n_sm);
 }
 
-template <typename K>
-static int set_smem(K kernel, int bytes) {
-    UDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return UDE_OK;
-}
-
 static long long dopri_tape_x_bytes(const ModelP& P, long long B, int max_steps) {
     return align_up((long long)(max_steps + 1) * kDopriStages * P.Dn * B * 4, 256);
 }
@@ -253,6 +204,17 @@ static int n_state_for(int method, bool bwd) {
 }
 static int n_rbuf_for(int method, bool bwd) { return (method == UDE_METHOD_DOPRI5 && !bwd) ? (int)DF_NRB : 0; }
 
+}  // namespace ude
+
+namespace ude {
+// tensor-core path, defined in ude_tc_host.cu
+int tc_choose(const UdeDesc* d, TcModel& M);
+void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas);
+int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
+               float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
+                const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_theta,
+                void* workspace, int64_t workspace_bytes, cudaStream_t s);
 }  // namespace ude
 
 using namespace ude;
@@ -278,7 +240,7 @@ const char* ude_strerror(int status) {
     }
 }
 
-const char* ude_last_cuda_error(void) { return g_cuda_err; }
+const char* ude_last_cuda_error(void) { return cuda_err_buf(); }
 
 int64_t ude_theta_size(const UdeDesc* desc) {
     if (check_desc(desc) != UDE_OK) return UDE_ERR_INVALID;
@@ -312,6 +274,9 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     const int cold_max = Pf.cold_floats > Pb.cold_floats ? Pf.cold_floats : Pb.cold_floats;
     Workspace w = carve_workspace(nullptr, Pf, n_ctas, cold_max);
     plan->workspace_bytes = w.bytes;
+    TcModel Mt;
+    const int path = method == UDE_METHOD_RK4 ? tc_choose(desc, Mt) : 0;
+    if (path < 0) return path;
     if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up((long long)n_steps * 4 * Pf.Dn * desc->batch * 4, 256);
     else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
     plan->tile_traj = Pb.TB;
@@ -319,7 +284,26 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     plan->smem_bytes_fwd = Pf.smem_floats * 4;
     plan->smem_bytes_bwd = Pb.smem_floats * 4;
     plan->weights_in_smem = Pb.w_in_smem;
+    if (path == 1) {
+        int tc_ctas = 0;
+        long long tc_ws = 0;
+        tc_plan_info(desc, Mt, &tc_ws, &tc_ctas);
+        if (tc_ws > plan->workspace_bytes) plan->workspace_bytes = tc_ws;
+        plan->tile_traj = kTcTile;
+        plan->n_ctas = tc_ctas;
+        plan->smem_bytes_fwd = Mt.smem_bytes_fwd;
+        plan->smem_bytes_bwd = Mt.smem_bytes_bwd;
+        plan->weights_in_smem = 1;
+        plan->reserved = 1;       // tensor path
+    }
     return UDE_OK;
+}
+
+int ude_rk4_path(const UdeDesc* desc) {
+    int st = check_desc(desc);
+    if (st != UDE_OK) return st;
+    TcModel Mt;
+    return tc_choose(desc, Mt);
 }
 
 int ude_rk4_grid(const float* t, int32_t n_t, float step_size, int32_t use_step_size, int32_t cap_steps, float* dt,
@@ -401,6 +385,14 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    {
+        TcModel Mt;
+        const int path = tc_choose(desc, Mt);
+        if (path < 0) return path;
+        if (path == 1)
+            return tc_forward(desc, Mt, theta, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, y_out, tape,
+                              side, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    }
     ModelP P;
     if ((st = choose_plan(desc, P, F_NSTATE, 0, false)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);
@@ -444,6 +436,14 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    {
+        TcModel Mt;
+        const int path = tc_choose(desc, Mt);
+        if (path < 0) return path;
+        if (path == 1)
+            return tc_backward(desc, Mt, theta, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, tape, g_out,
+                               g_side, g_y0, g_theta, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+    }
     ModelP P;
     if ((st = choose_plan(desc, P, B_NSTATE, 0, true)) != UDE_OK) return st;
     const int n_ctas = grid_size(P, desc->batch);

@@ -1,0 +1,59 @@
+// ude_host_common.h — host-side helpers shared by the translation units of libude_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/ude_b200.h"
+
+namespace ude {
+
+inline char* cuda_err_buf() {
+    static thread_local char buf[256] = "";
+    return buf;
+}
+inline int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(cuda_err_buf(), 256, "%s: %s", where, cudaGetErrorString(e));
+    return UDE_ERR_CUDA;
+}
+#define UDE_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return ::ude::cuda_fail(e__, #call); \
+    } while (0)
+
+inline int round4(int x) { return (x + 3) & ~3; }
+inline long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+struct DeviceInfo {
+    int ok = 0;
+    int n_sm = 0;
+    int cc_major = 0;
+    int max_smem_optin = 0;
+};
+inline DeviceInfo& device_info() {
+    static DeviceInfo info;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+        info.n_sm = prop.multiProcessorCount;
+        info.cc_major = prop.major;
+        info.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        info.ok = 1;
+    });
+    return info;
+}
+
+template <typename K>
+inline int set_smem(K kernel, int bytes) {
+    UDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return UDE_OK;
+}
+
+}  // namespace ude

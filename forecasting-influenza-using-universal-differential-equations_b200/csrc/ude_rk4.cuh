@@ -10,15 +10,6 @@
 
 namespace ude {
 
-struct GridTables {
-    int n_steps;
-    const float* dt;        // [n_steps]
-    int n_out;
-    const int* out_step;    // [n_out]  (-1 for output 0)
-    const int* out_kind;    // [n_out]  0 copy y_n, 1 copy y_{n+1}, 2 lerp
-    const float* out_w;     // [n_out]
-};
-
 struct Rk4FwdArgs {
     const float* wpacked;   // [n_packed]
     const float* y0;        // [B,R,L]

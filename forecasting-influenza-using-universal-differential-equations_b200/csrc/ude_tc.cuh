@@ -1,0 +1,987 @@
+// ude_tc.cuh — tcgen05 (5th-gen tensor core) path of the fused RK4 forward / discrete-adjoint
+// kernels (sm_100a).  Used when batch x hidden width makes the MLP layers a real dense
+// contraction (BASELINE config 4: 2^20 trajectories, 64-wide nets); everything else runs the
+// FFMA engine of ude_engine.cuh.
+//
+// Replaces, like ude_rk4.cuh, the Python loop of torchdiffeq's FixedGridODESolver + rk4_alt_step_func
+// driven from /root/reference/lib/VAE.py:137 and the autograd replay of /root/reference/lib/VAE.py:203,
+// with the RHS of /root/reference/lib/models.py:129-146,177-188,230-254 fused in.
+//
+// One CTA = one tile of 128 trajectories for a whole integration.
+//   * a trajectory is TMEM lane t / operand row t; thread t (warps 0-3) also keeps its RK4 state,
+//     adjoint state and side-channel sums in REGISTERS;
+//   * layer products   z_l = a_l W_l^T      : M = 128 traj, N = out, K = in   (A, B from smem)
+//     delta products   dA_l = G_l W_l       : M = 128 traj, N = in,  K = out  (B = same image, MN-major view)
+//     weight gradients dW_l = G_l^T [a_l|1] : M = 64 (out), N = in + 8, K = 128 traj (both MN-major views
+//                                             of the SAME operand buffers the chain uses K-major)
+//   * operands are 3-way bf16 splits (ude_tc_model.h); accumulators are fp32 in TMEM;
+//   * epilogues (bias, ELU, ELU', splits) run thread-per-trajectory straight out of TMEM with
+//     tcgen05.ld 32x32b; the 8 warps split the columns (warp w: lane quarter w&3, column chunks w>>2);
+//   * weight gradients leave TMEM once per RHS evaluation as vector reductions (red.global.add.v4.f32)
+//     into a per-CTA slab; slabs are summed in a fixed order afterwards (deterministic).
+// Descriptor conventions (LBO/SBO of un-swizzled K-major and MN-major operands, M = 64 lane mapping)
+// are pinned on hardware by tools/umma_probe.cu.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ude_engine.cuh"
+#include "ude_tc_model.h"
+
+namespace ude {
+
+struct TcFwdArgs {
+    const uint8_t* blob;    // packed weight images + biases (TcModel::blob_bytes)
+    const float* y0;        // [B,R,L]
+    GridTables g;
+    float* y_out;           // [n_out,B,R,L]
+    float* tape;            // [n_steps,4,3R,B] or null (same format as the FFMA path)
+    double* side_partial;   // [gridDim.x, 8]
+    long long B;
+};
+
+struct TcBwdArgs {
+    const uint8_t* blob;
+    const float* y0;
+    GridTables g;
+    const float* tape;
+    const float* g_out;     // [n_out,B,R,L]
+    const float* g_side;    // [5] or null
+    float* g_y0;            // [B,R,L]
+    float* slabs;           // [gridDim.x, slab_floats], zeroed by the host wrapper
+    long long B;
+};
+
+// ----------------------------------------------------------------------------------
+// tcgen05 primitives
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version; layout type 0 = no swizzle
+    return d;
+}
+// kind::f16, bf16 x bf16 -> fp32
+__device__ __forceinline__ uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// three loads in flight before one wait (the forward accumulator is three column blocks)
+__device__ __forceinline__ void tc_ld16x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[16], float (&b)[16], float (&c)[16]) {
+    uint32_t r[48];
+#define UDE_LD16(T, O)                                                                                              \
+    asm volatile(                                                                                                   \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
+        : "=r"(r[O + 0]), "=r"(r[O + 1]), "=r"(r[O + 2]), "=r"(r[O + 3]), "=r"(r[O + 4]), "=r"(r[O + 5]),          \
+          "=r"(r[O + 6]), "=r"(r[O + 7]), "=r"(r[O + 8]), "=r"(r[O + 9]), "=r"(r[O + 10]), "=r"(r[O + 11]),        \
+          "=r"(r[O + 12]), "=r"(r[O + 13]), "=r"(r[O + 14]), "=r"(r[O + 15])                                       \
+        : "r"(T))
+    UDE_LD16(t0, 0);
+    UDE_LD16(t1, 16);
+    UDE_LD16(t2, 32);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[16 + i]);
+        c[i] = __uint_as_float(r[32 + i]);
+    }
+}
+__device__ __forceinline__ void tc_ld16x2(uint32_t t0, uint32_t t1, float (&a)[16], float (&b)[16]) {
+    uint32_t r[32];
+    UDE_LD16(t0, 0);
+    UDE_LD16(t1, 16);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[16 + i]);
+    }
+}
+#undef UDE_LD16
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(
+            __float_as_uint(v[0])),
+        "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
+        "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ----------------------------------------------------------------------------------
+// 3-way bf16 split of 8 consecutive features -> one 16-byte group per split array
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void split3_store8(const float* v /*8 values*/, uint8_t* p0, uint8_t* p1, uint8_t* p2) {
+    uint32_t h0[4], h1[4], h2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        h0[j] = pack_bf16x2(a, b);
+        const float ra = a - __uint_as_float(h0[j] << 16), rb = b - __uint_as_float(h0[j] & 0xFFFF0000u);
+        h1[j] = pack_bf16x2(ra, rb);
+        const float sa = ra - __uint_as_float(h1[j] << 16), sb = rb - __uint_as_float(h1[j] & 0xFFFF0000u);
+        h2[j] = pack_bf16x2(sa, sb);
+    }
+    *reinterpret_cast<uint4*>(p0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    *reinterpret_cast<uint4*>(p1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+    *reinterpret_cast<uint4*>(p2) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+}
+
+// Placement of the split arrays of an activation of width in_p inside Abuf, in 8-feature groups:
+//   [ a2 | a1 | ones | a3 ]   (the weight-gradient product reads [a2|a1|ones] and [a1|ones] as ONE B operand)
+__device__ __forceinline__ int abuf_group(int s, int in_p) {
+    const int g = in_p >> 3;
+    return s == 0 ? g : (s == 1 ? 0 : 2 * g + 1);
+}
+__device__ __forceinline__ int abuf_ones_group(int in_p) { return 2 * (in_p >> 3); }
+
+// ----------------------------------------------------------------------------------
+// MMA issue (one thread)
+// ----------------------------------------------------------------------------------
+// forward: D[128, 3*out_p] : block0 = a1 w1, block1 = a1 w2 + a2 w1, block2 = a1 w3 + a2 w2 + a3 w1
+__device__ __forceinline__ void tc_issue_forward(const TcLayer& Lp, uint32_t abuf, uint32_t wimg, uint32_t d_addr) {
+    const int ksteps = Lp.in_p >> 4;
+    const uint32_t w_kgrp = 3u * Lp.out_p * 16u;
+    const uint32_t id3 = tc_idesc(128, 3 * Lp.out_p, 0, 0), id2 = tc_idesc(128, 2 * Lp.out_p, 0, 0),
+                   id1 = tc_idesc(128, Lp.out_p, 0, 0);
+    const uint32_t a1 = abuf + abuf_group(0, Lp.in_p) * kTcGroupBytes, a2 = abuf + abuf_group(1, Lp.in_p) * kTcGroupBytes,
+                   a3 = abuf + abuf_group(2, Lp.in_p) * kTcGroupBytes;
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t ao = k * 2 * kTcGroupBytes;
+        const uint64_t wd = tc_desc(wimg + Lp.w_off + k * 2 * w_kgrp, w_kgrp, 128);
+        tc_mma(d_addr, tc_desc(a1 + ao, kTcGroupBytes, 128), wd, id3, k > 0);
+        tc_mma(d_addr + Lp.out_p, tc_desc(a2 + ao, kTcGroupBytes, 128), wd, id2, 1u);
+        tc_mma(d_addr + 2 * Lp.out_p, tc_desc(a3 + ao, kTcGroupBytes, 128), wd, id1, 1u);
+    }
+}
+// delta chain: D[128, in_p] = sum_{i+j<=4} G_i W_j   (W_j: MN-major view of split array j)
+__device__ __forceinline__ void tc_issue_delta(const TcLayer& Lp, uint32_t dbuf, uint32_t wimg, uint32_t d_addr) {
+    const int ksteps = Lp.out_p >> 4;
+    const uint32_t g_arr = (Lp.out_p >> 3) * kTcGroupBytes;
+    const uint32_t w_kgrp = 3u * Lp.out_p * 16u;
+    const uint32_t id = tc_idesc(128, Lp.in_p, 0, 1);
+    uint32_t acc = 0;
+    for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            const int i = (p == 2 || p == 3) ? 1 : (p == 5 ? 2 : 0);
+            const int j = (p == 1 || p == 3) ? 1 : (p == 4 ? 2 : 0);
+            tc_mma(d_addr, tc_desc(dbuf + i * g_arr + k * 2 * kTcGroupBytes, kTcGroupBytes, 128),
+                   tc_desc(wimg + Lp.w_off + j * Lp.out_p * 16 + k * 256, 128, w_kgrp), id, acc);
+            acc = 1u;
+        }
+    }
+}
+// weight gradients: Q[64, 2*in_p + 8]: cols [0,in_p) = (G1+G2) a2, [in_p,2in_p) = (G1+G2+G3) a1 + G1 a3,
+//                                       col 2in_p = sum_t (G1+G2+G3) = bias gradient
+__device__ __forceinline__ void tc_issue_dw(const TcLayer& Lp, uint32_t dbuf, uint32_t abuf, uint32_t q_addr) {
+    const uint32_t g_arr = (Lp.out_p >> 3) * kTcGroupBytes;
+    const int in_p = Lp.in_p;
+    const uint32_t id_full = tc_idesc(64, 2 * in_p + 8, 1, 1), id_a1 = tc_idesc(64, in_p + 8, 1, 1), id_a3 = tc_idesc(64, in_p, 1, 1);
+    const uint32_t b_a1 = abuf + abuf_group(0, in_p) * kTcGroupBytes, b_a3 = abuf + abuf_group(2, in_p) * kTcGroupBytes;
+    for (int k = 0; k < kTcTile / 16; ++k) {
+        const uint32_t ko = k * 256;
+        const uint64_t g1 = tc_desc(dbuf + ko, 128, kTcGroupBytes), g2 = tc_desc(dbuf + g_arr + ko, 128, kTcGroupBytes),
+                       g3 = tc_desc(dbuf + 2 * g_arr + ko, 128, kTcGroupBytes);
+        const uint64_t b_full = tc_desc(abuf + ko, 128, kTcGroupBytes);
+        tc_mma(q_addr, g1, b_full, id_full, k > 0);
+        tc_mma(q_addr, g2, b_full, id_full, 1u);
+        tc_mma(q_addr + in_p, g3, tc_desc(b_a1 + ko, 128, kTcGroupBytes), id_a1, 1u);
+        tc_mma(q_addr + in_p, g1, tc_desc(b_a3 + ko, 128, kTcGroupBytes), id_a3, 1u);
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// per-CTA context
+// ----------------------------------------------------------------------------------
+struct TcCtx {
+    uint8_t* abuf_p;        // operand buffers (generic pointers)
+    uint8_t* dbuf_p;
+    uint32_t abuf, dbuf, wimg;   // shared-space addresses
+    const float* bias;      // bias block in smem
+    uint32_t tmem;          // TMEM base address
+    uint64_t* bar;          // MMA completion barrier
+    uint32_t phase;
+    int q, h, lane, t;      // lane quarter, column half, lane, trajectory row of this thread
+    uint32_t lane_addr;     // (32*q) << 16
+};
+
+__device__ __forceinline__ void tc_sync_issue_begin() {
+    tc_proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+}
+__device__ __forceinline__ void tc_wait_mma(TcCtx& c) {
+    mbar_wait(c.bar, c.phase);
+    c.phase ^= 1u;
+    tc_fence_after();
+}
+
+// write 16 consecutive features [16*chunk, 16*chunk+16) of an activation of width `width` into Abuf
+__device__ __forceinline__ void tc_store_act16(const TcCtx& c, const float (&v)[16], int chunk, int width) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint8_t* base = c.abuf_p + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
+        split3_store8(v + 8 * g, base + abuf_group(0, width) * kTcGroupBytes, base + abuf_group(1, width) * kTcGroupBytes,
+                      base + abuf_group(2, width) * kTcGroupBytes);
+    }
+}
+// write 16 consecutive features of a cotangent of width `width` into Dbuf ([G1 | G2 | G3])
+__device__ __forceinline__ void tc_store_delta16(const TcCtx& c, const float (&v)[16], int chunk, int width) {
+    const size_t arr = (size_t)(width >> 3) * kTcGroupBytes;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint8_t* base = c.dbuf_p + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
+        split3_store8(v + 8 * g, base, base + arr, base + 2 * arr);
+    }
+}
+__device__ __forceinline__ void tc_store_ones(const TcCtx& c, int width) {
+    uint8_t* p = c.abuf_p + (size_t)abuf_ones_group(width) * kTcGroupBytes + c.t * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(0x00003F80u, 0u, 0u, 0u);      // feature 0 = bf16(1.0)
+}
+
+// X (the MLP input u = vec(x), lib/models.py:119 Flatten) -> Abuf as the width-16 input of layer 0
+template <int D0>
+__device__ __forceinline__ void tc_store_x(const TcCtx& c, const float (&x)[D0], bool with_ones) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = i < D0 ? x[i] : 0.f;
+    tc_store_act16(c, v, 0, 16);
+    if (with_ones) tc_store_ones(c, 16);
+}
+
+// ----------------------------------------------------------------------------------
+// forward of one net over the tile.  Pre: X in Abuf (not yet fenced).  Post: head outputs in
+// `head` (threads of warps 0-3), activations saved to TMEM when SAVE.
+// ----------------------------------------------------------------------------------
+template <bool SAVE, int NH>
+__device__ __forceinline__ void tc_net_forward(const TcLayer* Ls, int n_layers, int tm_fwd, TcCtx& c, float (&head)[NH]) {
+    for (int l = 0; l < n_layers; ++l) {
+        const TcLayer& Lp = Ls[l];
+        tc_sync_issue_begin();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            tc_issue_forward(Lp, c.abuf, c.wimg, c.tmem + tm_fwd);
+            tc_commit(c.bar);
+        }
+        tc_wait_mma(c);
+        const uint32_t d0 = c.tmem + c.lane_addr + tm_fwd;
+        const float* bias = c.bias + Lp.b_off;
+        if (l + 1 < n_layers) {
+            for (int ch = c.h; ch < (Lp.out_p >> 4); ch += 2) {
+                float v0[16], v1[16], v2[16];
+                tc_ld16x3(d0 + 16 * ch, d0 + Lp.out_p + 16 * ch, d0 + 2 * Lp.out_p + 16 * ch, v0, v1, v2);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
+                    v0[i + 0] = ((v2[i + 0] + v1[i + 0]) + v0[i + 0]) + b.x;
+                    v0[i + 1] = ((v2[i + 1] + v1[i + 1]) + v0[i + 1]) + b.y;
+                    v0[i + 2] = ((v2[i + 2] + v1[i + 2]) + v0[i + 2]) + b.z;
+                    v0[i + 3] = ((v2[i + 3] + v1[i + 3]) + v0[i + 3]) + b.w;
+                }
+                if (Lp.elu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v0[i] = elu_f(v0[i]);
+                }
+                if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
+                tc_store_act16(c, v0, ch, Lp.out_p);
+            }
+        } else if (c.h == 0) {      // head: out_p == 16, warps 0-3 = trajectory threads
+            float v0[16], v1[16], v2[16];
+            tc_ld16x3(d0, d0 + Lp.out_p, d0 + 2 * Lp.out_p, v0, v1, v2);
+#pragma unroll
+            for (int i = 0; i < NH; ++i) head[i] = ((v2[i] + v1[i]) + v0[i]) + bias[i];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// RHS tail on registers (same arithmetic, same operation order as rhs_tail in ude_engine.cuh):
+//   lib/models.py:135-146 (Fp), :183-188 (Fa), :236-254 (FaFp)
+// ----------------------------------------------------------------------------------
+template <int R, int L>
+__device__ __forceinline__ void tc_rhs_tail(const TcModel& M, const float (&x)[R * L], const float (&o_r)[2 * R],
+                                            const float (&o_a)[3 * R], bool valid, SideAcc& side, float (&f)[3 * R]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float x0 = x[r * L], x1 = x[r * L + 1], x2 = x[r * L + 2];
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+        if (M.n_rate > 0) {
+            const float beta = fabsf(o_r[2 * r]), gamma = fabsf(o_r[2 * r + 1]);
+            const float plus_i = __fmul_rn(__fmul_rn(beta, x0), x1);
+            const float minus_i = __fmul_rn(gamma, x1);
+            f0 = -plus_i;
+            f1 = __fsub_rn(plus_i, minus_i);
+            f2 = minus_i;
+            if (valid) {
+                side.sb += beta; side.sg += gamma;
+                side.sb2 += (double)beta * beta; side.sg2 += (double)gamma * gamma;
+            }
+        }
+        if (M.n_aug > 0) {
+            const float a0 = o_a[3 * r], a1 = o_a[3 * r + 1], a2 = o_a[3 * r + 2];
+            if (M.n_rate > 0) {
+                f0 = __fadd_rn(f0, __fmul_rn(M.fa_w, a0));
+                f1 = __fadd_rn(f1, __fmul_rn(M.fa_w, a1));
+                f2 = __fadd_rn(f2, __fmul_rn(M.fa_w, a2));
+            } else {
+                f0 = a0; f1 = a1; f2 = a2;
+            }
+            if (valid) side.sf2 += (double)a0 * a0 + (double)a1 * a1 + (double)a2 * a2;
+        }
+        if (valid) side.rows += 1;
+        if (x0 > 2.f || x0 < -1.f) f0 = 0.f;
+        if (x1 > 2.f || x1 < -1.f) f1 = 0.f;
+        if (x2 > 2.f || x2 < -1.f) f2 = 0.f;
+        f[3 * r] = f0; f[3 * r + 1] = f1; f[3 * r + 2] = f2;
+    }
+}
+
+// VJP of the tail (same arithmetic as rhs_tail_vjp): g = dL/df -> head cotangents + direct dL/dx
+template <int R, int L>
+__device__ __forceinline__ void tc_rhs_tail_vjp(const TcModel& M, const float (&x)[R * L], const float (&o_r)[2 * R],
+                                                const float (&o_a)[3 * R], bool valid, const float (&gs)[5],
+                                                const float (&g)[3 * R], float (&d_r)[2 * R], float (&d_a)[3 * R],
+                                                float (&xb)[3 * R]) {
+    const float vm = valid ? 1.f : 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float x0 = x[r * L], x1 = x[r * L + 1], x2 = x[r * L + 2];
+        float g0 = g[3 * r], g1 = g[3 * r + 1], g2 = g[3 * r + 2];
+        if (x0 > 2.f || x0 < -1.f) g0 = 0.f;
+        if (x1 > 2.f || x1 < -1.f) g1 = 0.f;
+        if (x2 > 2.f || x2 < -1.f) g2 = 0.f;
+        xb[3 * r] = xb[3 * r + 1] = xb[3 * r + 2] = 0.f;
+        if (M.n_rate > 0) {
+            const float o0 = o_r[2 * r], o1 = o_r[2 * r + 1];
+            const float beta = fabsf(o0), gamma = fabsf(o1);
+            const float gp = g1 - g0, gm = g2 - g1;
+            const float dbeta = gp * x0 * x1 + vm * (gs[0] + 2.f * gs[2] * beta);
+            const float dgamma = gm * x1 + vm * (gs[1] + 2.f * gs[3] * gamma);
+            d_r[2 * r] = (o0 > 0.f ? dbeta : (o0 < 0.f ? -dbeta : 0.f));
+            d_r[2 * r + 1] = (o1 > 0.f ? dgamma : (o1 < 0.f ? -dgamma : 0.f));
+            xb[3 * r] = gp * beta * x1;
+            xb[3 * r + 1] = gp * beta * x0 + gm * gamma;
+        }
+        if (M.n_aug > 0) {
+            const float w = M.n_rate > 0 ? M.fa_w : 1.0f;
+            const float cc = vm * 2.f * gs[4];
+            d_a[3 * r] = w * g0 + cc * o_a[3 * r];
+            d_a[3 * r + 1] = w * g1 + cc * o_a[3 * r + 1];
+            d_a[3 * r + 2] = w * g2 + cc * o_a[3 * r + 2];
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------
+// common kernel prologue / epilogue
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_copy_model(TcModel* dst, const TcModel& src) {
+    const int* s = reinterpret_cast<const int*>(&src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(TcModel) / sizeof(int)); i += kTcThreads) d[i] = s[i];
+}
+
+__device__ __forceinline__ void tc_stage_blob(uint8_t* dst, const uint8_t* src, uint32_t total, uint64_t* bar, uint32_t& phase) {
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, total);
+        uint32_t done = 0;
+        while (done < total) {
+            uint32_t chunk = total - done;
+            if (chunk > 32768u) chunk = 32768u;
+            tma_bulk_g2s(dst + done, src + done, chunk, bar);
+            done += chunk;
+        }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tc_tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tc_tmem_free(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(NCOLS));
+}
+
+// block reduction of the side sums over the 128 trajectory threads (warps 0-3)
+__device__ __forceinline__ void tc_side_reduce(const SideAcc& s, double n_evals, double* scratch /*[8*8]*/, double* out) {
+    double v[6] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int w = 0; w < kTcThreads / 32; ++w) t += scratch[w * 8 + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 6) out[6] = n_evals;
+    if (threadIdx.x == 7) out[7] = 0.0;
+}
+
+// ===================================================================================
+// forward kernel
+// ===================================================================================
+template <int R, int L>
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel Mg, const TcFwdArgs a) {
+    constexpr int D0 = R * L, DN = 3 * R;
+    static_assert(D0 <= 16, "tensor path: R*L <= 16");
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* const smem = tc_smem;
+    __shared__ TcModel M;
+    __shared__ __align__(8) uint64_t wbar;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ double red[8 * 8];
+
+    tc_copy_model(&M, Mg);
+    if (threadIdx.x == 0) {
+        mbar_init(&wbar, 1);
+        mbar_init(&mbar, 1);
+    }
+    if (threadIdx.x < 32) tc_tmem_alloc<256>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t wphase = 0;
+    tc_stage_blob(smem + M.off_w, a.blob, (uint32_t)M.blob_bytes, &wbar, wphase);
+
+    TcCtx c;
+    c.abuf_p = smem + M.off_abuf;
+    c.dbuf_p = smem + M.off_dbuf;
+    c.abuf = smem_u32(smem + M.off_abuf);
+    c.dbuf = smem_u32(smem + M.off_dbuf);
+    c.wimg = smem_u32(smem + M.off_w);
+    c.bias = reinterpret_cast<const float*>(smem + M.off_bias);
+    c.tmem = tmem_slot;
+    c.bar = &mbar;
+    c.phase = 0;
+    const int warp = threadIdx.x >> 5;
+    c.q = warp & 3; c.h = warp >> 2; c.lane = threadIdx.x & 31;
+    c.t = c.q * 32 + c.lane;
+    c.lane_addr = (uint32_t)(c.q * 32) << 16;
+    const bool is_traj = warp < 4;
+
+    SideAcc side;
+    side.clear();
+    const long long B = a.B;
+    const long long n_tiles = (B + kTcTile - 1) / kTcTile;
+    const long long tape_stage = (long long)DN * B;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long b0 = tile * kTcTile;
+        const bool valid = is_traj && (b0 + c.t < B);
+        float x[D0], y[DN], k1[DN], k2[DN], k3[DN];
+#pragma unroll
+        for (int i = 0; i < D0; ++i) x[i] = 0.f;
+        if (valid) {
+            const float* src = a.y0 + (b0 + c.t) * (long long)D0;
+            float* dst = a.y_out + (b0 + c.t) * (long long)D0;          // output 0 = y0 (torchdiffeq: solution[0] = y0)
+            if ((D0 & 3) == 0) {
+#pragma unroll
+                for (int i = 0; i < D0; i += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+                    x[i] = v.x; x[i + 1] = v.y; x[i + 2] = v.z; x[i + 3] = v.w;
+                    st4(dst + i, v);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < D0; ++i) { x[i] = __ldg(src + i); dst[i] = x[i]; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            y[3 * r] = x[r * L]; y[3 * r + 1] = x[r * L + 1]; y[3 * r + 2] = x[r * L + 2];
+        }
+        int j = 1;
+        for (int n = 0; n < a.g.n_steps; ++n) {
+            const float dt = __ldg(a.g.dt + n);
+#pragma unroll 1
+            for (int stage = 0; stage < 4; ++stage) {
+                float o_r[2 * R], o_a[3 * R];
+#pragma unroll
+                for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
+                if (M.n_rate > 0) {
+                    if (is_traj) tc_store_x<D0>(c, x, false);
+                    tc_net_forward<false, 2 * R>(M.rate, M.n_rate, 0, c, o_r);
+                }
+                if (M.n_aug > 0) {
+                    if (is_traj) tc_store_x<D0>(c, x, false);
+                    tc_net_forward<false, 3 * R>(M.aug, M.n_aug, 0, c, o_a);
+                }
+                if (is_traj) {
+                    float f[DN];
+                    tc_rhs_tail<R, L>(M, x, o_r, o_a, valid, side, f);
+                    if (a.tape && valid) {
+                        float* tp = a.tape + (long long)(n * 4 + stage) * tape_stage + b0 + c.t;
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) tp[(long long)(3 * r + cc) * B] = x[r * L + cc];   // stage input
+                    }
+                    float xn[DN];
+#pragma unroll
+                    for (int i = 0; i < DN; ++i) {
+                        if (stage == 0) {
+                            k1[i] = f[i];
+                            xn[i] = __fadd_rn(y[i], __fmul_rn(__fmul_rn(dt, f[i]), 1.0f / 3.0f));
+                        } else if (stage == 1) {
+                            k2[i] = f[i];
+                            xn[i] = __fadd_rn(y[i], __fmul_rn(dt, __fsub_rn(f[i], __fmul_rn(k1[i], 1.0f / 3.0f))));
+                        } else if (stage == 2) {
+                            k3[i] = f[i];
+                            xn[i] = __fadd_rn(y[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[i], k2[i]), f[i])));
+                        } else {
+                            const float s = __fadd_rn(__fadd_rn(k1[i], __fmul_rn(3.0f, __fadd_rn(k2[i], k3[i]))), f[i]);
+                            xn[i] = __fadd_rn(y[i], __fmul_rn(__fmul_rn(s, dt), 0.125f));
+                        }
+                    }
+                    if (stage == 3) {
+                        // outputs that fall into (t_n, t_{n+1}]  (FixedGridODESolver.integrate)
+                        int jj = j;
+                        while (jj < a.g.n_out && __ldg(a.g.out_step + jj) == n) {
+                            if (valid) {
+                                const int kind = __ldg(a.g.out_kind + jj);
+                                const float w = __ldg(a.g.out_w + jj);
+                                float row[D0];
+#pragma unroll
+                                for (int i = 0; i < D0; ++i) row[i] = x[i];
+#pragma unroll
+                                for (int r = 0; r < R; ++r)
+#pragma unroll
+                                    for (int cc = 0; cc < 3; ++cc) {
+                                        const float yy = y[3 * r + cc], xx = xn[3 * r + cc];
+                                        row[r * L + cc] = kind == 1 ? xx : (kind == 0 ? yy : __fadd_rn(yy, __fmul_rn(w, __fsub_rn(xx, yy))));
+                                    }
+                                float* dst = a.y_out + ((long long)jj * B + b0 + c.t) * (long long)D0;
+                                if ((D0 & 3) == 0) {
+#pragma unroll
+                                    for (int i = 0; i < D0; i += 4) st4(dst + i, make_float4(row[i], row[i + 1], row[i + 2], row[i + 3]));
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < D0; ++i) dst[i] = row[i];
+                                }
+                            }
+                            ++jj;
+                        }
+                        j = jj;
+#pragma unroll
+                        for (int i = 0; i < DN; ++i) y[i] = xn[i];
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        x[r * L] = xn[3 * r]; x[r * L + 1] = xn[3 * r + 1]; x[r * L + 2] = xn[3 * r + 2];
+                    }
+                }
+            }
+        }
+    }
+    tc_side_reduce(side, 4.0 * a.g.n_steps, red, a.side_partial + (long long)blockIdx.x * 8);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc_tmem_free<256>(c.tmem);
+}
+
+// ===================================================================================
+// backward kernel (discrete adjoint)
+// ===================================================================================
+// Sweep one net backwards over the tile.  Pre: G_head in `g_head` (trajectory threads), saved
+// activations in TMEM, x in registers.  Post: dx[0..D0) += W_0^T G_0 (trajectory threads), weight and
+// bias gradients added to the CTA slab.
+template <int D0, int NH>
+__device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer* Ls, int n_layers, TcCtx& c,
+                                                const float (&g_head)[NH], const float (&x)[D0], float* slab,
+                                                float (&dx)[D0], bool is_traj) {
+    // ---- operands of the head phase: G_{n-1} (width 16, zero padded) and a_{n-1}
+    {
+        const TcLayer& Lh = Ls[n_layers - 1];
+        if (is_traj) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = i < NH ? g_head[i] : 0.f;
+            tc_store_delta16(c, v, 0, 16);
+        }
+        const TcLayer& Lprev = Ls[n_layers - 2];
+        for (int ch = c.h; ch < (Lh.in_p >> 4); ch += 2) {
+            float v[16];
+            tc_ld16(c.tmem + c.lane_addr + Lprev.save_col + 16 * ch, v);
+            tc_store_act16(c, v, ch, Lh.in_p);
+        }
+        if (c.h == 0) tc_store_ones(c, Lh.in_p);
+    }
+    for (int l = n_layers - 1; l >= 0; --l) {
+        const TcLayer& Lp = Ls[l];
+        tc_sync_issue_begin();
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            tc_issue_delta(Lp, c.dbuf, c.wimg, c.tmem + M.tm_dd);
+            tc_issue_dw(Lp, c.dbuf, c.abuf, c.tmem + M.tm_q);
+            tc_commit(c.bar);
+        }
+        tc_wait_mma(c);
+        // ---- weight / bias gradients of layer l: TMEM -> per-CTA slab (rows 16q..16q+15 live in lanes 0..15)
+        {
+            const int m = 16 * c.q + c.lane;
+            const bool act = c.lane < 16 && m < Lp.out;
+            const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
+            float* row = slab + Lp.slab_off + (size_t)m * (Lp.in_p + 8);
+            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += 2) {
+                float u[16], v[16];
+                tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        red_add_v4(row + 16 * ch + i, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
+                }
+            }
+            if (c.h == 0) {
+                float u[16];
+                tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
+                if (act) atomicAdd(row + Lp.in_p, u[0]);
+            }
+        }
+        if (l >= 1) {
+            // ---- G_{l-1} = dA_l * ELU'(a_l)   and   a_{l-1} for the next phase
+            const TcLayer& Lq = Ls[l - 1];
+            const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
+            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += 2) {
+                float d[16], s[16];
+                tc_ld16x2(dd + 16 * ch, c.tmem + c.lane_addr + Lq.save_col + 16 * ch, d, s);
+                if (Lq.elu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(s[i]);
+                }
+                tc_store_delta16(c, d, ch, Lp.in_p);
+            }
+            if (l >= 2) {
+                const TcLayer& Lr = Ls[l - 2];
+                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += 2) {
+                    float v[16];
+                    tc_ld16(c.tmem + c.lane_addr + Lr.save_col + 16 * ch, v);
+                    tc_store_act16(c, v, ch, Lq.in_p);
+                }
+                if (c.h == 0) tc_store_ones(c, Lq.in_p);
+            } else if (is_traj) {
+                tc_store_x<D0>(c, x, true);
+            }
+        } else if (is_traj) {
+            float d[16];
+            tc_ld16(c.tmem + c.lane_addr + M.tm_dd, d);
+#pragma unroll
+            for (int i = 0; i < D0; ++i) dx[i] += d[i];
+        }
+    }
+}
+
+template <int R, int L>
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel Mg, const TcBwdArgs a) {
+    constexpr int D0 = R * L, DN = 3 * R;
+    static_assert(D0 <= 16, "tensor path: R*L <= 16");
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    uint8_t* const smem = tc_smem;
+    __shared__ TcModel M;
+    __shared__ __align__(8) uint64_t wbar;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+
+    tc_copy_model(&M, Mg);
+    if (threadIdx.x == 0) {
+        mbar_init(&wbar, 1);
+        mbar_init(&mbar, 1);
+    }
+    if (threadIdx.x < 32) tc_tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t wphase = 0;
+    tc_stage_blob(smem + M.off_w, a.blob, (uint32_t)M.blob_bytes, &wbar, wphase);
+
+    TcCtx c;
+    c.abuf_p = smem + M.off_abuf;
+    c.dbuf_p = smem + M.off_dbuf;
+    c.abuf = smem_u32(smem + M.off_abuf);
+    c.dbuf = smem_u32(smem + M.off_dbuf);
+    c.wimg = smem_u32(smem + M.off_w);
+    c.bias = reinterpret_cast<const float*>(smem + M.off_bias);
+    c.tmem = tmem_slot;
+    c.bar = &mbar;
+    c.phase = 0;
+    const int warp = threadIdx.x >> 5;
+    c.q = warp & 3; c.h = warp >> 2; c.lane = threadIdx.x & 31;
+    c.t = c.q * 32 + c.lane;
+    c.lane_addr = (uint32_t)(c.q * 32) << 16;
+    const bool is_traj = warp < 4;
+
+    // the operand buffers feed MN-major (K = trajectory) products: start from finite contents
+    for (int i = threadIdx.x; i < (M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
+        reinterpret_cast<uint4*>(smem + M.off_abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (a.g_side) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
+    }
+    float* slab = a.slabs + (long long)blockIdx.x * M.slab_floats;
+
+    const long long B = a.B;
+    const long long n_tiles = (B + kTcTile - 1) / kTcTile;
+    const long long tape_stage = (long long)DN * B;
+    const int n_steps = a.g.n_steps;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long b0 = tile * kTcTile;
+        const bool valid = is_traj && (b0 + c.t < B);
+        float x[D0], lam[DN], cb[D0], kb[4][DN];
+#pragma unroll
+        for (int i = 0; i < D0; ++i) { x[i] = 0.f; cb[i] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < DN; ++i) lam[i] = 0.f;
+        if (valid) {
+            const float* src = a.y0 + (b0 + c.t) * (long long)D0;      // constants of x; dynamic comps come from the tape
+#pragma unroll
+            for (int i = 0; i < D0; ++i) x[i] = __ldg(src + i);
+        }
+        int j = a.g.n_out - 1;
+        for (int n = n_steps - 1; n >= 0; --n) {
+            const float dt = __ldg(a.g.dt + n);
+            // ---- outputs tied to step n feed lambda_{n+1} (and, for copies of y_n / lerps, lambda_n)
+            {
+                float pend[DN];
+#pragma unroll
+                for (int i = 0; i < DN; ++i) pend[i] = 0.f;
+                int jj = j;
+                while (jj >= 1 && __ldg(a.g.out_step + jj) == n) {
+                    if (valid) {
+                        const int kind = __ldg(a.g.out_kind + jj);
+                        const float w = __ldg(a.g.out_w + jj);
+                        const float* gp = a.g_out + ((long long)jj * B + b0 + c.t) * (long long)D0;
+                        float gr[D0];
+                        if ((D0 & 3) == 0) {
+#pragma unroll
+                            for (int i = 0; i < D0; i += 4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4*>(gp + i));
+                                gr[i] = v.x; gr[i + 1] = v.y; gr[i + 2] = v.z; gr[i + 3] = v.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < D0; ++i) gr[i] = __ldg(gp + i);
+                        }
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+#pragma unroll
+                            for (int l = 0; l < L; ++l) {
+                                const float g = gr[r * L + l];
+                                if (l < 3) {
+                                    if (kind == 1) lam[3 * r + l] += g;
+                                    else if (kind == 0) pend[3 * r + l] += g;
+                                    else { const float sg = w * g; lam[3 * r + l] += sg; pend[3 * r + l] += g - sg; }
+                                } else {
+                                    cb[r * L + l] += g;
+                                }
+                            }
+                    }
+                    --jj;
+                }
+                j = jj;
+                const float c8 = dt * 0.125f;
+#pragma unroll
+                for (int i = 0; i < DN; ++i) {
+                    const float base = lam[i] * c8;
+                    kb[0][i] = base; kb[1][i] = 3.f * base; kb[2][i] = 3.f * base; kb[3][i] = base;
+                    lam[i] = lam[i] + pend[i];        // becomes lambda_n once the four stage VJPs are added
+                }
+            }
+#pragma unroll 1
+            for (int stage = 3; stage >= 0; --stage) {
+                // ---- stage input from the tape
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        x[r * L + cc] = valid ? __ldg(a.tape + (long long)(n * 4 + stage) * tape_stage + (long long)(3 * r + cc) * B + b0 + c.t) : 0.f;
+                // ---- recompute the stage activations
+                float o_r[2 * R], o_a[3 * R];
+#pragma unroll
+                for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
+                if (M.n_rate > 0) {
+                    if (is_traj) tc_store_x<D0>(c, x, false);
+                    tc_net_forward<true, 2 * R>(M.rate, M.n_rate, M.tm_fwd, c, o_r);
+                }
+                if (M.n_aug > 0) {
+                    if (is_traj) tc_store_x<D0>(c, x, false);
+                    tc_net_forward<true, 3 * R>(M.aug, M.n_aug, M.tm_fwd, c, o_a);
+                }
+                // ---- tail VJP
+                float d_r[2 * R], d_a[3 * R], xb[DN], dx[D0];
+#pragma unroll
+                for (int i = 0; i < 2 * R; ++i) d_r[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3 * R; ++i) d_a[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < DN; ++i) xb[i] = 0.f;
+#pragma unroll
+                for (int i = 0; i < D0; ++i) dx[i] = 0.f;
+                if (is_traj) {
+                    float g[DN];
+#pragma unroll
+                    for (int i = 0; i < DN; ++i) g[i] = stage == 3 ? kb[3][i] : (stage == 2 ? kb[2][i] : (stage == 1 ? kb[1][i] : kb[0][i]));
+                    tc_rhs_tail_vjp<R, L>(M, x, o_r, o_a, valid, gs, g, d_r, d_a, xb);
+                }
+                if (M.n_rate > 0) tc_net_backward<D0, 2 * R>(M, M.rate, M.n_rate, c, d_r, x, slab, dx, is_traj);
+                if (M.n_aug > 0) tc_net_backward<D0, 3 * R>(M, M.aug, M.n_aug, c, d_a, x, slab, dx, is_traj);
+                // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
+                if (is_traj) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const int i = 3 * r + cc;
+                            const float xbar = xb[i] + dx[r * L + cc];
+                            const float u = xbar * dt;
+                            if (stage == 3) {            // x4 = y + dt*((k1 - k2) + k3)
+                                kb[2][i] += u; kb[0][i] += u; kb[1][i] -= u;
+                            } else if (stage == 2) {     // x3 = y + dt*(k2 - k1/3)
+                                kb[1][i] += u; kb[0][i] -= u * (1.0f / 3.0f);
+                            } else if (stage == 1) {     // x2 = y + (dt*k1)/3
+                                kb[0][i] += (xbar * (1.0f / 3.0f)) * dt;
+                            }
+                            lam[i] += xbar;
+                        }
+#pragma unroll
+                        for (int l = 3; l < L; ++l) cb[r * L + l] += dx[r * L + l];
+                    }
+                }
+            }
+        }
+        // ---- output 0 (= y0 itself) and the final store of dL/dy0
+        if (valid) {
+            const float* gp = a.g_out + (b0 + c.t) * (long long)D0;
+            float* dst = a.g_y0 + (b0 + c.t) * (long long)D0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int l = 0; l < L; ++l) {
+                    const float g = __ldg(gp + r * L + l);
+                    dst[r * L + l] = (l < 3 ? lam[3 * r + l] : cb[r * L + l]) + g;
+                }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tc_tmem_free<512>(c.tmem);
+}
+
+// ===================================================================================
+// utility kernels of the tensor path
+// ===================================================================================
+// theta (PyTorch layout) -> weight images (bf16 x3, zero padded) + bias block.  One block per layer.
+__global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* __restrict__ theta, uint8_t* __restrict__ blob) {
+    const int li = blockIdx.x;
+    const TcLayer& Lp = li < M.n_rate ? M.rate[li] : M.aug[li - M.n_rate];
+    uint16_t* img = reinterpret_cast<uint16_t*>(blob + Lp.w_off);
+    const int total = Lp.in_p * Lp.out_p;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int n = idx / Lp.in_p, k = idx - n * Lp.in_p;
+        const float w = (n < Lp.out && k < Lp.in) ? theta[Lp.th_w + n * Lp.in + k] : 0.f;
+        float r = w;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(r);
+            r -= __bfloat162float(hb);
+            // [k/8][s][n][k%8]
+            img[((size_t)(k >> 3) * 3 + s) * Lp.out_p * 8 + (size_t)n * 8 + (k & 7)] = *reinterpret_cast<const uint16_t*>(&hb);
+        }
+    }
+    float* bias = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.b_off;
+    for (int n = threadIdx.x; n < Lp.out_p; n += blockDim.x) bias[n] = n < Lp.out ? theta[Lp.th_b + n] : 0.f;
+}
+
+// side[0..7] = sum over CTA partials (fixed order)
+__global__ void tc_reduce_side_kernel(const double* __restrict__ partial, int n_parts, double* __restrict__ side) {
+    const int i = threadIdx.x;
+    if (i >= 8) return;
+    double s = 0.0;
+    for (int cidx = 0; cidx < n_parts; ++cidx) s += partial[cidx * 8 + i];
+    if (i == 6) s = partial[6];   // RHS evaluations per trajectory: identical in every CTA
+    side[i] = s;
+}
+
+// g_theta[e] = sum over CTA slabs (fixed order => deterministic)
+__global__ void tc_reduce_dtheta_kernel(const __grid_constant__ TcModel M, const float* __restrict__ slabs, int n_slabs,
+                                        float* __restrict__ g_theta) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M.n_theta) return;
+    int sidx = -1;
+    const int nl = M.n_rate + M.n_aug;
+    for (int li = 0; li < nl; ++li) {
+        const TcLayer& Lp = li < M.n_rate ? M.rate[li] : M.aug[li - M.n_rate];
+        if (e >= Lp.th_w && e < Lp.th_w + Lp.in * Lp.out) {
+            const int k = e - Lp.th_w;
+            const int row = k / Lp.in, col = k - row * Lp.in;
+            sidx = Lp.slab_off + row * (Lp.in_p + 8) + col;
+            break;
+        }
+        if (e >= Lp.th_b && e < Lp.th_b + Lp.out) {
+            sidx = Lp.slab_off + (e - Lp.th_b) * (Lp.in_p + 8) + Lp.in_p;
+            break;
+        }
+    }
+    float s = 0.f;
+    if (sidx >= 0)
+        for (int cidx = 0; cidx < n_slabs; ++cidx) s += slabs[(size_t)cidx * M.slab_floats + sidx];
+    g_theta[e] = s;
+}
+
+}  // namespace ude

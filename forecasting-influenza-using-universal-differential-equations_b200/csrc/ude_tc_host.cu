@@ -1,0 +1,207 @@
+// ude_tc_host.cu — host-side planning and launch of the tcgen05 path (own translation unit: the
+// two kernel families compile in parallel).
+#include "ude_host_common.h"
+#include "ude_tc.cuh"
+
+namespace ude {
+
+static inline int round16(int x) { return (x + 15) & ~15; }
+
+// Trajectories from which the layer products count as "real dense contractions" (BASELINE north_star):
+// below this the 128-trajectory tiles cannot fill the 148 SMs and the FFMA engine (32/64-trajectory
+// tiles) is the better fit.
+static const long long kTcMinBatch = 148LL * kTcTile;
+static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit minus the static part
+
+static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes, int head_elu, int& th) {
+    if (n == 0) return true;
+    if (n < 2 || n > kTcMaxLayers) return false;
+    int n_in = M.D0, in_p = M.D0_p;
+    for (int i = 0; i < n; ++i) {
+        TcLayer& Lp = Ls[i];
+        memset(&Lp, 0, sizeof(Lp));
+        Lp.in = n_in;
+        Lp.out = sizes[i];
+        Lp.in_p = in_p;
+        Lp.out_p = round16(Lp.out);
+        if (i == n - 1 && Lp.out_p != 16) return false;          // heads: 2R / 3R <= 16
+        if (Lp.out_p > 64 || Lp.in_p > 64) return false;         // accumulators: 3*out_p columns, M = 64 rows of dW
+        Lp.elu = (i <= n - 3 + (head_elu ? 1 : 0)) ? 1 : 0;       // lib/models.py: no ELU before the head
+        Lp.th_w = th;
+        th += Lp.in * Lp.out;
+        Lp.th_b = th;
+        th += Lp.out;
+        Lp.w_off = M.w_bytes;
+        M.w_bytes += Lp.in_p * Lp.out_p * 6;
+        Lp.b_off = M.n_bias;
+        M.n_bias += Lp.out_p;
+        Lp.save_col = -1;
+        if (i < n - 1) {
+            Lp.save_col = M.tm_save;
+            M.tm_save += Lp.out_p;
+        }
+        Lp.slab_off = M.slab_floats;
+        M.slab_floats += Lp.out_p * (Lp.in_p + 8);
+        n_in = Lp.out;
+        in_p = Lp.out_p;
+    }
+    return true;
+}
+
+// descriptor -> TcModel; false when the tensor path does not cover the configuration
+static bool tc_build_model(const UdeDesc* d, TcModel& M) {
+    memset(&M, 0, sizeof(M));
+    if (d->n_groups != 1) return false;
+    M.kind = d->kind;
+    M.R = d->n_regions;
+    M.L = d->latent_dim;
+    M.D0 = M.R * M.L;
+    M.D0_p = 16;
+    if (!(M.R == 1 && (M.L == 4 || M.L == 8 || M.L == 16))) return false;      // instantiated (R, L) pairs
+    M.n_rate = d->n_rate_layers;
+    M.n_aug = d->n_aug_layers;
+    M.fa_w = d->fa_w;
+    int th = 0;
+    if (!tc_fill_layers(M, M.rate, M.n_rate, d->rate_sizes, d->flags & UDE_FLAG_RATE_HEAD_ELU, th)) return false;
+    if (!tc_fill_layers(M, M.aug, M.n_aug, d->aug_sizes, d->flags & UDE_FLAG_AUG_HEAD_ELU, th)) return false;
+    M.n_theta = th;
+    M.blob_bytes = (int)align_up(M.w_bytes + 4 * M.n_bias, 16);
+    int max_in = 16, max_out = 16, dcap = 0;
+    for (int net = 0; net < 2; ++net) {
+        const TcLayer* Ls = net == 0 ? M.rate : M.aug;
+        const int n = net == 0 ? M.n_rate : M.n_aug;
+        for (int i = 0; i < n; ++i) {
+            if (Ls[i].in_p > max_in) max_in = Ls[i].in_p;
+            if (Ls[i].out_p > max_out) max_out = Ls[i].out_p;
+            const int g = Ls[i].out_p / 8;
+            const int need = 2 * g + (g > 8 ? g : 8);        // the M = 64 view of the third split array reads 8 groups
+            if (need > dcap) dcap = need;
+        }
+    }
+    // tensor memory (columns)
+    M.tm_q = M.tm_save;
+    M.tm_q_cols = 2 * max_in + 16;
+    M.tm_dd = M.tm_q + M.tm_q_cols;
+    M.tm_fwd = M.tm_q;
+    const int bwd_cols = (M.tm_dd + max_in) > (M.tm_fwd + 3 * max_out) ? (M.tm_dd + max_in) : (M.tm_fwd + 3 * max_out);
+    if (bwd_cols > 512 || 3 * max_out > 256) return false;
+    M.tm_cols_fwd = 256;
+    M.tm_cols_bwd = 512;
+    // shared memory
+    M.off_w = 0;
+    M.off_bias = M.w_bytes;
+    M.off_abuf = (int)align_up(M.blob_bytes, 1024);
+    M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;
+    M.off_dbuf = M.off_abuf + M.abuf_bytes;
+    M.dbuf_bytes = dcap * kTcGroupBytes;
+    M.smem_bytes_fwd = M.off_abuf + M.abuf_bytes;
+    M.smem_bytes_bwd = M.off_dbuf + M.dbuf_bytes;
+    if (M.smem_bytes_bwd > kTcSmemLimit) return false;
+    return true;
+}
+
+// 0 = FFMA engine, 1 = tensor path, negative = error
+int tc_choose(const UdeDesc* d, TcModel& M) {
+    const bool ok = tc_build_model(d, M);
+    if (d->flags & UDE_FLAG_FORCE_TENSOR) return ok ? 1 : UDE_ERR_UNSUPPORTED;
+    if (d->flags & UDE_FLAG_FORCE_FFMA) return 0;
+    return (ok && d->batch >= kTcMinBatch) ? 1 : 0;
+}
+
+struct TcWorkspace {
+    uint8_t* blob;
+    double* side_partial;
+    float* slabs;
+    long long bytes;
+};
+static TcWorkspace tc_carve(void* base, const TcModel& M, int n_ctas) {
+    TcWorkspace w;
+    long long off = 0;
+    w.blob = reinterpret_cast<uint8_t*>(base) + off;
+    off = align_up(off + M.blob_bytes, 256);
+    w.side_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * 8 * 8, 256);
+    w.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * M.slab_floats * 4, 256);
+    w.bytes = off;
+    return w;
+}
+static int tc_grid(long long B) {
+    const DeviceInfo& di = device_info();
+    const long long tiles = (B + kTcTile - 1) / kTcTile;
+    const int n_sm = di.ok ? di.n_sm : 148;
+    return (int)(tiles < n_sm ? tiles : n_sm);
+}
+
+int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
+                      float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    const int n_ctas = tc_grid(desc->batch);
+    TcWorkspace w = tc_carve(workspace, M, n_ctas);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
+    UDE_CUDA(cudaGetLastError());
+    TcFwdArgs a;
+    a.blob = w.blob;
+    a.y0 = y0;
+    a.g = g;
+    a.y_out = y_out;
+    a.tape = tape;
+    a.side_partial = w.side_partial;
+    a.B = desc->batch;
+    int st;
+#define UDE_TC_FWD(RR, LL)                                                                     \
+    do {                                                                                       \
+        if ((st = set_smem(rk4_fwd_tc_kernel<RR, LL>, M.smem_bytes_fwd)) != UDE_OK) return st; \
+        rk4_fwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_fwd, s>>>(M, a);          \
+    } while (0)
+    if (M.L == 8) UDE_TC_FWD(1, 8);
+    else if (M.L == 4) UDE_TC_FWD(1, 4);
+    else UDE_TC_FWD(1, 16);
+#undef UDE_TC_FWD
+    UDE_CUDA(cudaGetLastError());
+    tc_reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
+                       const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_theta,
+                       void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    const int n_ctas = tc_grid(desc->batch);
+    TcWorkspace w = tc_carve(workspace, M, n_ctas);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
+    UDE_CUDA(cudaGetLastError());
+    UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)n_ctas * M.slab_floats * 4, s));
+    TcBwdArgs a;
+    a.blob = w.blob;
+    a.y0 = y0;
+    a.g = g;
+    a.tape = tape;
+    a.g_out = g_out;
+    a.g_side = g_side;
+    a.g_y0 = g_y0;
+    a.slabs = w.slabs;
+    a.B = desc->batch;
+    int st;
+#define UDE_TC_BWD(RR, LL)                                                                     \
+    do {                                                                                       \
+        if ((st = set_smem(rk4_bwd_tc_kernel<RR, LL>, M.smem_bytes_bwd)) != UDE_OK) return st; \
+        rk4_bwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_bwd, s>>>(M, a);          \
+    } while (0)
+    if (M.L == 8) UDE_TC_BWD(1, 8);
+    else if (M.L == 4) UDE_TC_BWD(1, 4);
+    else UDE_TC_BWD(1, 16);
+#undef UDE_TC_BWD
+    UDE_CUDA(cudaGetLastError());
+    tc_reduce_dtheta_kernel<<<(M.n_theta + 255) / 256, 256, 0, s>>>(M, w.slabs, n_ctas, g_theta);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas) {
+    *n_ctas = tc_grid(d->batch);
+    *workspace_bytes = tc_carve(nullptr, M, *n_ctas).bytes;
+}
+
+}  // namespace ude

@@ -1,0 +1,66 @@
+// ude_tc_model.h — host+device description of one UDE func for the tcgen05 (tensor-core) path.
+//
+// The tensor path integrates tiles of 128 trajectories; a trajectory is a ROW of every matrix
+// product (M = 128 trajectories for the layer chain, K = 128 trajectories for the weight
+// gradients).  fp32 accuracy comes from a 3-way bf16 split of every operand
+//     x = x1 + x2 + x3,  x1 = bf16_rn(x), x2 = bf16_rn(x - x1), x3 = bf16_rn(x - x1 - x2)
+// and the six products x_i * w_j with i + j <= 4 (error ~2^-24, measured at the fp32 FFMA level:
+// tools/umma_probe.cu), issued as kind::f16 tcgen05.mma with fp32 accumulation in TMEM.
+//
+// Same reference structure as ude_model.h:
+//   Fp / Fa / FaFp of /root/reference/lib/models.py:109-265.
+#pragma once
+#include <stdint.h>
+
+namespace ude {
+
+constexpr int kTcThreads = 256;        // 8 warps: warp w owns TMEM lane quarter (w & 3) and column half (w >> 2)
+constexpr int kTcTile = 128;           // trajectories per tile (= UMMA M)
+constexpr int kTcMaxLayers = 4;        // nn.Linear layers per net on the tensor path
+constexpr int kTcGroupBytes = kTcTile * 16;   // one 8-feature group of an operand array: [128 traj][8 bf16]
+
+struct TcLayer {
+    int in, out;            // true nn.Linear dims
+    int in_p, out_p;        // padded to a multiple of 16 (UMMA K / N granularity used here)
+    int elu;                // ELU on the output
+    int w_off;              // byte offset of the weight image inside the packed blob
+    int b_off;              // float offset of the bias (padded to out_p) in the bias block
+    int save_col;           // TMEM column of the saved OUTPUT activation (backward), -1 for the head
+    int th_w, th_b;         // offsets into theta (PyTorch layout)
+    int slab_off;           // float offset of this layer's gradient rows in a CTA slab: [out_p][8 + in_p]
+    int pad_;
+};
+
+// Weight image of one layer (bf16): [k/8][s = 0..2][n (out_p)][k%8], i.e. for every group of 8
+// input features the three split arrays are stacked along N.  Viewed as
+//   * K-major B operand of the forward product (N-stacked over s: one instruction computes
+//     a_i x [w1|w2|w3]):          SBO = 128, LBO = 3*out_p*16
+//   * MN-major B operand of the delta product (N' = in, K' = out) for ONE split array s:
+//                                  SBO = 3*out_p*16, LBO = 128
+struct TcModel {
+    int kind;               // UdeKind
+    int R, L;
+    int D0, D0_p;           // R*L and its padding to 16
+    int n_rate, n_aug;
+    TcLayer rate[kTcMaxLayers];
+    TcLayer aug[kTcMaxLayers];
+    float fa_w;
+    int n_theta;
+    int w_bytes;            // total bytes of all weight images
+    int n_bias;             // floats of the bias block
+    int blob_bytes;         // w_bytes + 4*n_bias, rounded up to 16
+    int slab_floats;        // floats of one CTA gradient slab
+    // ---- shared memory plan (byte offsets into the dynamic arena) ----
+    int off_w, off_bias, off_abuf, off_dbuf;
+    int abuf_bytes, dbuf_bytes;
+    int smem_bytes_fwd, smem_bytes_bwd;
+    // ---- tensor memory plan (columns) ----
+    int tm_save;            // [0, tm_save): saved activations (backward only)
+    int tm_q;               // weight-gradient accumulator: 8 + 2*max_in_p columns
+    int tm_q_cols;
+    int tm_dd;              // delta-chain accumulator: max_in_p columns
+    int tm_fwd;             // forward accumulator (3*max_out_p columns); aliases [tm_q, ...)
+    int tm_cols_fwd, tm_cols_bwd;   // allocation sizes (power of two >= 32)
+};
+
+}  // namespace ude

@@ -141,6 +141,7 @@ class FuncInfo:
     fa_w: float
     rate_head_elu: bool = False      # ELU between the last hidden layer and the head (tune_node.py Fp)
     aug_head_elu: bool = False
+    kernels: Optional[str] = None    # None: library picks; 'ffma' | 'tensor' pin the RK4 kernel family
 
     def desc(self, batch: int, n_groups: int = 1) -> "_lib.UdeDesc":
         d = _lib.UdeDesc()
@@ -156,6 +157,10 @@ class FuncInfo:
         d.fa_w = float(self.fa_w)
         d.n_groups = n_groups
         d.flags = (1 if self.rate_head_elu else 0) | (2 if self.aug_head_elu else 0)
+        if self.kernels is not None:
+            if self.kernels not in ("ffma", "tensor"):
+                raise ValueError("kernels must be 'ffma' or 'tensor'")
+            d.flags |= 4 if self.kernels == "ffma" else 8
         d.batch = batch
         return d
 

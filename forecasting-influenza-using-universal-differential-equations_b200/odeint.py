@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 from typing import Optional
 
@@ -218,6 +219,7 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         return dopri5_solve(func, info, y0, t_cpu, rtol, atol, options)
 
     group = options.pop("process_group", None)        # fused-path extra: all-reduce the side sums over this group
+    info.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)   # fused-path extra: pin the kernel family
     unknown = set(options) - {"step_size", "interp", "perturb", "grid_constructor"}
     if unknown:
         raise ValueError(f"unexpected rk4 options {sorted(unknown)}")

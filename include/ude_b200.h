@@ -88,6 +88,12 @@ typedef struct UdeDesc {
  * nn.Sequential with an ELU before the head as well.  These flags select the latter. */
 #define UDE_FLAG_RATE_HEAD_ELU 1
 #define UDE_FLAG_AUG_HEAD_ELU 2
+/* Kernel family of the RK4 solve.  By default the library picks the tcgen05 tensor-core kernels when
+ * the configuration is one they cover AND the batch makes the layer products real dense contractions
+ * (BASELINE north_star), else the FFMA kernels.  These flags pin the choice (parity tests, benchmarks);
+ * FORCE_TENSOR on an uncovered configuration returns UDE_ERR_UNSUPPORTED. */
+#define UDE_FLAG_FORCE_FFMA 4
+#define UDE_FLAG_FORCE_TENSOR 8
 
 typedef enum UdeMethod { UDE_METHOD_RK4 = 0, UDE_METHOD_DOPRI5 = 1 } UdeMethod;
 
@@ -195,6 +201,10 @@ int ude_dopri5_backward(const UdeDesc* desc, const UdeDopri5Opts* opts,
                         const float* g_out /*dev*/, const float* g_side /*dev | NULL*/,
                         float* g_y0 /*dev*/, float* g_theta /*dev*/,
                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Which kernel family ude_rk4_forward/backward will run for `desc`: 0 = FFMA engine, 1 = tcgen05
+ * tensor-core path; negative UdeStatus on a bad descriptor.  Host only. */
+int ude_rk4_path(const UdeDesc* desc);
 
 /* Sustained fp32 FFMA throughput of the device in TFLOP/s (2 flops per FMA),
  * measured with a register-resident FMA chain kernel: the roofline denominator

@@ -140,6 +140,13 @@ class OracleFunc(torch.nn.Module):
     def clear_tracking(self):
         self.params, self.tracker = [], []
 
+    def posterior(self):
+        """Normal(mean, unbiased std) over every (eval, trajectory, region) row of (beta, gamma);
+        clears the list (/root/reference/lib/models.py:152-156, 261-265)."""
+        p = torch.stack(self.params).reshape(-1, 2)
+        self.params = []
+        return torch.distributions.Normal(p.mean(0), p.std(0))
+
     def side_sums(self) -> torch.Tensor:
         """[sum beta, sum gamma, sum beta^2, sum gamma^2, sum Fa^2, N] in fp64 —
         the reductions the fused kernels emit instead of the python lists."""
