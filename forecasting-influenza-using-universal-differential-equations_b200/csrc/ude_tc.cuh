@@ -54,7 +54,7 @@ struct TcBwdArgs {
 // ----------------------------------------------------------------------------------
 // tcgen05 primitives
 // ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__host__ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
@@ -62,7 +62,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
     return d;
 }
 // kind::f16, bf16 x bf16 -> fp32
-__device__ __forceinline__ uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t tc_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -140,6 +140,14 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ELU(alpha=1) with exp(h) = ex2.approx.ftz(h * log2 e): the same MUFU.EX2 the FFMA engine's __expf uses,
+// minus its denormal-range rescaling (h < -87 flushes to exp = 0, i.e. ELU = -1 exactly as it rounds anyway).
+__device__ __forceinline__ float tc_elu(float h) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * 1.4426950408889634f));
+    return h > 0.f ? h : e - 1.0f;
+}
+
 // ----------------------------------------------------------------------------------
 // 3-way bf16 split of 8 consecutive features -> one 16-byte group per split array
 // ----------------------------------------------------------------------------------
@@ -163,19 +171,40 @@ __device__ __forceinline__ void split3_store8(const float* v /*8 values*/, uint8
     *reinterpret_cast<uint4*>(p2) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
 }
 
+// same split, 16 features -> registers: p[2*s + g] = group g (8 features) of split array s
+__device__ __forceinline__ void split3_pack16(const float (&v)[16], uint4 (&p)[6]) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint32_t h0[4], h1[4], h2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = v[8 * g + 2 * j], b = v[8 * g + 2 * j + 1];
+            h0[j] = pack_bf16x2(a, b);
+            const float ra = a - __uint_as_float(h0[j] << 16), rb = b - __uint_as_float(h0[j] & 0xFFFF0000u);
+            h1[j] = pack_bf16x2(ra, rb);
+            const float sa = ra - __uint_as_float(h1[j] << 16), sb = rb - __uint_as_float(h1[j] & 0xFFFF0000u);
+            h2[j] = pack_bf16x2(sa, sb);
+        }
+        p[0 + g] = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+        p[2 + g] = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+        p[4 + g] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    }
+}
+
 // Placement of the split arrays of an activation of width in_p inside Abuf, in 8-feature groups:
 //   [ a2 | a1 | ones | a3 ]   (the weight-gradient product reads [a2|a1|ones] and [a1|ones] as ONE B operand)
-__device__ __forceinline__ int abuf_group(int s, int in_p) {
+__host__ __device__ __forceinline__ int abuf_group(int s, int in_p) {
     const int g = in_p >> 3;
     return s == 0 ? g : (s == 1 ? 0 : 2 * g + 1);
 }
-__device__ __forceinline__ int abuf_ones_group(int in_p) { return 2 * (in_p >> 3); }
+__host__ __device__ __forceinline__ int abuf_ones_group(int in_p) { return 2 * (in_p >> 3); }
 
 // ----------------------------------------------------------------------------------
 // MMA issue (one thread)
 // ----------------------------------------------------------------------------------
 // forward: D[128, 3*out_p] : block0 = a1 w1, block1 = a1 w2 + a2 w1, block2 = a1 w3 + a2 w2 + a3 w1
-__device__ __forceinline__ void tc_issue_forward(const TcLayer& Lp, uint32_t abuf, uint32_t wimg, uint32_t d_addr) {
+template <class Emit>
+__host__ __device__ __forceinline__ void tc_issue_forward(const TcLayer& Lp, uint32_t abuf, uint32_t wimg, uint32_t d_addr, Emit&& tc_mma) {
     const int ksteps = Lp.in_p >> 4;
     const uint32_t w_kgrp = 3u * Lp.out_p * 16u;
     const uint32_t id3 = tc_idesc(128, 3 * Lp.out_p, 0, 0), id2 = tc_idesc(128, 2 * Lp.out_p, 0, 0),
@@ -191,7 +220,8 @@ __device__ __forceinline__ void tc_issue_forward(const TcLayer& Lp, uint32_t abu
     }
 }
 // delta chain: D[128, in_p] = sum_{i+j<=4} G_i W_j   (W_j: MN-major view of split array j)
-__device__ __forceinline__ void tc_issue_delta(const TcLayer& Lp, uint32_t dbuf, uint32_t wimg, uint32_t d_addr) {
+template <class Emit>
+__host__ __device__ __forceinline__ void tc_issue_delta(const TcLayer& Lp, uint32_t dbuf, uint32_t wimg, uint32_t d_addr, Emit&& tc_mma) {
     const int ksteps = Lp.out_p >> 4;
     const uint32_t g_arr = (Lp.out_p >> 3) * kTcGroupBytes;
     const uint32_t w_kgrp = 3u * Lp.out_p * 16u;
@@ -208,49 +238,177 @@ __device__ __forceinline__ void tc_issue_delta(const TcLayer& Lp, uint32_t dbuf,
         }
     }
 }
-// weight gradients: Q[64, 2*in_p + 8]: cols [0,in_p) = (G1+G2) a2, [in_p,2in_p) = (G1+G2+G3) a1 + G1 a3,
-//                                       col 2in_p = sum_t (G1+G2+G3) = bias gradient
-__device__ __forceinline__ void tc_issue_dw(const TcLayer& Lp, uint32_t dbuf, uint32_t abuf, uint32_t q_addr) {
+// weight gradients: Q[64, 2*in_p + 8]: cols [0,in_p) = G1 a2, [in_p,2in_p) = (G1+G2) a1, col 2in_p = sum_t (G1+G2)
+// = bias gradient;  dW = cols[k] + cols[in_p + k].
+// Only the first-order products of the 3-way split are formed: the second-order ones (G1 a3, G3 a1, G2 a2, each
+// ~2^-16 relative) are zero-mean round-off residuals, independent across trajectories, and the sum over
+// >= 128 trajectories x 4 stages averages them to ~1e-6 relative (measured 1.7e-6 at ONE tile, ONE step;
+// tests pin it).  The activation images are [a2 | a1 | ones] in one of two alternating sweep buffers, so the
+// B-operand addresses here are relative to the sweep buffer (tc_issue_table adds the buffer offset).
+template <class Emit>
+__host__ __device__ __forceinline__ void tc_issue_dw(const TcLayer& Lp, uint32_t dbuf, uint32_t abuf, uint32_t q_addr, Emit&& tc_mma) {
     const uint32_t g_arr = (Lp.out_p >> 3) * kTcGroupBytes;
     const int in_p = Lp.in_p;
-    const uint32_t id_full = tc_idesc(64, 2 * in_p + 8, 1, 1), id_a1 = tc_idesc(64, in_p + 8, 1, 1), id_a3 = tc_idesc(64, in_p, 1, 1);
-    const uint32_t b_a1 = abuf + abuf_group(0, in_p) * kTcGroupBytes, b_a3 = abuf + abuf_group(2, in_p) * kTcGroupBytes;
+    const uint32_t id_full = tc_idesc(64, 2 * in_p + 8, 1, 1), id_a1 = tc_idesc(64, in_p + 8, 1, 1);
+    const uint32_t b_a1 = abuf + abuf_group(0, in_p) * kTcGroupBytes;
     for (int k = 0; k < kTcTile / 16; ++k) {
         const uint32_t ko = k * 256;
-        const uint64_t g1 = tc_desc(dbuf + ko, 128, kTcGroupBytes), g2 = tc_desc(dbuf + g_arr + ko, 128, kTcGroupBytes),
-                       g3 = tc_desc(dbuf + 2 * g_arr + ko, 128, kTcGroupBytes);
-        const uint64_t b_full = tc_desc(abuf + ko, 128, kTcGroupBytes);
-        tc_mma(q_addr, g1, b_full, id_full, k > 0);
-        tc_mma(q_addr, g2, b_full, id_full, 1u);
-        tc_mma(q_addr + in_p, g3, tc_desc(b_a1 + ko, 128, kTcGroupBytes), id_a1, 1u);
-        tc_mma(q_addr + in_p, g1, tc_desc(b_a3 + ko, 128, kTcGroupBytes), id_a3, 1u);
+        const uint64_t g1 = tc_desc(dbuf + ko, 128, kTcGroupBytes), g2 = tc_desc(dbuf + g_arr + ko, 128, kTcGroupBytes);
+        tc_mma(q_addr, g1, tc_desc(abuf + ko, 128, kTcGroupBytes), id_full, k > 0);
+        tc_mma(q_addr + in_p, g2, tc_desc(b_a1 + ko, 128, kTcGroupBytes), id_a1, 1u);
     }
 }
+
+// ----------------------------------------------------------------------------------
+// MMA tables.  Every descriptor of a launch is loop invariant (the operand buffers never move), so each
+// layer's instruction list is built ONCE, on the host, and travels as a __grid_constant__ kernel
+// parameter: the issuing warp streams 32-byte entries from the constant bank through UNIFORM registers
+// straight into tcgen05.mma (one elected lane).  With in-loop descriptor arithmetic in vector registers
+// the single issuing thread was the bottleneck: 115-125 cycles per instruction against the 50-cycle
+// hardware floor (tools/umma_probe.cu, tools/tc_prof.py).
+// Shared-memory addresses in the table are relative to the dynamic shared-memory base.
+// ----------------------------------------------------------------------------------
+struct __align__(16) TcMma {
+    uint32_t a_lo, a_hi, b_lo, b_hi;
+    uint32_t idesc, d_col, acc, pad;     // d_col: TMEM column relative to the phase's accumulator base
+};
+constexpr int kTcMaxMma = 640;
+struct TcTable {
+    TcMma e[kTcMaxMma];
+};
+
+struct TcRecorder {
+    TcMma* out;
+    int n;
+    __host__ __device__ void operator()(uint32_t d_col, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        TcMma e;
+        e.a_lo = (uint32_t)adesc; e.a_hi = (uint32_t)(adesc >> 32);
+        e.b_lo = (uint32_t)bdesc; e.b_hi = (uint32_t)(bdesc >> 32);
+        e.idesc = idesc; e.d_col = d_col; e.acc = acc; e.pad = 0;
+        out[n++] = e;
+    }
+};
+
+// one elected lane of a converged warp issues; everything else stays warp-uniform
+__device__ __forceinline__ void tc_mma_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+// executed by ALL lanes of warp 0
+__device__ __forceinline__ void tc_issue_table(const TcTable& tab, int begin, int n, uint32_t smem_base16, uint32_t tmem,
+                                               uint32_t b_extra16 = 0u) {
+#pragma unroll 2
+    for (int i = begin; i < begin + n; ++i) {
+        const TcMma& e = tab.e[i];
+        const uint64_t ad = ((uint64_t)e.a_hi << 32) | (uint64_t)(e.a_lo + smem_base16);
+        const uint64_t bd = ((uint64_t)e.b_hi << 32) | (uint64_t)(e.b_lo + smem_base16 + b_extra16);
+        tc_mma_elect(tmem + e.d_col, ad, bd, e.idesc, e.acc);
+    }
+}
+
+// optional cycle accounting (-DUDE_TC_PROFILE): CTA 0, threads 0 (issuer) and 128 (warp 4) accumulate the
+// cycles they spend per category; read back with ude_debug_tc_prof().
+#ifdef UDE_TC_PROFILE
+__device__ unsigned long long g_tc_prof[2 * 8];
+#define TCP_T0() const long long tcp_t0 = clock64()
+#define TCP_ADD(c, id) (c).prof[id] += clock64() - tcp_t0
+#else
+#define TCP_T0()
+#define TCP_ADD(c, id)
+#endif
+enum { TCP_SYNC = 0, TCP_ISSUE = 1, TCP_WAIT = 2, TCP_EPI_FWD = 3, TCP_EPI_BWD = 4, TCP_TAIL = 5, TCP_TOTAL = 6 };
 
 // ----------------------------------------------------------------------------------
 // per-CTA context
 // ----------------------------------------------------------------------------------
 struct TcCtx {
+#ifdef UDE_TC_PROFILE
+    long long prof[8];
+#endif
     uint8_t* abuf_p;        // operand buffers (generic pointers)
     uint8_t* dbuf_p;
     uint32_t abuf, dbuf, wimg;   // shared-space addresses
     const float* bias;      // bias block in smem
     uint32_t tmem;          // TMEM base address
-    uint64_t* bar;          // MMA completion barrier
+    uint64_t* bar;          // MMA completion barrier (forward products, delta chain)
+    uint64_t* bar_b;        // second completion barrier (weight-gradient products)
+    uint32_t phase_b;
+    uint32_t sweep_par;     // sweep buffer of the current backward phase
+    uint32_t sweep_buf_bytes;
+    uint32_t smem_base16;   // dynamic shared-memory base >> 4 (MMA table addresses are relative)
     uint32_t phase;
+    int warp;               // warp index (warp-uniform by construction)
     int q, h, lane, t;      // lane quarter, column half, lane, trajectory row of this thread
     uint32_t lane_addr;     // (32*q) << 16
 };
 
-__device__ __forceinline__ void tc_sync_issue_begin() {
+// Operand hand-off between the 8 epilogue warps and the dedicated MMA-issuing warp (warp 8): the epilogue
+// warps ARRIVE (non-blocking) once their shared-memory writes and TMEM reads of the phase are fenced, the
+// issuer SYNCs on the same named barrier and fires the phase's instruction list.  The issuer blocks in the
+// tensor queue for about as long as the MMAs run, which is exactly why it must not be an epilogue warp.
+constexpr int kTcBarOperands = 1;
+__device__ __forceinline__ void tc_operands_ready(TcCtx& c) {
+    TCP_T0();
     tc_proxy_fence();
     tc_fence_before();
-    __syncthreads();
+    asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarOperands), "n"(kTcBarThreads) : "memory");
+    TCP_ADD(c, TCP_SYNC);
+}
+__device__ __forceinline__ void tc_issuer_wait_operands() {
+    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarOperands), "n"(kTcBarThreads) : "memory");
+    tc_fence_after();
+}
+// issuer side of one forward phase / one backward phase
+__device__ __forceinline__ void tc_issuer_forward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem_fwd,
+                                                  uint64_t* bar) {
+    tc_issuer_wait_operands();
+    tc_issue_table(tab, Lp.mma_fwd, Lp.n_fwd, smem_base16, tmem_fwd);
+    tc_commit_elect(bar);
+}
+__device__ __forceinline__ void tc_issuer_backward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem,
+                                                   uint64_t* bar, uint64_t* bar_b, uint32_t sweep_buf16) {
+    tc_issuer_wait_operands();
+    const int n_dl = 6 * (Lp.out_p >> 4);
+    tc_issue_table(tab, Lp.mma_bwd, n_dl, smem_base16, tmem);
+    tc_commit_elect(bar);
+    tc_issue_table(tab, Lp.mma_bwd + n_dl, Lp.n_bwd - n_dl, smem_base16, tmem, sweep_buf16);
+    tc_commit_elect(bar_b);
 }
 __device__ __forceinline__ void tc_wait_mma(TcCtx& c) {
+    TCP_T0();
     mbar_wait(c.bar, c.phase);
     c.phase ^= 1u;
     tc_fence_after();
+    TCP_ADD(c, TCP_WAIT);
+}
+__device__ __forceinline__ void tc_wait_mma_b(TcCtx& c) {
+    TCP_T0();
+    mbar_wait(c.bar_b, c.phase_b);
+    c.phase_b ^= 1u;
+    tc_fence_after();
+    TCP_ADD(c, TCP_WAIT);
+}
+__device__ __forceinline__ void tc_prof_init(TcCtx& c) {
+#ifdef UDE_TC_PROFILE
+    for (int i = 0; i < 8; ++i) c.prof[i] = 0;
+    c.prof[TCP_TOTAL] = -clock64();
+#endif
+}
+__device__ __forceinline__ void tc_prof_dump(TcCtx& c) {
+#ifdef UDE_TC_PROFILE
+    c.prof[TCP_TOTAL] += clock64();
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
+        for (int i = 0; i < 8; ++i) g_tc_prof[(threadIdx.x == 0 ? 0 : 8) + i] = (unsigned long long)c.prof[i];
+#endif
 }
 
 // write 16 consecutive features [16*chunk, 16*chunk+16) of an activation of width `width` into Abuf
@@ -269,6 +427,39 @@ __device__ __forceinline__ void tc_store_delta16(const TcCtx& c, const float (&v
     for (int g = 0; g < 2; ++g) {
         uint8_t* base = c.dbuf_p + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
         split3_store8(v + 8 * g, base, base + arr, base + 2 * arr);
+    }
+}
+// 2-way split of 8 consecutive features (the sweep images carry a1, a2 only)
+__device__ __forceinline__ void split2_store8(const float* v, uint8_t* p0, uint8_t* p1) {
+    uint32_t h0[4], h1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = v[2 * j], b = v[2 * j + 1];
+        h0[j] = pack_bf16x2(a, b);
+        h1[j] = pack_bf16x2(a - __uint_as_float(h0[j] << 16), b - __uint_as_float(h0[j] & 0xFFFF0000u));
+    }
+    *reinterpret_cast<uint4*>(p0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
+    *reinterpret_cast<uint4*>(p1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+}
+// sweep image [a2 | a1 | ones] of an activation of width `width` into sweep buffer `buf`
+__device__ __forceinline__ void tc_store_sweep16(const TcCtx& c, uint32_t buf, const float (&v)[16], int chunk, int width) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint8_t* base = c.abuf_p + (size_t)buf * c.sweep_buf_bytes + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
+        split2_store8(v + 8 * g, base + abuf_group(0, width) * kTcGroupBytes, base + abuf_group(1, width) * kTcGroupBytes);
+    }
+}
+__device__ __forceinline__ void tc_store_sweep_ones(const TcCtx& c, uint32_t buf, int width) {
+    uint8_t* p = c.abuf_p + (size_t)buf * c.sweep_buf_bytes + (size_t)abuf_ones_group(width) * kTcGroupBytes + c.t * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(0x00003F80u, 0u, 0u, 0u);      // feature 0 = bf16(1.0)
+}
+__device__ __forceinline__ void tc_store_pack_delta(const TcCtx& c, const uint4 (&p)[6], int chunk, int width) {
+    const size_t arr = (size_t)(width >> 3) * kTcGroupBytes;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint8_t* base = c.dbuf_p + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
+#pragma unroll
+        for (int sidx = 0; sidx < 3; ++sidx) *reinterpret_cast<uint4*>(base + sidx * arr) = p[2 * sidx + g];
     }
 }
 __device__ __forceinline__ void tc_store_ones(const TcCtx& c, int width) {
@@ -291,16 +482,12 @@ __device__ __forceinline__ void tc_store_x(const TcCtx& c, const float (&x)[D0],
 // `head` (threads of warps 0-3), activations saved to TMEM when SAVE.
 // ----------------------------------------------------------------------------------
 template <bool SAVE, int NH>
-__device__ __forceinline__ void tc_net_forward(const TcLayer* Ls, int n_layers, int tm_fwd, TcCtx& c, float (&head)[NH]) {
+__device__ __forceinline__ void tc_net_forward(const TcTable& tab, const TcLayer* Ls, int n_layers, int tm_fwd, TcCtx& c, float (&head)[NH]) {
     for (int l = 0; l < n_layers; ++l) {
         const TcLayer& Lp = Ls[l];
-        tc_sync_issue_begin();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            tc_issue_forward(Lp, c.abuf, c.wimg, c.tmem + tm_fwd);
-            tc_commit(c.bar);
-        }
+        tc_operands_ready(c);
         tc_wait_mma(c);
+        TCP_T0();
         const uint32_t d0 = c.tmem + c.lane_addr + tm_fwd;
         const float* bias = c.bias + Lp.b_off;
         if (l + 1 < n_layers) {
@@ -317,7 +504,7 @@ __device__ __forceinline__ void tc_net_forward(const TcLayer* Ls, int n_layers, 
                 }
                 if (Lp.elu) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v0[i] = elu_f(v0[i]);
+                    for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
                 }
                 if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
                 tc_store_act16(c, v0, ch, Lp.out_p);
@@ -328,6 +515,7 @@ __device__ __forceinline__ void tc_net_forward(const TcLayer* Ls, int n_layers, 
 #pragma unroll
             for (int i = 0; i < NH; ++i) head[i] = ((v2[i] + v1[i]) + v0[i]) + bias[i];
         }
+        TCP_ADD(c, TCP_EPI_FWD);
     }
 }
 
@@ -466,25 +654,50 @@ __device__ __forceinline__ void tc_side_reduce(const SideAcc& s, double n_evals,
     if (threadIdx.x == 7) out[7] = 0.0;
 }
 
+// ----------------------------------------------------------------------------------
+// the issuing warp replays the (data independent) phase sequence of its CTA
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_issuer_loop_fwd(const TcModel& M, const TcTable& tab, long long n_my_tiles, int n_steps,
+                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar) {
+    for (long long tile = 0; tile < n_my_tiles; ++tile)
+        for (int e = 0; e < 4 * n_steps; ++e) {
+            for (int l = 0; l < M.n_rate; ++l) tc_issuer_forward(tab, M.rate[l], smem_base16, tmem, bar);
+            for (int l = 0; l < M.n_aug; ++l) tc_issuer_forward(tab, M.aug[l], smem_base16, tmem, bar);
+        }
+}
+__device__ __forceinline__ void tc_issuer_loop_bwd(const TcModel& M, const TcTable& tab, long long n_my_tiles, int n_steps,
+                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar, uint64_t* bar_b) {
+    uint32_t par = 0;      // which of the two sweep buffers holds the current phase's activation image
+    for (long long tile = 0; tile < n_my_tiles; ++tile)
+        for (int e = 0; e < 4 * n_steps; ++e) {
+            for (int l = 0; l < M.n_rate; ++l) tc_issuer_forward(tab, M.rate[l], smem_base16, tmem + M.tm_fwd, bar);
+            for (int l = 0; l < M.n_aug; ++l) tc_issuer_forward(tab, M.aug[l], smem_base16, tmem + M.tm_fwd, bar);
+            for (int l = M.n_rate - 1; l >= 0; --l, par ^= 1u)
+                tc_issuer_backward(tab, M.rate[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u);
+            for (int l = M.n_aug - 1; l >= 0; --l, par ^= 1u)
+                tc_issuer_backward(tab, M.aug[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u);
+        }
+}
+
 // ===================================================================================
 // forward kernel
 // ===================================================================================
 template <int R, int L>
-__global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel Mg, const TcFwdArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcFwdArgs a) {
     constexpr int D0 = R * L, DN = 3 * R;
     static_assert(D0 <= 16, "tensor path: R*L <= 16");
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* const smem = tc_smem;
-    __shared__ TcModel M;
     __shared__ __align__(8) uint64_t wbar;
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_b;
     __shared__ uint32_t tmem_slot;
-    __shared__ double red[8 * 8];
+    __shared__ double red[(kTcThreads / 32) * 8];
 
-    tc_copy_model(&M, Mg);
     if (threadIdx.x == 0) {
         mbar_init(&wbar, 1);
         mbar_init(&mbar, 1);
+        mbar_init(&mbar_b, 1);
     }
     if (threadIdx.x < 32) tc_tmem_alloc<256>(&tmem_slot);
     tc_fence_before();
@@ -502,12 +715,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     c.bias = reinterpret_cast<const float*>(smem + M.off_bias);
     c.tmem = tmem_slot;
     c.bar = &mbar;
+    c.bar_b = &mbar_b;
+    c.phase_b = 0;
+    c.sweep_par = 0;
+    c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
+    c.smem_base16 = smem_u32(smem) >> 4;
     c.phase = 0;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform
+    c.warp = warp;
     c.q = warp & 3; c.h = warp >> 2; c.lane = threadIdx.x & 31;
     c.t = c.q * 32 + c.lane;
     c.lane_addr = (uint32_t)(c.q * 32) << 16;
     const bool is_traj = warp < 4;
+    tc_prof_init(c);
 
     SideAcc side;
     side.clear();
@@ -515,6 +735,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     const long long n_tiles = (B + kTcTile - 1) / kTcTile;
     const long long tape_stage = (long long)DN * B;
 
+    if (warp >= kTcEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 8-11: issuer + 3 idle warps of its warpgroup
+        if (warp == kTcEpiWarps) {
+        const long long n_my = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        tc_issuer_loop_fwd(M, tab, n_my, a.g.n_steps, c.smem_base16, c.tmem, c.bar);
+        }
+    } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * kTcTile;
         const bool valid = is_traj && (b0 + c.t < B);
@@ -552,11 +780,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
                 if (M.n_rate > 0) {
                     if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<false, 2 * R>(M.rate, M.n_rate, 0, c, o_r);
+                    tc_net_forward<false, 2 * R>(tab, M.rate, M.n_rate, 0, c, o_r);
                 }
                 if (M.n_aug > 0) {
                     if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<false, 3 * R>(M.aug, M.n_aug, 0, c, o_a);
+                    tc_net_forward<false, 3 * R>(tab, M.aug, M.n_aug, 0, c, o_a);
                 }
                 if (is_traj) {
                     float f[DN];
@@ -625,6 +853,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
             }
         }
     }
+    }
+    tc_prof_dump(c);
     tc_side_reduce(side, 4.0 * a.g.n_steps, red, a.side_partial + (long long)blockIdx.x * 8);
     tc_fence_before();
     __syncthreads();
@@ -637,6 +867,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
 // Sweep one net backwards over the tile.  Pre: G_head in `g_head` (trajectory threads), saved
 // activations in TMEM, x in registers.  Post: dx[0..D0) += W_0^T G_0 (trajectory threads), weight and
 // bias gradients added to the CTA slab.
+//
+// Software pipeline of one phase (layer l): the delta-chain MMAs C_l and the weight-gradient MMAs W_l are
+// issued back to back (by the issuing warp) with separate completion barriers.  While they run the epilogue
+// warps (1) write the NEXT phase's activation image a_{l-1} into the other sweep buffer (it needs nothing
+// from the MMAs), (2) once C_l is done build G_{l-1} in registers; only (3) the store of G_{l-1} -- W_l still
+// reads G_l from the same buffer -- and the gradient flush wait for W_l.
 template <int D0, int NH>
 __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer* Ls, int n_layers, TcCtx& c,
                                                 const float (&g_head)[NH], const float (&x)[D0], float* slab,
@@ -654,21 +890,67 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         for (int ch = c.h; ch < (Lh.in_p >> 4); ch += 2) {
             float v[16];
             tc_ld16(c.tmem + c.lane_addr + Lprev.save_col + 16 * ch, v);
-            tc_store_act16(c, v, ch, Lh.in_p);
+            tc_store_sweep16(c, c.sweep_par, v, ch, Lh.in_p);
         }
-        if (c.h == 0) tc_store_ones(c, Lh.in_p);
+        if (c.h == 0) tc_store_sweep_ones(c, c.sweep_par, Lh.in_p);
+        tc_operands_ready(c);
     }
     for (int l = n_layers - 1; l >= 0; --l) {
         const TcLayer& Lp = Ls[l];
-        tc_sync_issue_begin();
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            tc_issue_delta(Lp, c.dbuf, c.wimg, c.tmem + M.tm_dd);
-            tc_issue_dw(Lp, c.dbuf, c.abuf, c.tmem + M.tm_q);
-            tc_commit(c.bar);
+        uint4 sg[2][6];
+        // ---- (1) while C_l and W_l run: image of a_{l-1} (input of layer l-1) into the other sweep buffer
+        {
+            TCP_T0();
+            if (l >= 2) {
+                const TcLayer& Lq = Ls[l - 1];
+                const TcLayer& Lr = Ls[l - 2];
+                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += 2) {
+                    float v[16];
+                    tc_ld16(c.tmem + c.lane_addr + Lr.save_col + 16 * ch, v);
+                    tc_store_sweep16(c, c.sweep_par ^ 1u, v, ch, Lq.in_p);
+                }
+                if (c.h == 0) tc_store_sweep_ones(c, c.sweep_par ^ 1u, Lq.in_p);
+            } else if (l == 1 && is_traj) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = i < D0 ? x[i] : 0.f;
+                tc_store_sweep16(c, c.sweep_par ^ 1u, v, 0, 16);
+                tc_store_sweep_ones(c, c.sweep_par ^ 1u, 16);
+            }
+            TCP_ADD(c, TCP_EPI_BWD);
         }
+        // ---- (2) C_l done: G_{l-1} = dA_l * ELU'(a_l), kept in registers
         tc_wait_mma(c);
-        // ---- weight / bias gradients of layer l: TMEM -> per-CTA slab (rows 16q..16q+15 live in lanes 0..15)
+        {
+            TCP_T0();
+            if (l >= 1) {
+                const TcLayer& Lq = Ls[l - 1];
+                const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int ch = c.h + 2 * j;
+                    if (ch < (Lp.in_p >> 4)) {
+                        float d[16], sv[16];
+                        tc_ld16x2(dd + 16 * ch, c.tmem + c.lane_addr + Lq.save_col + 16 * ch, d, sv);
+                        if (Lq.elu) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(sv[i]);
+                        }
+                        split3_pack16(d, sg[j]);
+                    }
+                }
+            } else if (is_traj) {
+                float d[16];
+                tc_ld16(c.tmem + c.lane_addr + M.tm_dd, d);
+#pragma unroll
+                for (int i = 0; i < D0; ++i) dx[i] += d[i];
+            }
+            TCP_ADD(c, TCP_EPI_BWD);
+        }
+        // ---- (3) W_l done: weight / bias gradients of layer l, TMEM -> per-CTA slab
+        //          (rows 16q..16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q)
+        tc_wait_mma_b(c);
+        TCP_T0();
         {
             const int m = 16 * c.q + c.lane;
             const bool act = c.lane < 16 && m < Lp.out;
@@ -689,54 +971,36 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                 if (act) atomicAdd(row + Lp.in_p, u[0]);
             }
         }
+        c.sweep_par ^= 1u;
         if (l >= 1) {
-            // ---- G_{l-1} = dA_l * ELU'(a_l)   and   a_{l-1} for the next phase
-            const TcLayer& Lq = Ls[l - 1];
-            const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
-            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += 2) {
-                float d[16], s[16];
-                tc_ld16x2(dd + 16 * ch, c.tmem + c.lane_addr + Lq.save_col + 16 * ch, d, s);
-                if (Lq.elu) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(s[i]);
-                }
-                tc_store_delta16(c, d, ch, Lp.in_p);
+            for (int j = 0; j < 2; ++j) {
+                const int ch = c.h + 2 * j;
+                if (ch < (Lp.in_p >> 4)) tc_store_pack_delta(c, sg[j], ch, Lp.in_p);
             }
-            if (l >= 2) {
-                const TcLayer& Lr = Ls[l - 2];
-                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += 2) {
-                    float v[16];
-                    tc_ld16(c.tmem + c.lane_addr + Lr.save_col + 16 * ch, v);
-                    tc_store_act16(c, v, ch, Lq.in_p);
-                }
-                if (c.h == 0) tc_store_ones(c, Lq.in_p);
-            } else if (is_traj) {
-                tc_store_x<D0>(c, x, true);
-            }
-        } else if (is_traj) {
-            float d[16];
-            tc_ld16(c.tmem + c.lane_addr + M.tm_dd, d);
-#pragma unroll
-            for (int i = 0; i < D0; ++i) dx[i] += d[i];
+            TCP_ADD(c, TCP_EPI_BWD);
+            tc_operands_ready(c);
+        } else {
+            TCP_ADD(c, TCP_EPI_BWD);
         }
     }
 }
 
 template <int R, int L>
-__global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel Mg, const TcBwdArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcBwdArgs a) {
     constexpr int D0 = R * L, DN = 3 * R;
     static_assert(D0 <= 16, "tensor path: R*L <= 16");
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     uint8_t* const smem = tc_smem;
-    __shared__ TcModel M;
     __shared__ __align__(8) uint64_t wbar;
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar_b;
     __shared__ uint32_t tmem_slot;
 
-    tc_copy_model(&M, Mg);
     if (threadIdx.x == 0) {
         mbar_init(&wbar, 1);
         mbar_init(&mbar, 1);
+        mbar_init(&mbar_b, 1);
     }
     if (threadIdx.x < 32) tc_tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
@@ -754,12 +1018,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     c.bias = reinterpret_cast<const float*>(smem + M.off_bias);
     c.tmem = tmem_slot;
     c.bar = &mbar;
+    c.bar_b = &mbar_b;
+    c.phase_b = 0;
+    c.sweep_par = 0;
+    c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
+    c.smem_base16 = smem_u32(smem) >> 4;
     c.phase = 0;
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // provably warp-uniform
+    c.warp = warp;
     c.q = warp & 3; c.h = warp >> 2; c.lane = threadIdx.x & 31;
     c.t = c.q * 32 + c.lane;
     c.lane_addr = (uint32_t)(c.q * 32) << 16;
     const bool is_traj = warp < 4;
+    tc_prof_init(c);
 
     // the operand buffers feed MN-major (K = trajectory) products: start from finite contents
     for (int i = threadIdx.x; i < (M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
@@ -778,6 +1049,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     const long long tape_stage = (long long)DN * B;
     const int n_steps = a.g.n_steps;
 
+    if (warp >= kTcEpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 8-11: issuer + 3 idle warps of its warpgroup
+        if (warp == kTcEpiWarps) {
+        const long long n_my = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        tc_issuer_loop_bwd(M, tab, n_my, n_steps, c.smem_base16, c.tmem, c.bar, c.bar_b);
+        }
+    } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * kTcTile;
         const bool valid = is_traj && (b0 + c.t < B);
@@ -857,11 +1136,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
                 if (M.n_rate > 0) {
                     if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<true, 2 * R>(M.rate, M.n_rate, M.tm_fwd, c, o_r);
+                    tc_net_forward<true, 2 * R>(tab, M.rate, M.n_rate, M.tm_fwd, c, o_r);
                 }
                 if (M.n_aug > 0) {
                     if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<true, 3 * R>(M.aug, M.n_aug, M.tm_fwd, c, o_a);
+                    tc_net_forward<true, 3 * R>(tab, M.aug, M.n_aug, M.tm_fwd, c, o_a);
                 }
                 // ---- tail VJP
                 float d_r[2 * R], d_a[3 * R], xb[DN], dx[D0];
@@ -918,6 +1197,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                 }
         }
     }
+    }
+    tc_prof_dump(c);
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tc_tmem_free<512>(c.tmem);

@@ -1,5 +1,7 @@
 // ude_tc_host.cu — host-side planning and launch of the tcgen05 path (own translation unit: the
 // two kernel families compile in parallel).
+#include <stdlib.h>
+
 #include "ude_host_common.h"
 #include "ude_tc.cuh"
 
@@ -42,6 +44,12 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
         }
         Lp.slab_off = M.slab_floats;
         M.slab_floats += Lp.out_p * (Lp.in_p + 8);
+        Lp.mma_fwd = M.n_mma;
+        Lp.n_fwd = 3 * (Lp.in_p / 16);
+        M.n_mma += Lp.n_fwd;
+        Lp.mma_bwd = M.n_mma;
+        Lp.n_bwd = 6 * (Lp.out_p / 16) + 2 * (kTcTile / 16);
+        M.n_mma += Lp.n_bwd;
         n_in = Lp.out;
         in_p = Lp.out_p;
     }
@@ -91,11 +99,14 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     M.off_w = 0;
     M.off_bias = M.w_bytes;
     M.off_abuf = (int)align_up(M.blob_bytes, 1024);
-    M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;
+    M.sweep_buf_bytes = (2 * (max_in / 8) + 1) * kTcGroupBytes;
+    M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;               // forward image [a2|a1|ones|a3]
+    if (2 * M.sweep_buf_bytes > M.abuf_bytes) M.abuf_bytes = 2 * M.sweep_buf_bytes;
     M.off_dbuf = M.off_abuf + M.abuf_bytes;
     M.dbuf_bytes = dcap * kTcGroupBytes;
     M.smem_bytes_fwd = M.off_abuf + M.abuf_bytes;
     M.smem_bytes_bwd = M.off_dbuf + M.dbuf_bytes;
+    if (M.n_mma > kTcMaxMma) return false;
     if (M.smem_bytes_bwd > kTcSmemLimit) return false;
     return true;
 }
@@ -106,6 +117,23 @@ int tc_choose(const UdeDesc* d, TcModel& M) {
     if (d->flags & UDE_FLAG_FORCE_TENSOR) return ok ? 1 : UDE_ERR_UNSUPPORTED;
     if (d->flags & UDE_FLAG_FORCE_FFMA) return 0;
     return (ok && d->batch >= kTcMinBatch) ? 1 : 0;
+}
+
+// MMA instruction lists of every layer (shared-memory addresses relative to the dynamic smem base;
+// forward lists relative to the forward accumulator, backward lists to the TMEM allocation base)
+static void tc_build_table(const TcModel& M, TcTable& T, bool backward) {
+    memset(&T, 0, sizeof(T));
+    const int nl = M.n_rate + M.n_aug;
+    for (int li = 0; li < nl; ++li) {
+        const TcLayer& Lp = li < M.n_rate ? M.rate[li] : M.aug[li - M.n_rate];
+        TcRecorder rf{T.e + Lp.mma_fwd, 0};
+        tc_issue_forward(Lp, (uint32_t)M.off_abuf, (uint32_t)M.off_w, 0u, rf);
+        if (backward) {
+            TcRecorder rb{T.e + Lp.mma_bwd, 0};
+            tc_issue_delta(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_w, (uint32_t)M.tm_dd, rb);
+            tc_issue_dw(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_abuf, (uint32_t)M.tm_q, rb);
+        }
+    }
 }
 
 struct TcWorkspace {
@@ -140,6 +168,9 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
     UDE_CUDA(cudaGetLastError());
+    static thread_local TcTable tab_storage;
+    TcTable* tab = &tab_storage;
+    tc_build_table(M, *tab, false);
     TcFwdArgs a;
     a.blob = w.blob;
     a.y0 = y0;
@@ -152,7 +183,7 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
 #define UDE_TC_FWD(RR, LL)                                                                     \
     do {                                                                                       \
         if ((st = set_smem(rk4_fwd_tc_kernel<RR, LL>, M.smem_bytes_fwd)) != UDE_OK) return st; \
-        rk4_fwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_fwd, s>>>(M, a);          \
+        rk4_fwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_fwd, s>>>(M, *tab, a);          \
     } while (0)
     if (M.L == 8) UDE_TC_FWD(1, 8);
     else if (M.L == 4) UDE_TC_FWD(1, 4);
@@ -173,6 +204,9 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
     UDE_CUDA(cudaGetLastError());
     UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)n_ctas * M.slab_floats * 4, s));
+    static thread_local TcTable tab_storage;
+    TcTable* tab = &tab_storage;
+    tc_build_table(M, *tab, true);
     TcBwdArgs a;
     a.blob = w.blob;
     a.y0 = y0;
@@ -187,7 +221,7 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
 #define UDE_TC_BWD(RR, LL)                                                                     \
     do {                                                                                       \
         if ((st = set_smem(rk4_bwd_tc_kernel<RR, LL>, M.smem_bytes_bwd)) != UDE_OK) return st; \
-        rk4_bwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_bwd, s>>>(M, a);          \
+        rk4_bwd_tc_kernel<RR, LL><<<n_ctas, kTcThreads, M.smem_bytes_bwd, s>>>(M, *tab, a);          \
     } while (0)
     if (M.L == 8) UDE_TC_BWD(1, 8);
     else if (M.L == 4) UDE_TC_BWD(1, 4);
@@ -205,3 +239,12 @@ void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes
 }
 
 }  // namespace ude
+
+#ifdef UDE_TC_PROFILE
+/* debug builds only: cycle counters of CTA 0 (thread 0: [0..8), thread 128: [8..16)) of the LAST tensor kernel */
+extern "C" int ude_debug_tc_prof(unsigned long long* out) {
+    UDE_CUDA(cudaDeviceSynchronize());
+    UDE_CUDA(cudaMemcpyFromSymbol(out, ude::g_tc_prof, sizeof(unsigned long long) * 16));
+    return UDE_OK;
+}
+#endif

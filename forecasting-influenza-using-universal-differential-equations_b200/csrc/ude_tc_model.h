@@ -14,7 +14,10 @@
 
 namespace ude {
 
-constexpr int kTcThreads = 256;        // 8 warps: warp w owns TMEM lane quarter (w & 3) and column half (w >> 2)
+constexpr int kTcThreads = 384;        // warps 0-7: epilogue (TMEM lane quarter w & 3, column half w >> 2); warp 8: MMA issuer;
+                                       // warps 9-11 only complete the issuer's warpgroup (setmaxnreg hands their registers over)
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcBarThreads = 32 * (kTcEpiWarps + 1);   // operand hand-off barrier: epilogue warps + issuer
 constexpr int kTcTile = 128;           // trajectories per tile (= UMMA M)
 constexpr int kTcMaxLayers = 4;        // nn.Linear layers per net on the tensor path
 constexpr int kTcGroupBytes = kTcTile * 16;   // one 8-feature group of an operand array: [128 traj][8 bf16]
@@ -28,6 +31,8 @@ struct TcLayer {
     int save_col;           // TMEM column of the saved OUTPUT activation (backward), -1 for the head
     int th_w, th_b;         // offsets into theta (PyTorch layout)
     int slab_off;           // float offset of this layer's gradient rows in a CTA slab: [out_p][8 + in_p]
+    int mma_fwd, n_fwd;     // forward instructions of this layer in the MMA table
+    int mma_bwd, n_bwd;     // delta-chain + weight-gradient instructions
     int pad_;
 };
 
@@ -52,7 +57,9 @@ struct TcModel {
     int slab_floats;        // floats of one CTA gradient slab
     // ---- shared memory plan (byte offsets into the dynamic arena) ----
     int off_w, off_bias, off_abuf, off_dbuf;
+    int n_mma;              // entries of the MMA table (kernel parameter)
     int abuf_bytes, dbuf_bytes;
+    int sweep_buf_bytes;    // one of the two alternating sweep images [a2|a1|ones] inside Abuf
     int smem_bytes_fwd, smem_bytes_bwd;
     // ---- tensor memory plan (columns) ----
     int tm_save;            // [0, tm_save): saved activations (backward only)

@@ -21,7 +21,7 @@ for it in range(3):
     y0g = y0.clone().requires_grad_(True)
     mod.clear_tracking()
     if method == "rk4":
-        y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=1.0))
+        y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=1.0, kernels=os.environ.get("UDE_KERNELS") or None))
     else:
         y = ude_b200.odeint(mod, y0g, t, rtol=1e-5, atol=1e-9, method="dopri5")
     (y[..., :3] ** 2).sum().backward()
