@@ -202,21 +202,26 @@ __host__ __device__ __forceinline__ int abuf_ones_group(int in_p) { return 2 * (
 // ----------------------------------------------------------------------------------
 // MMA issue (one thread)
 // ----------------------------------------------------------------------------------
-// forward: D[128, 3*out_p] : block0 = a1 w1, block1 = a1 w2 + a2 w1, block2 = a1 w3 + a2 w2 + a3 w1
+// forward: D[128, out_p] = sum_{i+j<=4} a_i w_j, ONE fp32 accumulator block.  (Accumulating the small products into
+// the same columns as a1 w1 costs nothing in accuracy -- every partial sum is rounded at the magnitude of the
+// result either way -- and keeps the accumulator of a layer at out_p TMEM columns, so the rate and the aug chain
+// can be in flight at the same time next to the saved activations of both nets.)
 template <class Emit>
 __host__ __device__ __forceinline__ void tc_issue_forward(const TcLayer& Lp, uint32_t abuf, uint32_t wimg, uint32_t d_addr, Emit&& tc_mma) {
     const int ksteps = Lp.in_p >> 4;
     const uint32_t w_kgrp = 3u * Lp.out_p * 16u;
-    const uint32_t id3 = tc_idesc(128, 3 * Lp.out_p, 0, 0), id2 = tc_idesc(128, 2 * Lp.out_p, 0, 0),
-                   id1 = tc_idesc(128, Lp.out_p, 0, 0);
-    const uint32_t a1 = abuf + abuf_group(0, Lp.in_p) * kTcGroupBytes, a2 = abuf + abuf_group(1, Lp.in_p) * kTcGroupBytes,
-                   a3 = abuf + abuf_group(2, Lp.in_p) * kTcGroupBytes;
+    const uint32_t id = tc_idesc(128, Lp.out_p, 0, 0);
+    uint32_t acc = 0;
     for (int k = 0; k < ksteps; ++k) {
         const uint32_t ao = k * 2 * kTcGroupBytes;
-        const uint64_t wd = tc_desc(wimg + Lp.w_off + k * 2 * w_kgrp, w_kgrp, 128);
-        tc_mma(d_addr, tc_desc(a1 + ao, kTcGroupBytes, 128), wd, id3, k > 0);
-        tc_mma(d_addr + Lp.out_p, tc_desc(a2 + ao, kTcGroupBytes, 128), wd, id2, 1u);
-        tc_mma(d_addr + 2 * Lp.out_p, tc_desc(a3 + ao, kTcGroupBytes, 128), wd, id1, 1u);
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {      // smallest products first
+            const int i = (0x001210 >> (4 * p)) & 15;      // a split: 0,1,2,1,0,0
+            const int j = (0x010012 >> (4 * p)) & 15;      // w split: 2,1,0,0,1,0
+            tc_mma(d_addr, tc_desc(abuf + abuf_group(i, Lp.in_p) * kTcGroupBytes + ao, kTcGroupBytes, 128),
+                   tc_desc(wimg + Lp.w_off + j * Lp.out_p * 16 + k * 2 * w_kgrp, w_kgrp, 128), id, acc);
+            acc = 1u;
+        }
     }
 }
 // delta chain: D[128, in_p] = sum_{i+j<=4} G_i W_j   (W_j: MN-major view of split array j)
@@ -305,11 +310,11 @@ __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
 }
 // executed by ALL lanes of warp 0
 __device__ __forceinline__ void tc_issue_table(const TcTable& tab, int begin, int n, uint32_t smem_base16, uint32_t tmem,
-                                               uint32_t b_extra16 = 0u) {
+                                               uint32_t b_extra16 = 0u, uint32_t a_extra16 = 0u) {
 #pragma unroll 2
     for (int i = begin; i < begin + n; ++i) {
         const TcMma& e = tab.e[i];
-        const uint64_t ad = ((uint64_t)e.a_hi << 32) | (uint64_t)(e.a_lo + smem_base16);
+        const uint64_t ad = ((uint64_t)e.a_hi << 32) | (uint64_t)(e.a_lo + smem_base16 + a_extra16);
         const uint64_t bd = ((uint64_t)e.b_hi << 32) | (uint64_t)(e.b_lo + smem_base16 + b_extra16);
         tc_mma_elect(tmem + e.d_col, ad, bd, e.idesc, e.acc);
     }
@@ -334,14 +339,16 @@ struct TcCtx {
 #ifdef UDE_TC_PROFILE
     long long prof[8];
 #endif
-    uint8_t* abuf_p;        // operand buffers (generic pointers)
+    uint8_t* abuf_p;        // operand buffers (generic pointers): forward image of the rate chain / sweep images
+    uint8_t* abuf2_p;       // forward image of the aug chain
     uint8_t* dbuf_p;
     uint32_t abuf, dbuf, wimg;   // shared-space addresses
     const float* bias;      // bias block in smem
     uint32_t tmem;          // TMEM base address
     uint64_t* bar;          // MMA completion barrier (forward products, delta chain)
     uint64_t* bar_b;        // second completion barrier (weight-gradient products)
-    uint32_t phase_b;
+    uint64_t* bar2;         // completion barrier of the aug chain's forward products
+    uint32_t phase_b, phase2;
     uint32_t sweep_par;     // sweep buffer of the current backward phase
     uint32_t sweep_buf_bytes;
     uint32_t smem_base16;   // dynamic shared-memory base >> 4 (MMA table addresses are relative)
@@ -355,31 +362,41 @@ struct TcCtx {
 // warps ARRIVE (non-blocking) once their shared-memory writes and TMEM reads of the phase are fenced, the
 // issuer SYNCs on the same named barrier and fires the phase's instruction list.  The issuer blocks in the
 // tensor queue for about as long as the MMAs run, which is exactly why it must not be an epilogue warp.
-constexpr int kTcBarOperands = 1;
-__device__ __forceinline__ void tc_operands_ready(TcCtx& c) {
+constexpr int kTcBarOperands = 1;      // rate chain / backward sweep
+constexpr int kTcBarOperands2 = 2;     // aug chain
+constexpr int kTcBarDrained = 3;       // backward sweep: weight-gradient accumulator read out
+// register hand-over (setmaxnreg): 65536 >= 32 * (kTcEpiWarps * kTcEpiRegs + 4 * kTcIssuerRegs)
+// (the pool is what the CTA got at launch: threads x launch registers; asking for more than the issuer warpgroup
+// released blocks forever.  With 16 epilogue warps ptxas fits the epilogue code into the 96 launch registers and
+// no hand-over is needed.)
+constexpr int kTcIssuerRegs = 40;
+constexpr int kTcEpiRegs = 232;
+constexpr bool kTcRegHandOver = kTcEpiWarps == 8;
+__device__ __forceinline__ void tc_operands_ready(TcCtx& c, int bar_id = kTcBarOperands) {
     TCP_T0();
     tc_proxy_fence();
     tc_fence_before();
-    asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarOperands), "n"(kTcBarThreads) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(bar_id), "n"(kTcBarThreads) : "memory");
     TCP_ADD(c, TCP_SYNC);
 }
-__device__ __forceinline__ void tc_issuer_wait_operands() {
-    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarOperands), "n"(kTcBarThreads) : "memory");
+__device__ __forceinline__ void tc_issuer_wait_operands(int bar_id = kTcBarOperands) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTcBarThreads) : "memory");
     tc_fence_after();
 }
 // issuer side of one forward phase / one backward phase
-__device__ __forceinline__ void tc_issuer_forward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem_fwd,
-                                                  uint64_t* bar) {
-    tc_issuer_wait_operands();
-    tc_issue_table(tab, Lp.mma_fwd, Lp.n_fwd, smem_base16, tmem_fwd);
+__device__ __forceinline__ void tc_issuer_forward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem_acc,
+                                                  uint64_t* bar, int bar_id, uint32_t a_extra16) {
+    tc_issuer_wait_operands(bar_id);
+    tc_issue_table(tab, Lp.mma_fwd, Lp.n_fwd, smem_base16, tmem_acc, 0u, a_extra16);
     tc_commit_elect(bar);
 }
 __device__ __forceinline__ void tc_issuer_backward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem,
-                                                   uint64_t* bar, uint64_t* bar_b, uint32_t sweep_buf16) {
+                                                   uint64_t* bar, uint64_t* bar_b, uint32_t sweep_buf16, bool first) {
     tc_issuer_wait_operands();
     const int n_dl = 6 * (Lp.out_p >> 4);
     tc_issue_table(tab, Lp.mma_bwd, n_dl, smem_base16, tmem);
     tc_commit_elect(bar);
+    if (!first) tc_issuer_wait_operands(kTcBarDrained);      // the previous layer's gradients have left the accumulator
     tc_issue_table(tab, Lp.mma_bwd + n_dl, Lp.n_bwd - n_dl, smem_base16, tmem, sweep_buf16);
     tc_commit_elect(bar_b);
 }
@@ -412,10 +429,10 @@ __device__ __forceinline__ void tc_prof_dump(TcCtx& c) {
 }
 
 // write 16 consecutive features [16*chunk, 16*chunk+16) of an activation of width `width` into Abuf
-__device__ __forceinline__ void tc_store_act16(const TcCtx& c, const float (&v)[16], int chunk, int width) {
+__device__ __forceinline__ void tc_store_act16(const TcCtx& c, uint8_t* img, const float (&v)[16], int chunk, int width) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-        uint8_t* base = c.abuf_p + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
+        uint8_t* base = img + (size_t)(2 * chunk + g) * kTcGroupBytes + c.t * 16;
         split3_store8(v + 8 * g, base + abuf_group(0, width) * kTcGroupBytes, base + abuf_group(1, width) * kTcGroupBytes,
                       base + abuf_group(2, width) * kTcGroupBytes);
     }
@@ -469,53 +486,82 @@ __device__ __forceinline__ void tc_store_ones(const TcCtx& c, int width) {
 
 // X (the MLP input u = vec(x), lib/models.py:119 Flatten) -> Abuf as the width-16 input of layer 0
 template <int D0>
-__device__ __forceinline__ void tc_store_x(const TcCtx& c, const float (&x)[D0], bool with_ones) {
+__device__ __forceinline__ void tc_store_x(const TcCtx& c, uint8_t* img, const float (&x)[D0]) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = i < D0 ? x[i] : 0.f;
-    tc_store_act16(c, v, 0, 16);
-    if (with_ones) tc_store_ones(c, 16);
+    tc_store_act16(c, img, v, 0, 16);
 }
 
 // ----------------------------------------------------------------------------------
-// forward of one net over the tile.  Pre: X in Abuf (not yet fenced).  Post: head outputs in
-// `head` (threads of warps 0-3), activations saved to TMEM when SAVE.
+// Forward of the nets over the tile.  The rate chain and the aug chain (lib/models.py:230-254: both nets eat the
+// same input) advance in LOCK STEP: while the epilogue warps turn the accumulator of rate layer p into the operand
+// image of rate layer p+1, the tensor pipe runs aug layer p, and vice versa.  Each chain has its own forward image,
+// accumulator columns, completion mbarrier and operand hand-off barrier.
 // ----------------------------------------------------------------------------------
+struct TcChain {
+    uint8_t* img;           // forward image of this chain
+    uint64_t* bar;          // completion barrier of this chain's products
+    uint32_t acc_col;       // TMEM accumulator (column offset)
+    int bar_id;             // operand hand-off barrier
+};
+// epilogue of layer Lp of one chain: accumulator -> bias, ELU -> (saved activation) -> image of the next layer,
+// or the head outputs (threads of warps 0-3)
 template <bool SAVE, int NH>
-__device__ __forceinline__ void tc_net_forward(const TcTable& tab, const TcLayer* Ls, int n_layers, int tm_fwd, TcCtx& c, float (&head)[NH]) {
-    for (int l = 0; l < n_layers; ++l) {
-        const TcLayer& Lp = Ls[l];
-        tc_operands_ready(c);
-        tc_wait_mma(c);
+__device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, bool last, const TcChain& ch_, uint32_t& phase, TcCtx& c,
+                                                float (&head)[NH]) {
+    {
         TCP_T0();
-        const uint32_t d0 = c.tmem + c.lane_addr + tm_fwd;
-        const float* bias = c.bias + Lp.b_off;
-        if (l + 1 < n_layers) {
-            for (int ch = c.h; ch < (Lp.out_p >> 4); ch += 2) {
-                float v0[16], v1[16], v2[16];
-                tc_ld16x3(d0 + 16 * ch, d0 + Lp.out_p + 16 * ch, d0 + 2 * Lp.out_p + 16 * ch, v0, v1, v2);
+        mbar_wait(ch_.bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        TCP_ADD(c, TCP_WAIT);
+    }
+    TCP_T0();
+    const uint32_t d0 = c.tmem + c.lane_addr + ch_.acc_col;
+    const float* bias = c.bias + Lp.b_off;
+    if (!last) {
+        for (int ch = c.h; ch < (Lp.out_p >> 4); ch += kTcSlots) {
+            float v0[16];
+            tc_ld16(d0 + 16 * ch, v0);
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
-                    v0[i + 0] = ((v2[i + 0] + v1[i + 0]) + v0[i + 0]) + b.x;
-                    v0[i + 1] = ((v2[i + 1] + v1[i + 1]) + v0[i + 1]) + b.y;
-                    v0[i + 2] = ((v2[i + 2] + v1[i + 2]) + v0[i + 2]) + b.z;
-                    v0[i + 3] = ((v2[i + 3] + v1[i + 3]) + v0[i + 3]) + b.w;
-                }
-                if (Lp.elu) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
-                }
-                if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
-                tc_store_act16(c, v0, ch, Lp.out_p);
+            for (int i = 0; i < 16; i += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
+                v0[i + 0] += b.x; v0[i + 1] += b.y; v0[i + 2] += b.z; v0[i + 3] += b.w;
             }
-        } else if (c.h == 0) {      // head: out_p == 16, warps 0-3 = trajectory threads
-            float v0[16], v1[16], v2[16];
-            tc_ld16x3(d0, d0 + Lp.out_p, d0 + 2 * Lp.out_p, v0, v1, v2);
+            if (Lp.elu) {
 #pragma unroll
-            for (int i = 0; i < NH; ++i) head[i] = ((v2[i] + v1[i]) + v0[i]) + bias[i];
+                for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
+            }
+            if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
+            tc_store_act16(c, ch_.img, v0, ch, Lp.out_p);
         }
         TCP_ADD(c, TCP_EPI_FWD);
+        tc_operands_ready(c, ch_.bar_id);
+    } else {
+        if (c.h == 0) {      // head: out_p == 16, warps 0-3 = trajectory threads
+            float v0[16];
+            tc_ld16(d0, v0);
+#pragma unroll
+            for (int i = 0; i < NH; ++i) head[i] = v0[i] + bias[i];
+        }
+        TCP_ADD(c, TCP_EPI_FWD);
+    }
+}
+// one RHS evaluation's MLPs: x (registers of the trajectory threads) -> head outputs
+template <bool SAVE, int R, int L>
+__device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain& cr, const TcChain& ca, TcCtx& c, bool is_traj,
+                                                const float (&x)[R * L], float (&o_r)[2 * R], float (&o_a)[3 * R]) {
+    if (is_traj) {
+        if (M.n_rate > 0) tc_store_x<R * L>(c, cr.img, x);
+        if (M.n_aug > 0) tc_store_x<R * L>(c, ca.img, x);
+    }
+    if (M.n_rate > 0) tc_operands_ready(c, cr.bar_id);
+    if (M.n_aug > 0) tc_operands_ready(c, ca.bar_id);
+    const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
+    for (int p = 0; p < np; ++p) {
+        if (p < M.n_rate) tc_fwd_epilogue<SAVE, 2 * R>(M.rate[p], p == M.n_rate - 1, cr, c.phase, c, o_r);
+        if (p < M.n_aug) tc_fwd_epilogue<SAVE, 3 * R>(M.aug[p], p == M.n_aug - 1, ca, c.phase2, c, o_a);
     }
 }
 
@@ -657,25 +703,33 @@ __device__ __forceinline__ void tc_side_reduce(const SideAcc& s, double n_evals,
 // ----------------------------------------------------------------------------------
 // the issuing warp replays the (data independent) phase sequence of its CTA
 // ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_issuer_nets_forward(const TcModel& M, const TcTable& tab, uint32_t smem_base16, uint32_t tmem_r,
+                                                       uint32_t tmem_a, uint64_t* bar, uint64_t* bar2) {
+    const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
+    const uint32_t a2 = (uint32_t)(M.off_abuf2 - M.off_abuf) >> 4;
+    for (int p = 0; p < np; ++p) {
+        if (p < M.n_rate) tc_issuer_forward(tab, M.rate[p], smem_base16, tmem_r, bar, kTcBarOperands, 0u);
+        if (p < M.n_aug) tc_issuer_forward(tab, M.aug[p], smem_base16, tmem_a, bar2, kTcBarOperands2, a2);
+    }
+}
 __device__ __forceinline__ void tc_issuer_loop_fwd(const TcModel& M, const TcTable& tab, long long n_my_tiles, int n_steps,
-                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar) {
+                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar, uint64_t* bar2) {
     for (long long tile = 0; tile < n_my_tiles; ++tile)
-        for (int e = 0; e < 4 * n_steps; ++e) {
-            for (int l = 0; l < M.n_rate; ++l) tc_issuer_forward(tab, M.rate[l], smem_base16, tmem, bar);
-            for (int l = 0; l < M.n_aug; ++l) tc_issuer_forward(tab, M.aug[l], smem_base16, tmem, bar);
-        }
+        for (int e = 0; e < 4 * n_steps; ++e)
+            tc_issuer_nets_forward(M, tab, smem_base16, tmem + M.tm_acc_fwd, tmem + M.tm_acc_fwd + M.tm_acc_stride, bar, bar2);
 }
 __device__ __forceinline__ void tc_issuer_loop_bwd(const TcModel& M, const TcTable& tab, long long n_my_tiles, int n_steps,
-                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar, uint64_t* bar_b) {
+                                                   uint32_t smem_base16, uint32_t tmem, uint64_t* bar, uint64_t* bar2, uint64_t* bar_b) {
     uint32_t par = 0;      // which of the two sweep buffers holds the current phase's activation image
     for (long long tile = 0; tile < n_my_tiles; ++tile)
         for (int e = 0; e < 4 * n_steps; ++e) {
-            for (int l = 0; l < M.n_rate; ++l) tc_issuer_forward(tab, M.rate[l], smem_base16, tmem + M.tm_fwd, bar);
-            for (int l = 0; l < M.n_aug; ++l) tc_issuer_forward(tab, M.aug[l], smem_base16, tmem + M.tm_fwd, bar);
+            tc_issuer_nets_forward(M, tab, smem_base16, tmem + M.tm_fwd, tmem + M.tm_fwd + M.tm_acc_stride, bar, bar2);
             for (int l = M.n_rate - 1; l >= 0; --l, par ^= 1u)
-                tc_issuer_backward(tab, M.rate[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u);
+                tc_issuer_backward(tab, M.rate[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u,
+                                   l == M.n_rate - 1);
             for (int l = M.n_aug - 1; l >= 0; --l, par ^= 1u)
-                tc_issuer_backward(tab, M.aug[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u);
+                tc_issuer_backward(tab, M.aug[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u,
+                                   l == M.n_aug - 1);
         }
 }
 
@@ -691,6 +745,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t wbar;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_b;
+    __shared__ __align__(8) uint64_t mbar2;
     __shared__ uint32_t tmem_slot;
     __shared__ double red[(kTcThreads / 32) * 8];
 
@@ -698,8 +753,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
         mbar_init(&wbar, 1);
         mbar_init(&mbar, 1);
         mbar_init(&mbar_b, 1);
+        mbar_init(&mbar2, 1);
     }
-    if (threadIdx.x < 32) tc_tmem_alloc<256>(&tmem_slot);
+    if (threadIdx.x < 32) tc_tmem_alloc<128>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -716,7 +772,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     c.tmem = tmem_slot;
     c.bar = &mbar;
     c.bar_b = &mbar_b;
+    c.bar2 = &mbar2;
+    c.abuf2_p = smem + M.off_abuf2;
     c.phase_b = 0;
+    c.phase2 = 0;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -728,6 +787,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     c.lane_addr = (uint32_t)(c.q * 32) << 16;
     const bool is_traj = warp < 4;
     tc_prof_init(c);
+    const TcChain chain_r{c.abuf_p, c.bar, (uint32_t)M.tm_acc_fwd, kTcBarOperands};
+    const TcChain chain_a{c.abuf2_p, c.bar2, (uint32_t)(M.tm_acc_fwd + M.tm_acc_stride), kTcBarOperands2};
 
     SideAcc side;
     side.clear();
@@ -736,13 +797,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     const long long tape_stage = (long long)DN * B;
 
     if (warp >= kTcEpiWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 8-11: issuer + 3 idle warps of its warpgroup
+        if (kTcRegHandOver) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcIssuerRegs));      // issuer + 3 idle warps of its warpgroup
         if (warp == kTcEpiWarps) {
         const long long n_my = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        tc_issuer_loop_fwd(M, tab, n_my, a.g.n_steps, c.smem_base16, c.tmem, c.bar);
+        tc_issuer_loop_fwd(M, tab, n_my, a.g.n_steps, c.smem_base16, c.tmem, c.bar, c.bar2);
         }
     } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (kTcRegHandOver) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * kTcTile;
         const bool valid = is_traj && (b0 + c.t < B);
@@ -778,14 +839,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                 for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
-                if (M.n_rate > 0) {
-                    if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<false, 2 * R>(tab, M.rate, M.n_rate, 0, c, o_r);
-                }
-                if (M.n_aug > 0) {
-                    if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<false, 3 * R>(tab, M.aug, M.n_aug, 0, c, o_a);
-                }
+                tc_nets_forward<false, R, L>(M, chain_r, chain_a, c, is_traj, x, o_r, o_a);
                 if (is_traj) {
                     float f[DN];
                     tc_rhs_tail<R, L>(M, x, o_r, o_a, valid, side, f);
@@ -858,7 +912,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     tc_side_reduce(side, 4.0 * a.g.n_steps, red, a.side_partial + (long long)blockIdx.x * 8);
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x < 32) tc_tmem_free<256>(c.tmem);
+    if (threadIdx.x < 32) tc_tmem_free<128>(c.tmem);
 }
 
 // ===================================================================================
@@ -887,7 +941,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
             tc_store_delta16(c, v, 0, 16);
         }
         const TcLayer& Lprev = Ls[n_layers - 2];
-        for (int ch = c.h; ch < (Lh.in_p >> 4); ch += 2) {
+        for (int ch = c.h; ch < (Lh.in_p >> 4); ch += kTcSlots) {
             float v[16];
             tc_ld16(c.tmem + c.lane_addr + Lprev.save_col + 16 * ch, v);
             tc_store_sweep16(c, c.sweep_par, v, ch, Lh.in_p);
@@ -897,14 +951,14 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
     }
     for (int l = n_layers - 1; l >= 0; --l) {
         const TcLayer& Lp = Ls[l];
-        uint4 sg[2][6];
+        uint4 sg[kTcChunksPerWarp][6];
         // ---- (1) while C_l and W_l run: image of a_{l-1} (input of layer l-1) into the other sweep buffer
         {
             TCP_T0();
             if (l >= 2) {
                 const TcLayer& Lq = Ls[l - 1];
                 const TcLayer& Lr = Ls[l - 2];
-                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += 2) {
+                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += kTcSlots) {
                     float v[16];
                     tc_ld16(c.tmem + c.lane_addr + Lr.save_col + 16 * ch, v);
                     tc_store_sweep16(c, c.sweep_par ^ 1u, v, ch, Lq.in_p);
@@ -919,7 +973,23 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
             }
             TCP_ADD(c, TCP_EPI_BWD);
         }
-        // ---- (2) C_l done: G_{l-1} = dA_l * ELU'(a_l), kept in registers
+        // ---- (1b) still waiting: ELU' factors of a_{l-1} from the saved activations
+        float ef[kTcChunksPerWarp][16];
+        if (l >= 1 && Ls[l - 1].elu) {
+            TCP_T0();
+#pragma unroll
+            for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                const int ch = c.h + kTcSlots * j;
+                if (ch < (Lp.in_p >> 4)) {
+                    float sv[16];
+                    tc_ld16(c.tmem + c.lane_addr + Ls[l - 1].save_col + 16 * ch, sv);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ef[j][i] = elu_grad_from_out(sv[i]);
+                }
+            }
+            TCP_ADD(c, TCP_EPI_BWD);
+        }
+        // ---- (2) C_l done: G_{l-1} = dA_l * ELU'(a_{l-1}), kept in registers
         tc_wait_mma(c);
         {
             TCP_T0();
@@ -927,14 +997,14 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                 const TcLayer& Lq = Ls[l - 1];
                 const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int ch = c.h + 2 * j;
+                for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                    const int ch = c.h + kTcSlots * j;
                     if (ch < (Lp.in_p >> 4)) {
-                        float d[16], sv[16];
-                        tc_ld16x2(dd + 16 * ch, c.tmem + c.lane_addr + Lq.save_col + 16 * ch, d, sv);
+                        float d[16];
+                        tc_ld16(dd + 16 * ch, d);
                         if (Lq.elu) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(sv[i]);
+                            for (int i = 0; i < 16; ++i) d[i] *= ef[j][i];
                         }
                         split3_pack16(d, sg[j]);
                     }
@@ -947,16 +1017,27 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
             }
             TCP_ADD(c, TCP_EPI_BWD);
         }
-        // ---- (3) W_l done: weight / bias gradients of layer l, TMEM -> per-CTA slab
-        //          (rows 16q..16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q)
+        // ---- (3) W_l done: Dbuf is free again -> G_{l-1} goes out and the issuer starts C_{l-1} right away
         tc_wait_mma_b(c);
         TCP_T0();
+        c.sweep_par ^= 1u;
+        if (l >= 1) {
+#pragma unroll
+            for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                const int ch = c.h + kTcSlots * j;
+                if (ch < (Lp.in_p >> 4)) tc_store_pack_delta(c, sg[j], ch, Lp.in_p);
+            }
+            tc_operands_ready(c);
+        }
+        // ---- (4) while C_{l-1} runs: weight / bias gradients of layer l, TMEM -> per-CTA slab
+        //          (rows 16q..16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q).
+        //          W_{l-1} overwrites the same accumulator: the issuer holds it back until every warp has drained.
         {
             const int m = 16 * c.q + c.lane;
             const bool act = c.lane < 16 && m < Lp.out;
             const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
             float* row = slab + Lp.slab_off + (size_t)m * (Lp.in_p + 8);
-            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += 2) {
+            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
                 float u[16], v[16];
                 tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
                 if (act) {
@@ -971,18 +1052,11 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                 if (act) atomicAdd(row + Lp.in_p, u[0]);
             }
         }
-        c.sweep_par ^= 1u;
         if (l >= 1) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int ch = c.h + 2 * j;
-                if (ch < (Lp.in_p >> 4)) tc_store_pack_delta(c, sg[j], ch, Lp.in_p);
-            }
-            TCP_ADD(c, TCP_EPI_BWD);
-            tc_operands_ready(c);
-        } else {
-            TCP_ADD(c, TCP_EPI_BWD);
+            tc_fence_before();
+            asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarDrained), "n"(kTcBarThreads) : "memory");
         }
+        TCP_ADD(c, TCP_EPI_BWD);
     }
 }
 
@@ -995,12 +1069,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t wbar;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_b;
+    __shared__ __align__(8) uint64_t mbar2;
     __shared__ uint32_t tmem_slot;
 
     if (threadIdx.x == 0) {
         mbar_init(&wbar, 1);
         mbar_init(&mbar, 1);
         mbar_init(&mbar_b, 1);
+        mbar_init(&mbar2, 1);
     }
     if (threadIdx.x < 32) tc_tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
@@ -1019,7 +1095,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     c.tmem = tmem_slot;
     c.bar = &mbar;
     c.bar_b = &mbar_b;
+    c.bar2 = &mbar2;
+    c.abuf2_p = smem + M.off_abuf2;
     c.phase_b = 0;
+    c.phase2 = 0;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -1031,6 +1110,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     c.lane_addr = (uint32_t)(c.q * 32) << 16;
     const bool is_traj = warp < 4;
     tc_prof_init(c);
+    const TcChain chain_r{c.abuf_p, c.bar, (uint32_t)M.tm_fwd, kTcBarOperands};
+    const TcChain chain_a{c.abuf2_p, c.bar2, (uint32_t)(M.tm_fwd + M.tm_acc_stride), kTcBarOperands2};
 
     // the operand buffers feed MN-major (K = trajectory) products: start from finite contents
     for (int i = threadIdx.x; i < (M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
@@ -1050,13 +1131,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     const int n_steps = a.g.n_steps;
 
     if (warp >= kTcEpiWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // warps 8-11: issuer + 3 idle warps of its warpgroup
+        if (kTcRegHandOver) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcIssuerRegs));      // issuer + 3 idle warps of its warpgroup
         if (warp == kTcEpiWarps) {
         const long long n_my = n_tiles > (long long)blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        tc_issuer_loop_bwd(M, tab, n_my, n_steps, c.smem_base16, c.tmem, c.bar, c.bar_b);
+        tc_issuer_loop_bwd(M, tab, n_my, n_steps, c.smem_base16, c.tmem, c.bar, c.bar2, c.bar_b);
         }
     } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    if (kTcRegHandOver) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * kTcTile;
         const bool valid = is_traj && (b0 + c.t < B);
@@ -1070,6 +1151,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < D0; ++i) x[i] = __ldg(src + i);
         }
+        float xt[DN];       // tape prefetch: stage input of the NEXT evaluation to be reversed
+#pragma unroll
+        for (int i = 0; i < DN; ++i)
+            xt[i] = (valid && n_steps > 0) ? __ldg(a.tape + (long long)(n_steps * 4 - 1) * tape_stage + (long long)i * B + b0 + c.t) : 0.f;
         int j = a.g.n_out - 1;
         for (int n = n_steps - 1; n >= 0; --n) {
             const float dt = __ldg(a.g.dt + n);
@@ -1122,26 +1207,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
             }
 #pragma unroll 1
             for (int stage = 3; stage >= 0; --stage) {
-                // ---- stage input from the tape
+                // ---- stage input from the tape (loaded one evaluation ahead: the latency hides behind the sweep)
 #pragma unroll
                 for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int cc = 0; cc < 3; ++cc)
-                        x[r * L + cc] = valid ? __ldg(a.tape + (long long)(n * 4 + stage) * tape_stage + (long long)(3 * r + cc) * B + b0 + c.t) : 0.f;
+                    for (int cc = 0; cc < 3; ++cc) x[r * L + cc] = xt[3 * r + cc];
+                {
+                    const int e_next = n * 4 + stage - 1;
+                    if (valid && e_next >= 0) {
+#pragma unroll
+                        for (int i = 0; i < DN; ++i) xt[i] = __ldg(a.tape + (long long)e_next * tape_stage + (long long)i * B + b0 + c.t);
+                    }
+                }
                 // ---- recompute the stage activations
                 float o_r[2 * R], o_a[3 * R];
 #pragma unroll
                 for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
-                if (M.n_rate > 0) {
-                    if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<true, 2 * R>(tab, M.rate, M.n_rate, M.tm_fwd, c, o_r);
-                }
-                if (M.n_aug > 0) {
-                    if (is_traj) tc_store_x<D0>(c, x, false);
-                    tc_net_forward<true, 3 * R>(tab, M.aug, M.n_aug, M.tm_fwd, c, o_a);
-                }
+                tc_nets_forward<true, R, L>(M, chain_r, chain_a, c, is_traj, x, o_r, o_a);
                 // ---- tail VJP
                 float d_r[2 * R], d_a[3 * R], xb[DN], dx[D0];
 #pragma unroll

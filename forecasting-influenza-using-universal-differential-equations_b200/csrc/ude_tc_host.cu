@@ -45,7 +45,7 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
         Lp.slab_off = M.slab_floats;
         M.slab_floats += Lp.out_p * (Lp.in_p + 8);
         Lp.mma_fwd = M.n_mma;
-        Lp.n_fwd = 3 * (Lp.in_p / 16);
+        Lp.n_fwd = 6 * (Lp.in_p / 16);
         M.n_mma += Lp.n_fwd;
         Lp.mma_bwd = M.n_mma;
         Lp.n_bwd = 6 * (Lp.out_p / 16) + 2 * (kTcTile / 16);
@@ -91,9 +91,11 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     M.tm_q_cols = 2 * max_in + 16;
     M.tm_dd = M.tm_q + M.tm_q_cols;
     M.tm_fwd = M.tm_q;
-    const int bwd_cols = (M.tm_dd + max_in) > (M.tm_fwd + 3 * max_out) ? (M.tm_dd + max_in) : (M.tm_fwd + 3 * max_out);
-    if (bwd_cols > 512 || 3 * max_out > 256) return false;
-    M.tm_cols_fwd = 256;
+    M.tm_acc_fwd = 0;
+    M.tm_acc_stride = max_out;
+    const int bwd_cols = (M.tm_dd + max_in) > (M.tm_fwd + 2 * max_out) ? (M.tm_dd + max_in) : (M.tm_fwd + 2 * max_out);
+    if (bwd_cols > 512 || 2 * max_out > 128) return false;
+    M.tm_cols_fwd = 128;
     M.tm_cols_bwd = 512;
     // shared memory
     M.off_w = 0;
@@ -104,8 +106,11 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     if (2 * M.sweep_buf_bytes > M.abuf_bytes) M.abuf_bytes = 2 * M.sweep_buf_bytes;
     M.off_dbuf = M.off_abuf + M.abuf_bytes;
     M.dbuf_bytes = dcap * kTcGroupBytes;
-    M.smem_bytes_fwd = M.off_abuf + M.abuf_bytes;
+    const int fwd_image_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;
+    M.off_abuf2 = M.off_abuf + fwd_image_bytes;
+    M.smem_bytes_fwd = M.off_abuf2 + fwd_image_bytes;
     M.smem_bytes_bwd = M.off_dbuf + M.dbuf_bytes;
+    if (M.smem_bytes_bwd < M.off_abuf2 + fwd_image_bytes) M.smem_bytes_bwd = M.off_abuf2 + fwd_image_bytes;
     if (M.n_mma > kTcMaxMma) return false;
     if (M.smem_bytes_bwd > kTcSmemLimit) return false;
     return true;

@@ -14,9 +14,16 @@
 
 namespace ude {
 
-constexpr int kTcThreads = 384;        // warps 0-7: epilogue (TMEM lane quarter w & 3, column half w >> 2); warp 8: MMA issuer;
-                                       // warps 9-11 only complete the issuer's warpgroup (setmaxnreg hands their registers over)
-constexpr int kTcEpiWarps = 8;
+// Epilogue warps: warp w works on TMEM lane quarter w & 3 and on the 16-column chunks ch = (w >> 2) + kTcSlots * i of a
+// layer; warps 0-3 additionally own the per-trajectory solver state.  The next warp is the MMA issuer; three more warps
+// only complete its warpgroup (setmaxnreg hands their registers over).
+#ifndef UDE_TC_EPI_WARPS
+#define UDE_TC_EPI_WARPS 8
+#endif
+constexpr int kTcEpiWarps = UDE_TC_EPI_WARPS;
+constexpr int kTcSlots = kTcEpiWarps / 4;              // column slots per lane quarter
+constexpr int kTcChunksPerWarp = (4 + kTcSlots - 1) / kTcSlots;   // layers are at most 64 = 4 x 16 columns wide
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 4);
 constexpr int kTcBarThreads = 32 * (kTcEpiWarps + 1);   // operand hand-off barrier: epilogue warps + issuer
 constexpr int kTcTile = 128;           // trajectories per tile (= UMMA M)
 constexpr int kTcMaxLayers = 4;        // nn.Linear layers per net on the tensor path
@@ -57,6 +64,7 @@ struct TcModel {
     int slab_floats;        // floats of one CTA gradient slab
     // ---- shared memory plan (byte offsets into the dynamic arena) ----
     int off_w, off_bias, off_abuf, off_dbuf;
+    int off_abuf2;          // forward image of the aug chain (aliases the sweep buffers / Dbuf region in the backward kernel)
     int n_mma;              // entries of the MMA table (kernel parameter)
     int abuf_bytes, dbuf_bytes;
     int sweep_buf_bytes;    // one of the two alternating sweep images [a2|a1|ones] inside Abuf
@@ -66,7 +74,10 @@ struct TcModel {
     int tm_q;               // weight-gradient accumulator: 8 + 2*max_in_p columns
     int tm_q_cols;
     int tm_dd;              // delta-chain accumulator: max_in_p columns
-    int tm_fwd;             // forward accumulator (3*max_out_p columns); aliases [tm_q, ...)
+    int tm_fwd;             // backward kernel: forward accumulator of the rate chain (max_out_p columns, aliases [tm_q, ...));
+                            // the aug chain's follows at + tm_acc_stride
+    int tm_acc_fwd;         // forward kernel: accumulator of the rate chain (the aug chain's at + tm_acc_stride)
+    int tm_acc_stride;
     int tm_cols_fwd, tm_cols_bwd;   // allocation sizes (power of two >= 32)
 };
 
