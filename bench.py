@@ -40,6 +40,23 @@ def _spec():
     return UdeSpec("FaFp", 1, 8, (64, 64, 32), (64, 64))
 
 
+def tensor_macs_per_tile_eval(spec) -> dict:
+    """bf16 MACs the tcgen05 kernels ISSUE per 128-trajectory tile and RHS evaluation (3-way bf16 split: six
+    products per fp32 product in the layer chain and the delta chain, three first-order products in the
+    weight-gradient contraction; dims padded to 16) -- mirrors csrc/ude_tc_host.cu:tc_fill_layers."""
+    r16 = lambda v: (v + 15) // 16 * 16
+    fwd = dlt = dw = 0
+    for sizes, head in ((spec.net_sizes, 2 * spec.n_regions), (spec.aug_sizes, 3 * spec.n_regions)):
+        if not len(sizes):
+            continue
+        dims = [16] + [r16(v) for v in sizes] + [r16(head)]
+        for i, o in zip(dims[:-1], dims[1:]):
+            fwd += 6 * 128 * i * o
+            dlt += 6 * 128 * i * o
+            dw += 8 * 16 * 64 * ((2 * i + 8) + (i + 8))
+    return {"fwd": fwd, "bwd": fwd + dlt + dw}
+
+
 def flops_per_traj_step(macs: int) -> dict:
     """Algorithmic flops (SURVEY.md 8d): forward 2/MAC, backward 4/MAC (dX + dW), 4 stages;
     the adjoint's recomputation of the stage activations is NOT counted."""
@@ -337,6 +354,28 @@ def run_ours(args):
                 peaks = json.load(f)
         except Exception:
             pass
+        path = int(L.ude_rk4_path(C.byref(desc)))
+        kname = "rk4_bwd_tc_kernel<1,8> (tcgen05)" if path == 1 else "rk4_bwd_kernel (FFMA)"
+        tensor = None
+        if path == 1:
+            tm = tensor_macs_per_tile_eval(spec)
+            evals = (B + 127) // 128 * n_steps * 4
+            t_peak = peaks.get("bf16_tflops")
+            t_bwd = 2.0 * tm["bwd"] * evals / (bwd_ms * 1e-3) / 1e12
+            t_fwd = 2.0 * tm["fwd"] * evals / (fwd_ms * 1e-3) / 1e12
+            tensor = {"note": "bf16 flops actually issued to the tensor pipe (6 bf16 products emulate one fp32 product; "
+                              "M=128, N<=64 instructions sit on the 50-cycle issue floor measured by tools/umma_probe.cu)",
+                      "bwd_issued_tflops": t_bwd, "fwd_issued_tflops": t_fwd, "peak": t_peak,
+                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst), of measured",
+                      "bwd_frac": t_bwd / t_peak if t_peak else None, "fwd_frac": t_fwd / t_peak if t_peak else None}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f)
+            if tr.get("batch") == B and tr.get("grid_steps") == n_steps:
+                traffic = tr.get("bwd_dram_bytes_per_launch")
+        except Exception:
+            pass
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -354,10 +393,12 @@ def run_ours(args):
                        "trajectories_per_gpu": B, "grid_steps": n_steps, "parallelism": f"trajectory-shard x{world}",
                        "l2": "inputs larger than L2 (y0 32 MiB + cotangent 288 MiB + tape 384 MiB per pass)",
                        "tile_traj": int(plan.tile_traj), "ctas": int(plan.n_ctas)},
-            "roofline": {"bound": "fp32-fma", "kernel": "rk4_bwd_kernel", "achieved": ach_bwd, "peak": float(peak.value),
+            "roofline": {"bound": "fp32-fma", "kernel": kname, "achieved": ach_bwd, "peak": float(peak.value),
                          "unit": "TFLOP/s", "frac": ach_bwd / float(peak.value) if peak.value else None,
                          "peak_source": "measured live: ude_measure_ffma_tflops (register-resident FFMA chains)",
-                         "traffic": None,
+                         "traffic": traffic,
+                         "algorithmic_bytes_per_launch": B * n_steps * (48 + 32) + B * 64,
+                         "tensor_pipe": tensor,
                          "fwd_kernel": {"achieved": ach_fwd, "frac": ach_fwd / float(peak.value) if peak.value else None,
                                         "ms": fwd_ms},
                          "bwd_ms": bwd_ms,
