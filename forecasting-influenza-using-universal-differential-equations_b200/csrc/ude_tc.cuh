@@ -505,11 +505,34 @@ struct TcChain {
     uint32_t acc_col;       // TMEM accumulator (column offset)
     int bar_id;             // operand hand-off barrier
 };
-// epilogue of layer Lp of one chain: accumulator -> bias, ELU -> (saved activation) -> image of the next layer,
-// or the head outputs (threads of warps 0-3)
+// The head layers (2R / 3R outputs, lib/models.py:124,172) are too thin for the tensor pipe (a 64 -> 3 product costs
+// as many instructions as 64 -> 64): they run on the FMA pipe in fp32.  Every epilogue warp folds the 16 activations it
+// just produced into NH partial dot products; the helper warps park theirs in shared memory, the trajectory warp of
+// the same lane quarter adds them up one lock-step slot later.
+constexpr int kTcBarHead = 4;       // named barriers 4..7: rate chain, lane quarter q; 8..11: aug chain
+struct TcHeadScratch {
+    float4 p[2][kTcSlots > 1 ? kTcSlots - 1 : 1][kTcTile];
+};
+template <int NH>
+__device__ __forceinline__ void tc_head_partial(const float* hw, int in_p, int ch, const float (&v)[16], float (&acc)[NH]) {
+#pragma unroll
+    for (int o = 0; o < NH; ++o) {
+        const float4* w4 = reinterpret_cast<const float4*>(hw + o * in_p + 16 * ch);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 w = w4[i];
+            acc[o] = fmaf(v[4 * i + 0], w.x, acc[o]);
+            acc[o] = fmaf(v[4 * i + 1], w.y, acc[o]);
+            acc[o] = fmaf(v[4 * i + 2], w.z, acc[o]);
+            acc[o] = fmaf(v[4 * i + 3], w.w, acc[o]);
+        }
+    }
+}
+// epilogue of hidden layer Lp of one chain: accumulator -> bias, ELU -> (saved activation) -> image of the next
+// layer, or (last hidden layer) the partial head products
 template <bool SAVE, int NH>
-__device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, bool last, const TcChain& ch_, uint32_t& phase, TcCtx& c,
-                                                float (&head)[NH]) {
+__device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer* Lhead, int chain, const TcChain& ch_, uint32_t& phase,
+                                                TcCtx& c, TcHeadScratch* hs, float (&head)[NH]) {
     {
         TCP_T0();
         mbar_wait(ch_.bar, phase);
@@ -520,38 +543,64 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, bool last, co
     TCP_T0();
     const uint32_t d0 = c.tmem + c.lane_addr + ch_.acc_col;
     const float* bias = c.bias + Lp.b_off;
-    if (!last) {
-        for (int ch = c.h; ch < (Lp.out_p >> 4); ch += kTcSlots) {
-            float v0[16];
-            tc_ld16(d0 + 16 * ch, v0);
+    float acc[NH];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
-                v0[i + 0] += b.x; v0[i + 1] += b.y; v0[i + 2] += b.z; v0[i + 3] += b.w;
-            }
-            if (Lp.elu) {
+    for (int o = 0; o < NH; ++o) acc[o] = 0.f;
+    for (int ch = c.h; ch < (Lp.out_p >> 4); ch += kTcSlots) {
+        float v0[16];
+        tc_ld16(d0 + 16 * ch, v0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
-            }
-            if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
-            tc_store_act16(c, ch_.img, v0, ch, Lp.out_p);
+        for (int i = 0; i < 16; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
+            v0[i + 0] += b.x; v0[i + 1] += b.y; v0[i + 2] += b.z; v0[i + 3] += b.w;
         }
-        TCP_ADD(c, TCP_EPI_FWD);
+        if (Lp.elu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
+        }
+        if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
+        if (Lhead) tc_head_partial<NH>(c.bias + Lhead->hw_off, Lhead->in_p, ch, v0, acc);
+        else tc_store_act16(c, ch_.img, v0, ch, Lp.out_p);
+    }
+    TCP_ADD(c, TCP_EPI_FWD);
+    if (!Lhead) {
         tc_operands_ready(c, ch_.bar_id);
     } else {
-        if (c.h == 0) {      // head: out_p == 16, warps 0-3 = trajectory threads
-            float v0[16];
-            tc_ld16(d0, v0);
+        if (c.h == 0) {
 #pragma unroll
-            for (int i = 0; i < NH; ++i) head[i] = v0[i] + bias[i];
+            for (int o = 0; o < NH; ++o) head[o] = acc[o];
+        } else {
+            hs->p[chain][c.h - 1][c.t] = make_float4(acc[0], acc[1], NH > 2 ? acc[NH - 1] : 0.f, 0.f);
+            if (kTcSlots > 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTcBarHead + 4 * chain + c.q), "n"(32 * kTcSlots) : "memory");
         }
-        TCP_ADD(c, TCP_EPI_FWD);
+        // the accumulator and the saved activations are read: nothing else to hand over (the next products of this
+        // chain are issued after the next evaluation's operands_ready, which these threads reach in program order)
     }
+}
+// trajectory warps: head = own partial + helpers' partials + bias
+template <int NH>
+__device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, TcCtx& c, const TcHeadScratch* hs, float (&head)[NH]) {
+    if (c.h != 0) return;
+    if (kTcSlots > 1) asm volatile("bar.sync %0, %1;" ::"r"(kTcBarHead + 4 * chain + c.q), "n"(32 * kTcSlots) : "memory");
+    const float* bias = c.bias + Lh.b_off;
+    float s[NH];
+#pragma unroll
+    for (int o = 0; o < NH; ++o) s[o] = 0.f;
+#pragma unroll
+    for (int k = 0; k + 1 < kTcSlots; ++k) {
+        const float4 p = hs->p[chain][k][c.t];
+        s[0] += p.x;
+        if (NH > 1) s[NH > 1 ? 1 : 0] += p.y;
+        if (NH > 2) s[NH > 2 ? 2 : 0] += p.z;
+    }
+#pragma unroll
+    for (int o = 0; o < NH; ++o) head[o] = (head[o] + s[o]) + bias[o];
 }
 // one RHS evaluation's MLPs: x (registers of the trajectory threads) -> head outputs
 template <bool SAVE, int R, int L>
-__device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain& cr, const TcChain& ca, TcCtx& c, bool is_traj,
-                                                const float (&x)[R * L], float (&o_r)[2 * R], float (&o_a)[3 * R]) {
+__device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain& cr, const TcChain& ca, TcCtx& c, TcHeadScratch* hs,
+                                                bool is_traj, const float (&x)[R * L], float (&o_r)[2 * R], float (&o_a)[3 * R]) {
+    static_assert(R == 1, "FFMA heads: 2R / 3R partials travel as one float4");
     if (is_traj) {
         if (M.n_rate > 0) tc_store_x<R * L>(c, cr.img, x);
         if (M.n_aug > 0) tc_store_x<R * L>(c, ca.img, x);
@@ -560,8 +609,10 @@ __device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain&
     if (M.n_aug > 0) tc_operands_ready(c, ca.bar_id);
     const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
     for (int p = 0; p < np; ++p) {
-        if (p < M.n_rate) tc_fwd_epilogue<SAVE, 2 * R>(M.rate[p], p == M.n_rate - 1, cr, c.phase, c, o_r);
-        if (p < M.n_aug) tc_fwd_epilogue<SAVE, 3 * R>(M.aug[p], p == M.n_aug - 1, ca, c.phase2, c, o_a);
+        if (p < M.n_rate - 1) tc_fwd_epilogue<SAVE, 2 * R>(M.rate[p], p == M.n_rate - 2 ? &M.rate[p + 1] : nullptr, 0, cr, c.phase, c, hs, o_r);
+        else if (p == M.n_rate - 1) tc_head_finish<2 * R>(M.rate[p], 0, c, hs, o_r);
+        if (p < M.n_aug - 1) tc_fwd_epilogue<SAVE, 3 * R>(M.aug[p], p == M.n_aug - 2 ? &M.aug[p + 1] : nullptr, 1, ca, c.phase2, c, hs, o_a);
+        else if (p == M.n_aug - 1) tc_head_finish<3 * R>(M.aug[p], 1, c, hs, o_a);
     }
 }
 
@@ -708,8 +759,8 @@ __device__ __forceinline__ void tc_issuer_nets_forward(const TcModel& M, const T
     const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
     const uint32_t a2 = (uint32_t)(M.off_abuf2 - M.off_abuf) >> 4;
     for (int p = 0; p < np; ++p) {
-        if (p < M.n_rate) tc_issuer_forward(tab, M.rate[p], smem_base16, tmem_r, bar, kTcBarOperands, 0u);
-        if (p < M.n_aug) tc_issuer_forward(tab, M.aug[p], smem_base16, tmem_a, bar2, kTcBarOperands2, a2);
+        if (p < M.n_rate - 1) tc_issuer_forward(tab, M.rate[p], smem_base16, tmem_r, bar, kTcBarOperands, 0u);
+        if (p < M.n_aug - 1) tc_issuer_forward(tab, M.aug[p], smem_base16, tmem_a, bar2, kTcBarOperands2, a2);
     }
 }
 __device__ __forceinline__ void tc_issuer_loop_fwd(const TcModel& M, const TcTable& tab, long long n_my_tiles, int n_steps,
@@ -746,6 +797,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_b;
     __shared__ __align__(8) uint64_t mbar2;
+    __shared__ __align__(16) TcHeadScratch head_scratch;
     __shared__ uint32_t tmem_slot;
     __shared__ double red[(kTcThreads / 32) * 8];
 
@@ -839,7 +891,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                 for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
-                tc_nets_forward<false, R, L>(M, chain_r, chain_a, c, is_traj, x, o_r, o_a);
+                tc_nets_forward<false, R, L>(M, chain_r, chain_a, c, &head_scratch, is_traj, x, o_r, o_a);
                 if (is_traj) {
                     float f[DN];
                     tc_rhs_tail<R, L>(M, x, o_r, o_a, valid, side, f);
@@ -1070,6 +1122,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t mbar;
     __shared__ __align__(8) uint64_t mbar_b;
     __shared__ __align__(8) uint64_t mbar2;
+    __shared__ __align__(16) TcHeadScratch head_scratch;
     __shared__ uint32_t tmem_slot;
 
     if (threadIdx.x == 0) {
@@ -1225,7 +1278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                 for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3 * R; ++i) o_a[i] = 0.f;
-                tc_nets_forward<true, R, L>(M, chain_r, chain_a, c, is_traj, x, o_r, o_a);
+                tc_nets_forward<true, R, L>(M, chain_r, chain_a, c, &head_scratch, is_traj, x, o_r, o_a);
                 // ---- tail VJP
                 float d_r[2 * R], d_a[3 * R], xb[DN], dx[D0];
 #pragma unroll
@@ -1311,6 +1364,13 @@ __global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* _
     }
     float* bias = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.b_off;
     for (int n = threadIdx.x; n < Lp.out_p; n += blockDim.x) bias[n] = n < Lp.out ? theta[Lp.th_b + n] : 0.f;
+    if (Lp.hw_off >= 0) {
+        float* hw = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.hw_off;
+        for (int idx = threadIdx.x; idx < Lp.out * Lp.in_p; idx += blockDim.x) {
+            const int n = idx / Lp.in_p, k = idx - n * Lp.in_p;
+            hw[idx] = k < Lp.in ? theta[Lp.th_w + n * Lp.in + k] : 0.f;
+        }
+    }
 }
 
 // side[0..7] = sum over CTA partials (fixed order)

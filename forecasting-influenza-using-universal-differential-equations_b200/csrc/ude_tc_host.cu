@@ -37,6 +37,11 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
         M.w_bytes += Lp.in_p * Lp.out_p * 6;
         Lp.b_off = M.n_bias;
         M.n_bias += Lp.out_p;
+        Lp.hw_off = -1;
+        if (i == n - 1) {               // head: forward runs on the FMA pipe from fp32 weights (ude_tc.cuh: tc_head_partial)
+            Lp.hw_off = M.n_bias;
+            M.n_bias += Lp.out * Lp.in_p;
+        }
         Lp.save_col = -1;
         if (i < n - 1) {
             Lp.save_col = M.tm_save;
@@ -45,7 +50,7 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
         Lp.slab_off = M.slab_floats;
         M.slab_floats += Lp.out_p * (Lp.in_p + 8);
         Lp.mma_fwd = M.n_mma;
-        Lp.n_fwd = 6 * (Lp.in_p / 16);
+        Lp.n_fwd = (i == n - 1) ? 0 : 6 * (Lp.in_p / 16);
         M.n_mma += Lp.n_fwd;
         Lp.mma_bwd = M.n_mma;
         Lp.n_bwd = 6 * (Lp.out_p / 16) + 2 * (kTcTile / 16);

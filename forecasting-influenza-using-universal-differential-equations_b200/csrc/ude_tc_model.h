@@ -35,12 +35,12 @@ struct TcLayer {
     int elu;                // ELU on the output
     int w_off;              // byte offset of the weight image inside the packed blob
     int b_off;              // float offset of the bias (padded to out_p) in the bias block
+    int hw_off;             // heads only: float offset (bias block) of the fp32 weights [out][in_p] of the FFMA forward
     int save_col;           // TMEM column of the saved OUTPUT activation (backward), -1 for the head
     int th_w, th_b;         // offsets into theta (PyTorch layout)
     int slab_off;           // float offset of this layer's gradient rows in a CTA slab: [out_p][8 + in_p]
     int mma_fwd, n_fwd;     // forward instructions of this layer in the MMA table
     int mma_bwd, n_bwd;     // delta-chain + weight-gradient instructions
-    int pad_;
 };
 
 // Weight image of one layer (bf16): [k/8][s = 0..2][n (out_p)][k%8], i.e. for every group of 8
