@@ -326,9 +326,13 @@ __device__ __forceinline__ void tc_issue_table(const TcTable& tab, int begin, in
 __device__ unsigned long long g_tc_prof[2 * 8];
 #define TCP_T0() const long long tcp_t0 = clock64()
 #define TCP_ADD(c, id) (c).prof[id] += clock64() - tcp_t0
+#define TCP_T1() const long long tcp_t1 = clock64()
+#define TCP_ADD1(c, id) (c).prof[id] += clock64() - tcp_t1
 #else
 #define TCP_T0()
 #define TCP_ADD(c, id)
+#define TCP_T1()
+#define TCP_ADD1(c, id)
 #endif
 enum { TCP_SYNC = 0, TCP_ISSUE = 1, TCP_WAIT = 2, TCP_EPI_FWD = 3, TCP_EPI_BWD = 4, TCP_TAIL = 5, TCP_TOTAL = 6 };
 
@@ -1023,7 +1027,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                 tc_store_sweep16(c, c.sweep_par ^ 1u, v, 0, 16);
                 tc_store_sweep_ones(c, c.sweep_par ^ 1u, 16);
             }
-            TCP_ADD(c, TCP_EPI_BWD);
+            TCP_ADD(c, TCP_ISSUE);
         }
         // ---- (1b) still waiting: ELU' factors of a_{l-1} from the saved activations
         float ef[kTcChunksPerWarp][16];
@@ -1039,7 +1043,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                     for (int i = 0; i < 16; ++i) ef[j][i] = elu_grad_from_out(sv[i]);
                 }
             }
-            TCP_ADD(c, TCP_EPI_BWD);
+            TCP_ADD(c, TCP_ISSUE);
         }
         // ---- (2) C_l done: G_{l-1} = dA_l * ELU'(a_{l-1}), kept in registers
         tc_wait_mma(c);
@@ -1081,34 +1085,39 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
             }
             tc_operands_ready(c);
         }
+        TCP_ADD(c, TCP_EPI_BWD);
+        TCP_T1();
         // ---- (4) while C_{l-1} runs: weight / bias gradients of layer l, TMEM -> per-CTA slab
         //          (rows 16q..16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q).
         //          W_{l-1} overwrites the same accumulator: the issuer holds it back until every warp has drained.
         {
+            // slab layout of a layer: [in_p / 4][64 rows] float4, then [64] bias sums -- the 16 active lanes of a warp
+            // (rows 16q .. 16q+15) add 256 contiguous bytes per instruction, i.e. whole 32-byte sectors
             const int m = 16 * c.q + c.lane;
             const bool act = c.lane < 16 && m < Lp.out;
             const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
-            float* row = slab + Lp.slab_off + (size_t)m * (Lp.in_p + 8);
+            float* base = slab + Lp.slab_off;
             for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
                 float u[16], v[16];
                 tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
                 if (act) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
-                        red_add_v4(row + 16 * ch + i, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
+                        red_add_v4(base + ((size_t)(4 * ch + (i >> 2)) * 64 + m) * 4, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2],
+                                   u[i + 3] + v[i + 3]);
                 }
             }
             if (c.h == 0) {
                 float u[16];
                 tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
-                if (act) atomicAdd(row + Lp.in_p, u[0]);
+                if (act) atomicAdd(base + 64 * Lp.in_p + m, u[0]);
             }
         }
         if (l >= 1) {
             tc_fence_before();
             asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarDrained), "n"(kTcBarThreads) : "memory");
         }
-        TCP_ADD(c, TCP_EPI_BWD);
+        TCP_ADD1(c, TCP_TAIL);
     }
 }
 
@@ -1395,11 +1404,11 @@ __global__ void tc_reduce_dtheta_kernel(const __grid_constant__ TcModel M, const
         if (e >= Lp.th_w && e < Lp.th_w + Lp.in * Lp.out) {
             const int k = e - Lp.th_w;
             const int row = k / Lp.in, col = k - row * Lp.in;
-            sidx = Lp.slab_off + row * (Lp.in_p + 8) + col;
+            sidx = Lp.slab_off + ((col >> 2) * 64 + row) * 4 + (col & 3);
             break;
         }
         if (e >= Lp.th_b && e < Lp.th_b + Lp.out) {
-            sidx = Lp.slab_off + (e - Lp.th_b) * (Lp.in_p + 8) + Lp.in_p;
+            sidx = Lp.slab_off + 64 * Lp.in_p + (e - Lp.th_b);
             break;
         }
     }

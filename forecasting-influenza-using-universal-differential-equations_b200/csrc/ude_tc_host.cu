@@ -48,7 +48,7 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
             M.tm_save += Lp.out_p;
         }
         Lp.slab_off = M.slab_floats;
-        M.slab_floats += Lp.out_p * (Lp.in_p + 8);
+        M.slab_floats += 64 * Lp.in_p + 64;
         Lp.mma_fwd = M.n_mma;
         Lp.n_fwd = (i == n - 1) ? 0 : 6 * (Lp.in_p / 16);
         M.n_mma += Lp.n_fwd;

@@ -38,7 +38,7 @@ struct TcLayer {
     int hw_off;             // heads only: float offset (bias block) of the fp32 weights [out][in_p] of the FFMA forward
     int save_col;           // TMEM column of the saved OUTPUT activation (backward), -1 for the head
     int th_w, th_b;         // offsets into theta (PyTorch layout)
-    int slab_off;           // float offset of this layer's gradient rows in a CTA slab: [out_p][8 + in_p]
+    int slab_off;           // float offset of this layer's gradients in a CTA slab: [in_p / 4][64 rows] float4 + [64] bias sums
     int mma_fwd, n_fwd;     // forward instructions of this layer in the MMA table
     int mma_bwd, n_bwd;     // delta-chain + weight-gradient instructions
 };

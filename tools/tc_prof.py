@@ -32,7 +32,7 @@ mod = module_from_spec(spec, init_theta(spec, 0), 1.0, "cuda")
 y0 = synth_y0(B, 1, 8, seed=1).cuda()
 t = torch.arange(9.)
 L = ude_b200.lib()
-names = ["sync", "issue", "wait", "epi_fwd", "epi_bwd", "tail", "total", "-"]
+names = ["sync", "image+elu'", "wait", "epi_fwd", "delta_epi", "flush", "total", "-"]
 
 
 def dump(tag):
