@@ -50,8 +50,9 @@ def tensor_macs_per_tile_eval(spec) -> dict:
         if not len(sizes):
             continue
         dims = [16] + [r16(v) for v in sizes] + [r16(head)]
-        for i, o in zip(dims[:-1], dims[1:]):
-            fwd += 6 * 128 * i * o
+        for li, (i, o) in enumerate(zip(dims[:-1], dims[1:])):
+            if li < len(dims) - 2:          # the head layers' forward runs on the FMA pipe (fp32)
+                fwd += 6 * 128 * i * o
             dlt += 6 * 128 * i * o
             dw += 8 * 16 * 64 * ((2 * i + 8) + (i + 8))
     return {"fwd": fwd, "bwd": fwd + dlt + dw}

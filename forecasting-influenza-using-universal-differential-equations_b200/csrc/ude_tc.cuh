@@ -346,6 +346,7 @@ struct TcCtx {
     uint8_t* abuf_p;        // operand buffers (generic pointers): forward image of the rate chain / sweep images
     uint8_t* abuf2_p;       // forward image of the aug chain
     uint8_t* dbuf_p;
+    uint8_t* ghead_p;       // [G1 | G2] image of the head cotangent
     uint32_t abuf, dbuf, wimg;   // shared-space addresses
     const float* bias;      // bias block in smem
     uint32_t tmem;          // TMEM base address
@@ -394,15 +395,33 @@ __device__ __forceinline__ void tc_issuer_forward(const TcTable& tab, const TcLa
     tc_issue_table(tab, Lp.mma_fwd, Lp.n_fwd, smem_base16, tmem_acc, 0u, a_extra16);
     tc_commit_elect(bar);
 }
-__device__ __forceinline__ void tc_issuer_backward(const TcTable& tab, const TcLayer& Lp, uint32_t smem_base16, uint32_t tmem,
-                                                   uint64_t* bar, uint64_t* bar_b, uint32_t sweep_buf16, bool first) {
-    tc_issuer_wait_operands();
-    const int n_dl = 6 * (Lp.out_p >> 4);
-    tc_issue_table(tab, Lp.mma_bwd, n_dl, smem_base16, tmem);
-    tc_commit_elect(bar);
-    if (!first) tc_issuer_wait_operands(kTcBarDrained);      // the previous layer's gradients have left the accumulator
-    tc_issue_table(tab, Lp.mma_bwd + n_dl, Lp.n_bwd - n_dl, smem_base16, tmem, sweep_buf16);
+// issuer side of the backward sweep of one net (mirrors tc_net_backward): the head's Wh^T g and the first layer's
+// W0^T delta0 run on the FMA pipe, so the delta chain C_l exists for the hidden layers l = n-2 .. 1 only; the
+// weight-gradient products W_l of every layer share one accumulator and wait for the previous one to be drained.
+__device__ __forceinline__ void tc_issuer_net_backward(const TcTable& tab, const TcLayer* Ls, int n, uint32_t smem_base16, uint32_t tmem,
+                                                       uint64_t* bar, uint64_t* bar_b, uint32_t buf16, uint32_t& par) {
+    tc_issuer_wait_operands();                                   // step H1: head image + image of a_{n-2}
+    tc_issue_table(tab, Ls[n - 1].mma_w, Ls[n - 1].n_w, smem_base16, tmem, par ? buf16 : 0u);
     tc_commit_elect(bar_b);
+    par ^= 1u;
+    tc_issuer_wait_operands();                                   // step H2: G_{n-2}, image of a_{n-3}
+    tc_issue_table(tab, Ls[n - 2].mma_c, Ls[n - 2].n_c, smem_base16, tmem);
+    tc_commit_elect(bar);
+    tc_issuer_wait_operands(kTcBarDrained);                      // the head's gradients have left the accumulator
+    tc_issue_table(tab, Ls[n - 2].mma_w, Ls[n - 2].n_w, smem_base16, tmem, par ? buf16 : 0u);
+    tc_commit_elect(bar_b);
+    for (int l = n - 2; l >= 1; --l) {
+        tc_issuer_wait_operands();                               // G_{l-1}
+        if (l - 1 >= 1) {
+            tc_issue_table(tab, Ls[l - 1].mma_c, Ls[l - 1].n_c, smem_base16, tmem);
+            tc_commit_elect(bar);
+        }
+        par ^= 1u;
+        tc_issuer_wait_operands(kTcBarDrained);
+        tc_issue_table(tab, Ls[l - 1].mma_w, Ls[l - 1].n_w, smem_base16, tmem, par ? buf16 : 0u);
+        tc_commit_elect(bar_b);
+    }
+    par ^= 1u;
 }
 __device__ __forceinline__ void tc_wait_mma(TcCtx& c) {
     TCP_T0();
@@ -514,6 +533,7 @@ struct TcChain {
 // just produced into NH partial dot products; the helper warps park theirs in shared memory, the trajectory warp of
 // the same lane quarter adds them up one lock-step slot later.
 constexpr int kTcBarHead = 4;       // named barriers 4..7: rate chain, lane quarter q; 8..11: aug chain
+constexpr int kTcBarSweep = 12;     // named barriers 12..15: backward sweep, lane quarter q
 struct TcHeadScratch {
     float4 p[2][kTcSlots > 1 ? kTcSlots - 1 : 1][kTcTile];
 };
@@ -779,12 +799,8 @@ __device__ __forceinline__ void tc_issuer_loop_bwd(const TcModel& M, const TcTab
     for (long long tile = 0; tile < n_my_tiles; ++tile)
         for (int e = 0; e < 4 * n_steps; ++e) {
             tc_issuer_nets_forward(M, tab, smem_base16, tmem + M.tm_fwd, tmem + M.tm_fwd + M.tm_acc_stride, bar, bar2);
-            for (int l = M.n_rate - 1; l >= 0; --l, par ^= 1u)
-                tc_issuer_backward(tab, M.rate[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u,
-                                   l == M.n_rate - 1);
-            for (int l = M.n_aug - 1; l >= 0; --l, par ^= 1u)
-                tc_issuer_backward(tab, M.aug[l], smem_base16, tmem, bar, bar_b, par ? (uint32_t)(M.sweep_buf_bytes >> 4) : 0u,
-                                   l == M.n_aug - 1);
+            if (M.n_rate > 0) tc_issuer_net_backward(tab, M.rate, M.n_rate, smem_base16, tmem, bar, bar_b, (uint32_t)(M.sweep_buf_bytes >> 4), par);
+            if (M.n_aug > 0) tc_issuer_net_backward(tab, M.aug, M.n_aug, smem_base16, tmem, bar, bar_b, (uint32_t)(M.sweep_buf_bytes >> 4), par);
         }
 }
 
@@ -821,6 +837,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     TcCtx c;
     c.abuf_p = smem + M.off_abuf;
     c.dbuf_p = smem + M.off_dbuf;
+    c.ghead_p = smem + M.off_ghead;
     c.abuf = smem_u32(smem + M.off_abuf);
     c.dbuf = smem_u32(smem + M.off_dbuf);
     c.wimg = smem_u32(smem + M.off_w);
@@ -974,151 +991,256 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
 // ===================================================================================
 // backward kernel (discrete adjoint)
 // ===================================================================================
-// Sweep one net backwards over the tile.  Pre: G_head in `g_head` (trajectory threads), saved
-// activations in TMEM, x in registers.  Post: dx[0..D0) += W_0^T G_0 (trajectory threads), weight and
-// bias gradients added to the CTA slab.
+// Sweep one net backwards over the tile.  Pre: head cotangent in `g_head` (trajectory threads), saved activations
+// in TMEM, x in registers.  Post: dx[0..D0) += W_0^T G_0 (trajectory threads), weight and bias gradients added to the
+// CTA slab.
 //
-// Software pipeline of one phase (layer l): the delta-chain MMAs C_l and the weight-gradient MMAs W_l are
-// issued back to back (by the issuing warp) with separate completion barriers.  While they run the epilogue
-// warps (1) write the NEXT phase's activation image a_{l-1} into the other sweep buffer (it needs nothing
-// from the MMAs), (2) once C_l is done build G_{l-1} in registers; only (3) the store of G_{l-1} -- W_l still
-// reads G_l from the same buffer -- and the gradient flush wait for W_l.
+// The sweep is a dependency chain  G_l -> (delta products C_l) -> epilogue -> G_{l-1} -> ...  and every link costs a
+// tensor-pipe round trip, so the two thin ends of the chain stay on the CUDA cores: the head's Wh^T g (NH <= 3
+// outputs) and the first layer's W0^T G_0 (D0 <= 16 inputs) are FMA loops over fp32 weights in shared memory.
+// Everything that is not on the chain runs behind it: the weight-gradient products W_l (own completion barrier, one
+// shared accumulator guarded by the "drained" barrier), the activation image of the NEXT layer (two alternating
+// sweep buffers), the ELU' factors, and the flush of the gradients into the per-CTA slab.
+//
+//   step H1        : G_{n-1} (registers) -> head image [G1|G2], image of a_{n-2};  ready -> issuer: W_{n-1}
+//   step H2        : (behind W_{n-1}) G_{n-2} = (Wh^T g) * ELU'(a_{n-2}) -> Dbuf, image of a_{n-3};  ready -> issuer:
+//                    C_{n-2}, then W_{n-2} once the head's gradients are flushed out of the shared accumulator
+//   step l=n-2..1  : image for W_{l-1};  ELU'(a_{l-1});  wait C_l;  G_{l-1} -> registers (l = 1: partial W0^T G_0);
+//                    wait W_l;  G_{l-1} -> Dbuf;  ready -> issuer: C_{l-1} (l >= 2), W_{l-1};  flush W_l
+//   step 0         : wait W_0, flush;  partial dx of the helper warps -> trajectory warps (through TMEM)
+__device__ __forceinline__ void tc_flush_grad(const TcModel& M, const TcLayer& Lp, TcCtx& c, float* slab) {
+    // slab layout of a layer: [in_p / 4][64 rows] float4, then [64] bias sums -- the 16 active lanes of a warp
+    // (rows 16q .. 16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q) add 256 contiguous bytes per
+    // instruction, i.e. whole 32-byte sectors
+    const int m = 16 * c.q + c.lane;
+    const bool act = c.lane < 16 && m < Lp.out;
+    const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
+    float* base = slab + Lp.slab_off;
+    for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
+        float u[16], v[16];
+        tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                red_add_v4(base + ((size_t)(4 * ch + (i >> 2)) * 64 + m) * 4, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2],
+                           u[i + 3] + v[i + 3]);
+        }
+    }
+    if (c.h == 0) {
+        float u[16];
+        tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
+        if (act) atomicAdd(base + 64 * Lp.in_p + m, u[0]);
+    }
+}
+__device__ __forceinline__ void tc_drained(TcCtx& c) {
+    tc_fence_before();
+    asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarDrained), "n"(kTcBarThreads) : "memory");
+}
+// image [a2 | a1 | ones] of the INPUT of layer li (a_{li-1}, or x for the first layer) into sweep buffer `buf`
+template <int D0>
+__device__ __forceinline__ void tc_sweep_image(const TcLayer* Ls, int li, uint32_t buf, TcCtx& c, const float (&x)[D0], bool is_traj) {
+    if (li >= 1) {
+        const int w = Ls[li].in_p;
+        for (int ch = c.h; ch < (w >> 4); ch += kTcSlots) {
+            float v[16];
+            tc_ld16(c.tmem + c.lane_addr + Ls[li - 1].save_col + 16 * ch, v);
+            tc_store_sweep16(c, buf, v, ch, w);
+        }
+        if (c.h == 0) tc_store_sweep_ones(c, buf, w);
+    } else if (is_traj) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = i < D0 ? x[i] : 0.f;
+        tc_store_sweep16(c, buf, v, 0, 16);
+        tc_store_sweep_ones(c, buf, 16);
+    }
+}
 template <int D0, int NH>
-__device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer* Ls, int n_layers, TcCtx& c,
+__device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer* Ls, int n, int chain, TcCtx& c,
                                                 const float (&g_head)[NH], const float (&x)[D0], float* slab,
                                                 float (&dx)[D0], bool is_traj) {
-    // ---- operands of the head phase: G_{n-1} (width 16, zero padded) and a_{n-1}
+    const uint32_t tm_x = c.tmem + c.lane_addr + M.tm_dd;      // exchange columns between the warps of a lane quarter
+    // sync/sync exchanges of a lane quarter's warps; NOT the forward heads' arrive/sync barriers: a helper warp that
+    // arrived there could reach this sync before its trajectory warp consumed the arrival
+    const int bar_q = kTcBarSweep + c.q;
+    (void)chain;
+    uint32_t par = c.sweep_par;
+    float pdx[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pdx[i] = 0.f;
+    // ---------------- step H
     {
-        const TcLayer& Lh = Ls[n_layers - 1];
+        TCP_T0();
+        const TcLayer& Lh = Ls[n - 1];
+        const TcLayer& Lq = Ls[n - 2];
+        float gh[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) gh[i] = 0.f;
         if (is_traj) {
-            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = i < NH ? g_head[i] : 0.f;
-            tc_store_delta16(c, v, 0, 16);
+            for (int i = 0; i < NH; ++i) gh[i] = g_head[i];
+            uint8_t* base = c.ghead_p + c.t * 16;              // [G1 | G2], two 8-feature groups each
+            split2_store8(gh, base, base + 2 * kTcGroupBytes);
+            split2_store8(gh + 8, base + kTcGroupBytes, base + 3 * kTcGroupBytes);
+            if (kTcSlots > 1) {
+                tc_st16(tm_x, gh);
+                tc_fence_before();
+            }
         }
-        const TcLayer& Lprev = Ls[n_layers - 2];
+        if (kTcSlots > 1) {
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_q), "n"(32 * kTcSlots) : "memory");
+            if (!is_traj) {
+                tc_fence_after();
+                tc_ld16(tm_x, gh);
+            }
+        }
+        // H1: operands of the head's weight-gradient products -> the issuer starts W_{n-1} right away
         for (int ch = c.h; ch < (Lh.in_p >> 4); ch += kTcSlots) {
-            float v[16];
-            tc_ld16(c.tmem + c.lane_addr + Lprev.save_col + 16 * ch, v);
-            tc_store_sweep16(c, c.sweep_par, v, ch, Lh.in_p);
+            float sv[16];
+            tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
+            tc_store_sweep16(c, par, sv, ch, Lh.in_p);
         }
-        if (c.h == 0) tc_store_sweep_ones(c, c.sweep_par, Lh.in_p);
+        if (c.h == 0) tc_store_sweep_ones(c, par, Lh.in_p);
         tc_operands_ready(c);
+        // H2 (behind W_{n-1}): G_{n-2} = (Wh^T g) * ELU'(a_{n-2}) on the FMA pipe, image of a_{n-3}
+        const float* hw = c.bias + Lh.hw_off;
+        for (int ch = c.h; ch < (Lh.in_p >> 4); ch += kTcSlots) {
+            float d[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = 0.f;
+#pragma unroll
+            for (int o = 0; o < NH; ++o) {
+                const float4* w4 = reinterpret_cast<const float4*>(hw + o * Lh.in_p + 16 * ch);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = w4[i];
+                    d[4 * i + 0] = fmaf(gh[o], w.x, d[4 * i + 0]);
+                    d[4 * i + 1] = fmaf(gh[o], w.y, d[4 * i + 1]);
+                    d[4 * i + 2] = fmaf(gh[o], w.z, d[4 * i + 2]);
+                    d[4 * i + 3] = fmaf(gh[o], w.w, d[4 * i + 3]);
+                }
+            }
+            if (Lq.elu) {
+                float sv[16];
+                tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(sv[i]);
+            }
+            tc_store_delta16(c, d, ch, Lh.in_p);
+        }
+        tc_sweep_image<D0>(Ls, n - 2, par ^ 1u, c, x, is_traj);
+        tc_operands_ready(c);
+        TCP_ADD(c, TCP_ISSUE);
+        // the head's gradients leave the shared accumulator (W_{n-1} ran behind H2), W_{n-2} may follow
+        tc_wait_mma_b(c);
+        TCP_T1();
+        tc_flush_grad(M, Lh, c, slab);
+        tc_drained(c);
+        TCP_ADD1(c, TCP_TAIL);
     }
-    for (int l = n_layers - 1; l >= 0; --l) {
+    // ---------------- steps l = n-2 .. 1
+    for (int l = n - 2; l >= 1; --l) {
         const TcLayer& Lp = Ls[l];
+        const TcLayer& Lq = Ls[l - 1];
+        par ^= 1u;                              // W_l reads sweep buffer `par`
         uint4 sg[kTcChunksPerWarp][6];
-        // ---- (1) while C_l and W_l run: image of a_{l-1} (input of layer l-1) into the other sweep buffer
-        {
-            TCP_T0();
-            if (l >= 2) {
-                const TcLayer& Lq = Ls[l - 1];
-                const TcLayer& Lr = Ls[l - 2];
-                for (int ch = c.h; ch < (Lq.in_p >> 4); ch += kTcSlots) {
-                    float v[16];
-                    tc_ld16(c.tmem + c.lane_addr + Lr.save_col + 16 * ch, v);
-                    tc_store_sweep16(c, c.sweep_par ^ 1u, v, ch, Lq.in_p);
-                }
-                if (c.h == 0) tc_store_sweep_ones(c, c.sweep_par ^ 1u, Lq.in_p);
-            } else if (l == 1 && is_traj) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = i < D0 ? x[i] : 0.f;
-                tc_store_sweep16(c, c.sweep_par ^ 1u, v, 0, 16);
-                tc_store_sweep_ones(c, c.sweep_par ^ 1u, 16);
-            }
-            TCP_ADD(c, TCP_ISSUE);
-        }
-        // ---- (1b) still waiting: ELU' factors of a_{l-1} from the saved activations
         float ef[kTcChunksPerWarp][16];
-        if (l >= 1 && Ls[l - 1].elu) {
-            TCP_T0();
-#pragma unroll
-            for (int j = 0; j < kTcChunksPerWarp; ++j) {
-                const int ch = c.h + kTcSlots * j;
-                if (ch < (Lp.in_p >> 4)) {
-                    float sv[16];
-                    tc_ld16(c.tmem + c.lane_addr + Ls[l - 1].save_col + 16 * ch, sv);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) ef[j][i] = elu_grad_from_out(sv[i]);
-                }
-            }
-            TCP_ADD(c, TCP_ISSUE);
-        }
-        // ---- (2) C_l done: G_{l-1} = dA_l * ELU'(a_{l-1}), kept in registers
-        tc_wait_mma(c);
         {
             TCP_T0();
-            if (l >= 1) {
-                const TcLayer& Lq = Ls[l - 1];
-                const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
+            tc_sweep_image<D0>(Ls, l - 1, par ^ 1u, c, x, is_traj);
+            if (Lq.elu) {
 #pragma unroll
                 for (int j = 0; j < kTcChunksPerWarp; ++j) {
                     const int ch = c.h + kTcSlots * j;
                     if (ch < (Lp.in_p >> 4)) {
-                        float d[16];
-                        tc_ld16(dd + 16 * ch, d);
-                        if (Lq.elu) {
+                        float sv[16];
+                        tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) d[i] *= ef[j][i];
-                        }
-                        split3_pack16(d, sg[j]);
+                        for (int i = 0; i < 16; ++i) ef[j][i] = elu_grad_from_out(sv[i]);
                     }
                 }
-            } else if (is_traj) {
-                float d[16];
-                tc_ld16(c.tmem + c.lane_addr + M.tm_dd, d);
+            }
+            TCP_ADD(c, TCP_ISSUE);
+        }
+        tc_wait_mma(c);                         // C_l
+        {
+            TCP_T0();
+            const uint32_t dd = c.tmem + c.lane_addr + M.tm_dd;
 #pragma unroll
-                for (int i = 0; i < D0; ++i) dx[i] += d[i];
+            for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                const int ch = c.h + kTcSlots * j;
+                if (ch < (Lp.in_p >> 4)) {
+                    float d[16];
+                    tc_ld16(dd + 16 * ch, d);
+                    if (Lq.elu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) d[i] *= ef[j][i];
+                    }
+                    if (l == 1) {               // W0^T G_0 on the FMA pipe (fp32 rows of W0, broadcast loads)
+                        const float* w0 = c.bias + Lq.w0_off + (size_t)(16 * ch) * M.w0_stride;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                            for (int k4 = 0; k4 < (D0 + 3) / 4; ++k4) {
+                                const float4 w = *reinterpret_cast<const float4*>(w0 + i * M.w0_stride + 4 * k4);
+                                pdx[4 * k4 + 0] = fmaf(d[i], w.x, pdx[4 * k4 + 0]);
+                                pdx[4 * k4 + 1] = fmaf(d[i], w.y, pdx[4 * k4 + 1]);
+                                pdx[4 * k4 + 2] = fmaf(d[i], w.z, pdx[4 * k4 + 2]);
+                                pdx[4 * k4 + 3] = fmaf(d[i], w.w, pdx[4 * k4 + 3]);
+                            }
+                        }
+                    }
+                    split3_pack16(d, sg[j]);
+                }
             }
             TCP_ADD(c, TCP_EPI_BWD);
         }
-        // ---- (3) W_l done: Dbuf is free again -> G_{l-1} goes out and the issuer starts C_{l-1} right away
-        tc_wait_mma_b(c);
-        TCP_T0();
-        c.sweep_par ^= 1u;
-        if (l >= 1) {
+        tc_wait_mma_b(c);                       // W_l: Dbuf is free again, its gradients are complete
+        {
+            TCP_T0();
 #pragma unroll
             for (int j = 0; j < kTcChunksPerWarp; ++j) {
                 const int ch = c.h + kTcSlots * j;
                 if (ch < (Lp.in_p >> 4)) tc_store_pack_delta(c, sg[j], ch, Lp.in_p);
             }
             tc_operands_ready(c);
+            TCP_ADD(c, TCP_EPI_BWD);
         }
-        TCP_ADD(c, TCP_EPI_BWD);
         TCP_T1();
-        // ---- (4) while C_{l-1} runs: weight / bias gradients of layer l, TMEM -> per-CTA slab
-        //          (rows 16q..16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q).
-        //          W_{l-1} overwrites the same accumulator: the issuer holds it back until every warp has drained.
-        {
-            // slab layout of a layer: [in_p / 4][64 rows] float4, then [64] bias sums -- the 16 active lanes of a warp
-            // (rows 16q .. 16q+15) add 256 contiguous bytes per instruction, i.e. whole 32-byte sectors
-            const int m = 16 * c.q + c.lane;
-            const bool act = c.lane < 16 && m < Lp.out;
-            const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
-            float* base = slab + Lp.slab_off;
-            for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
-                float u[16], v[16];
-                tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
-                if (act) {
+        tc_flush_grad(M, Lp, c, slab);
+        tc_drained(c);
+        TCP_ADD1(c, TCP_TAIL);
+    }
+    // ---------------- step 0
+    par ^= 1u;
+    tc_wait_mma_b(c);
+    {
+        TCP_T1();
+        tc_flush_grad(M, Ls[0], c, slab);
+        if (kTcSlots > 1) {
+            if (!is_traj) {
+                tc_st16(tm_x + 16 * (c.h - 1), pdx);
+                tc_fence_before();
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_q), "n"(32 * kTcSlots) : "memory");
+            if (is_traj) {
+                tc_fence_after();
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        red_add_v4(base + ((size_t)(4 * ch + (i >> 2)) * 64 + m) * 4, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2],
-                                   u[i + 3] + v[i + 3]);
+                for (int k = 0; k + 1 < kTcSlots; ++k) {
+                    float o[16];
+                    tc_ld16(tm_x + 16 * k, o);
+#pragma unroll
+                    for (int i = 0; i < D0; ++i) pdx[i] += o[i];
                 }
             }
-            if (c.h == 0) {
-                float u[16];
-                tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
-                if (act) atomicAdd(base + 64 * Lp.in_p + m, u[0]);
-            }
         }
-        if (l >= 1) {
-            tc_fence_before();
-            asm volatile("bar.arrive %0, %1;" ::"n"(kTcBarDrained), "n"(kTcBarThreads) : "memory");
+        if (is_traj) {
+#pragma unroll
+            for (int i = 0; i < D0; ++i) dx[i] += pdx[i];
         }
         TCP_ADD1(c, TCP_TAIL);
     }
+    c.sweep_par = par ^ 1u;
 }
 
 template <int R, int L>
@@ -1150,6 +1272,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     TcCtx c;
     c.abuf_p = smem + M.off_abuf;
     c.dbuf_p = smem + M.off_dbuf;
+    c.ghead_p = smem + M.off_ghead;
     c.abuf = smem_u32(smem + M.off_abuf);
     c.dbuf = smem_u32(smem + M.off_dbuf);
     c.wimg = smem_u32(smem + M.off_w);
@@ -1176,8 +1299,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     const TcChain chain_a{c.abuf2_p, c.bar2, (uint32_t)(M.tm_fwd + M.tm_acc_stride), kTcBarOperands2};
 
     // the operand buffers feed MN-major (K = trajectory) products: start from finite contents
-    for (int i = threadIdx.x; i < (M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
-        reinterpret_cast<uint4*>(smem + M.off_abuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (M.off_abuf - M.off_ghead + M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
+        reinterpret_cast<uint4*>(smem + M.off_ghead)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
     float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1304,8 +1427,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                     for (int i = 0; i < DN; ++i) g[i] = stage == 3 ? kb[3][i] : (stage == 2 ? kb[2][i] : (stage == 1 ? kb[1][i] : kb[0][i]));
                     tc_rhs_tail_vjp<R, L>(M, x, o_r, o_a, valid, gs, g, d_r, d_a, xb);
                 }
-                if (M.n_rate > 0) tc_net_backward<D0, 2 * R>(M, M.rate, M.n_rate, c, d_r, x, slab, dx, is_traj);
-                if (M.n_aug > 0) tc_net_backward<D0, 3 * R>(M, M.aug, M.n_aug, c, d_a, x, slab, dx, is_traj);
+                if (M.n_rate > 0) tc_net_backward<D0, 2 * R>(M, M.rate, M.n_rate, 0, c, d_r, x, slab, dx, is_traj);
+                if (M.n_aug > 0) tc_net_backward<D0, 3 * R>(M, M.aug, M.n_aug, 1, c, d_a, x, slab, dx, is_traj);
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 if (is_traj) {
 #pragma unroll
@@ -1373,6 +1496,13 @@ __global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* _
     }
     float* bias = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.b_off;
     for (int n = threadIdx.x; n < Lp.out_p; n += blockDim.x) bias[n] = n < Lp.out ? theta[Lp.th_b + n] : 0.f;
+    if (Lp.w0_off >= 0) {
+        float* w0 = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.w0_off;
+        for (int idx = threadIdx.x; idx < Lp.out_p * M.w0_stride; idx += blockDim.x) {
+            const int n = idx / M.w0_stride, k = idx - n * M.w0_stride;
+            w0[idx] = (n < Lp.out && k < Lp.in) ? theta[Lp.th_w + n * Lp.in + k] : 0.f;
+        }
+    }
     if (Lp.hw_off >= 0) {
         float* hw = reinterpret_cast<float*>(blob + M.w_bytes) + Lp.hw_off;
         for (int idx = threadIdx.x; idx < Lp.out * Lp.in_p; idx += blockDim.x) {

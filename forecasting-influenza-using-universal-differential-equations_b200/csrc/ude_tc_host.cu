@@ -17,7 +17,7 @@ static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit 
 
 static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes, int head_elu, int& th) {
     if (n == 0) return true;
-    if (n < 2 || n > kTcMaxLayers) return false;
+    if (n < 3 || n > kTcMaxLayers) return false;      // at least two hidden layers + head (every net of the reference)
     int n_in = M.D0, in_p = M.D0_p;
     for (int i = 0; i < n; ++i) {
         TcLayer& Lp = Ls[i];
@@ -52,9 +52,17 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
         Lp.mma_fwd = M.n_mma;
         Lp.n_fwd = (i == n - 1) ? 0 : 6 * (Lp.in_p / 16);
         M.n_mma += Lp.n_fwd;
-        Lp.mma_bwd = M.n_mma;
-        Lp.n_bwd = 6 * (Lp.out_p / 16) + 2 * (kTcTile / 16);
-        M.n_mma += Lp.n_bwd;
+        Lp.mma_c = M.n_mma;
+        Lp.n_c = (i == 0 || i == n - 1) ? 0 : 6 * (Lp.out_p / 16);
+        M.n_mma += Lp.n_c;
+        Lp.mma_w = M.n_mma;
+        Lp.n_w = 2 * (kTcTile / 16);
+        M.n_mma += Lp.n_w;
+        Lp.w0_off = -1;
+        if (i == 0) {                   // first layer: W0^T delta0 runs on the FMA pipe from fp32 weights
+            Lp.w0_off = M.n_bias;
+            M.n_bias += Lp.out_p * M.w0_stride;
+        }
         n_in = Lp.out;
         in_p = Lp.out_p;
     }
@@ -70,6 +78,7 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     M.L = d->latent_dim;
     M.D0 = M.R * M.L;
     M.D0_p = 16;
+    M.w0_stride = M.D0 <= 8 ? 8 : 16;
     if (!(M.R == 1 && (M.L == 4 || M.L == 8 || M.L == 16))) return false;      // instantiated (R, L) pairs
     M.n_rate = d->n_rate_layers;
     M.n_aug = d->n_aug_layers;
@@ -105,7 +114,8 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     // shared memory
     M.off_w = 0;
     M.off_bias = M.w_bytes;
-    M.off_abuf = (int)align_up(M.blob_bytes, 1024);
+    M.off_ghead = (int)align_up(M.blob_bytes, 1024);
+    M.off_abuf = M.off_ghead + 4 * kTcGroupBytes;       // the M = 64 view of the image over-reads into Abuf (finite data)
     M.sweep_buf_bytes = (2 * (max_in / 8) + 1) * kTcGroupBytes;
     M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;               // forward image [a2|a1|ones|a3]
     if (2 * M.sweep_buf_bytes > M.abuf_bytes) M.abuf_bytes = 2 * M.sweep_buf_bytes;
@@ -139,9 +149,13 @@ static void tc_build_table(const TcModel& M, TcTable& T, bool backward) {
         TcRecorder rf{T.e + Lp.mma_fwd, 0};
         tc_issue_forward(Lp, (uint32_t)M.off_abuf, (uint32_t)M.off_w, 0u, rf);
         if (backward) {
-            TcRecorder rb{T.e + Lp.mma_bwd, 0};
-            tc_issue_delta(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_w, (uint32_t)M.tm_dd, rb);
-            tc_issue_dw(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_abuf, (uint32_t)M.tm_q, rb);
+            const bool head = (li == M.n_rate - 1) || (li == nl - 1);
+            if (Lp.n_c > 0) {
+                TcRecorder rc{T.e + Lp.mma_c, 0};
+                tc_issue_delta(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_w, (uint32_t)M.tm_dd, rc);
+            }
+            TcRecorder rw{T.e + Lp.mma_w, 0};
+            tc_issue_dw(Lp, (uint32_t)(head ? M.off_ghead : M.off_dbuf), (uint32_t)M.off_abuf, (uint32_t)M.tm_q, rw);
         }
     }
 }

@@ -40,7 +40,10 @@ struct TcLayer {
     int th_w, th_b;         // offsets into theta (PyTorch layout)
     int slab_off;           // float offset of this layer's gradients in a CTA slab: [in_p / 4][64 rows] float4 + [64] bias sums
     int mma_fwd, n_fwd;     // forward instructions of this layer in the MMA table
-    int mma_bwd, n_bwd;     // delta-chain + weight-gradient instructions
+    int mma_c, n_c;         // delta-chain instructions (hidden layers 1 .. n-2 only: the first layer's W0^T delta0 and the
+                            // head's Wh^T g run on the FMA pipe)
+    int mma_w, n_w;         // weight-gradient instructions
+    int w0_off;             // first layer only: float offset (bias block) of the fp32 weights [out_p][w0_stride]
 };
 
 // Weight image of one layer (bf16): [k/8][s = 0..2][n (out_p)][k%8], i.e. for every group of 8
@@ -64,6 +67,8 @@ struct TcModel {
     int slab_floats;        // floats of one CTA gradient slab
     // ---- shared memory plan (byte offsets into the dynamic arena) ----
     int off_w, off_bias, off_abuf, off_dbuf;
+    int off_ghead;          // [G1 | G2] image of the head cotangent (16 wide), read by the head's weight-gradient products
+    int w0_stride;          // 8 (D0 <= 8) or 16
     int off_abuf2;          // forward image of the aug chain (aliases the sweep buffers / Dbuf region in the backward kernel)
     int n_mma;              // entries of the MMA table (kernel parameter)
     int abuf_bytes, dbuf_bytes;
