@@ -354,6 +354,8 @@ struct TcCtx {
     uint64_t* bar_b;        // second completion barrier (weight-gradient products)
     uint64_t* bar2;         // completion barrier of the aug chain's forward products
     uint32_t phase_b, phase2;
+    uint32_t phase_h[2];    // head hand-off barriers (trajectory warps)
+    uint8_t* stage_p;       // backward: gradient staging buffer of the bulk reductions
     uint32_t sweep_par;     // sweep buffer of the current backward phase
     uint32_t sweep_buf_bytes;
     uint32_t smem_base16;   // dynamic shared-memory base >> 4 (MMA table addresses are relative)
@@ -532,11 +534,15 @@ struct TcChain {
 // as many instructions as 64 -> 64): they run on the FMA pipe in fp32.  Every epilogue warp folds the 16 activations it
 // just produced into NH partial dot products; the helper warps park theirs in shared memory, the trajectory warp of
 // the same lane quarter adds them up one lock-step slot later.
-constexpr int kTcBarHead = 4;       // named barriers 4..7: rate chain, lane quarter q; 8..11: aug chain
 constexpr int kTcBarSweep = 12;     // named barriers 12..15: backward sweep, lane quarter q
+constexpr int kTcBarFlush = 4;      // backward sweep: gradient staging buffer (the 8 epilogue warps)
 struct TcHeadScratch {
     float4 p[2][kTcSlots > 1 ? kTcSlots - 1 : 1][kTcTile];
+    uint64_t bar[2][4];             // helper warps -> trajectory warp of the lane quarter, per chain (count kTcSlots - 1)
 };
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int NH>
 __device__ __forceinline__ void tc_head_partial(const float* hw, int in_p, int ch, const float (&v)[16], float (&acc)[NH]) {
 #pragma unroll
@@ -595,7 +601,8 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
             for (int o = 0; o < NH; ++o) head[o] = acc[o];
         } else {
             hs->p[chain][c.h - 1][c.t] = make_float4(acc[0], acc[1], NH > 2 ? acc[NH - 1] : 0.f, 0.f);
-            if (kTcSlots > 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTcBarHead + 4 * chain + c.q), "n"(32 * kTcSlots) : "memory");
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive(&hs->bar[chain][c.q]);
         }
         // the accumulator and the saved activations are read: nothing else to hand over (the next products of this
         // chain are issued after the next evaluation's operands_ready, which these threads reach in program order)
@@ -603,9 +610,12 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
 }
 // trajectory warps: head = own partial + helpers' partials + bias
 template <int NH>
-__device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, TcCtx& c, const TcHeadScratch* hs, float (&head)[NH]) {
+__device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, TcCtx& c, TcHeadScratch* hs, uint32_t& phase, float (&head)[NH]) {
     if (c.h != 0) return;
-    if (kTcSlots > 1) asm volatile("bar.sync %0, %1;" ::"r"(kTcBarHead + 4 * chain + c.q), "n"(32 * kTcSlots) : "memory");
+    if (kTcSlots > 1) {
+        mbar_wait(&hs->bar[chain][c.q], phase);
+        phase ^= 1u;
+    }
     const float* bias = c.bias + Lh.b_off;
     float s[NH];
 #pragma unroll
@@ -634,9 +644,9 @@ __device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain&
     const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
     for (int p = 0; p < np; ++p) {
         if (p < M.n_rate - 1) tc_fwd_epilogue<SAVE, 2 * R>(M.rate[p], p == M.n_rate - 2 ? &M.rate[p + 1] : nullptr, 0, cr, c.phase, c, hs, o_r);
-        else if (p == M.n_rate - 1) tc_head_finish<2 * R>(M.rate[p], 0, c, hs, o_r);
+        else if (p == M.n_rate - 1) tc_head_finish<2 * R>(M.rate[p], 0, c, hs, c.phase_h[0], o_r);
         if (p < M.n_aug - 1) tc_fwd_epilogue<SAVE, 3 * R>(M.aug[p], p == M.n_aug - 2 ? &M.aug[p + 1] : nullptr, 1, ca, c.phase2, c, hs, o_a);
-        else if (p == M.n_aug - 1) tc_head_finish<3 * R>(M.aug[p], 1, c, hs, o_a);
+        else if (p == M.n_aug - 1) tc_head_finish<3 * R>(M.aug[p], 1, c, hs, c.phase_h[1], o_a);
     }
 }
 
@@ -826,6 +836,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
         mbar_init(&mbar, 1);
         mbar_init(&mbar_b, 1);
         mbar_init(&mbar2, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&head_scratch.bar[i >> 2][i & 3], kTcSlots > 1 ? kTcSlots - 1 : 1);
     }
     if (threadIdx.x < 32) tc_tmem_alloc<128>(&tmem_slot);
     tc_fence_before();
@@ -849,6 +860,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     c.abuf2_p = smem + M.off_abuf2;
     c.phase_b = 0;
     c.phase2 = 0;
+    c.phase_h[0] = c.phase_h[1] = 0;
+    c.stage_p = smem + M.off_stage;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -1008,28 +1021,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
 //   step l=n-2..1  : image for W_{l-1};  ELU'(a_{l-1});  wait C_l;  G_{l-1} -> registers (l = 1: partial W0^T G_0);
 //                    wait W_l;  G_{l-1} -> Dbuf;  ready -> issuer: C_{l-1} (l >= 2), W_{l-1};  flush W_l
 //   step 0         : wait W_0, flush;  partial dx of the helper warps -> trajectory warps (through TMEM)
+// Gradients of one layer, TMEM -> staging buffer -> ONE bulk reduction into the CTA slab
+// (cp.reduce.async.bulk.add.f32, SASS UBLKRED): the L2 atomics run on the copy engine in the background instead of
+// backing up the LSU behind 16-byte reductions.  Staging/slab layout of a layer: [in_p / 4][64 rows] float4, then
+// [64] bias sums (rows 16q .. 16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q).
+// Returns after the accumulator has been read; the caller releases it to the issuer ("drained").
 __device__ __forceinline__ void tc_flush_grad(const TcModel& M, const TcLayer& Lp, TcCtx& c, float* slab) {
-    // slab layout of a layer: [in_p / 4][64 rows] float4, then [64] bias sums -- the 16 active lanes of a warp
-    // (rows 16q .. 16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q) add 256 contiguous bytes per
-    // instruction, i.e. whole 32-byte sectors
     const int m = 16 * c.q + c.lane;
-    const bool act = c.lane < 16 && m < Lp.out;
+    const bool act = c.lane < 16;
     const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
-    float* base = slab + Lp.slab_off;
+    float4* st = reinterpret_cast<float4*>(c.stage_p);
+    // the previous bulk reduction must have read the staging buffer
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
     for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
         float u[16], v[16];
         tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
         if (act) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
-                red_add_v4(base + ((size_t)(4 * ch + (i >> 2)) * 64 + m) * 4, u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2],
-                           u[i + 3] + v[i + 3]);
+                st[(4 * ch + (i >> 2)) * 64 + m] = make_float4(u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
         }
     }
     if (c.h == 0) {
         float u[16];
         tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
-        if (act) atomicAdd(base + 64 * Lp.in_p + m, u[0]);
+        if (act) reinterpret_cast<float*>(c.stage_p)[64 * Lp.in_p + m] = u[0];
+    }
+}
+// second half: hand the staged gradients to the copy engine (call after tc_drained)
+__device__ __forceinline__ void tc_flush_commit(const TcLayer& Lp, TcCtx& c, float* slab) {
+    tc_proxy_fence();
+    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(64 * Lp.in_p + 64) * 4u;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(slab + Lp.slab_off),
+                     "r"(smem_u32(c.stage_p)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 }
 __device__ __forceinline__ void tc_drained(TcCtx& c) {
@@ -1079,6 +1108,11 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         if (is_traj) {
 #pragma unroll
             for (int i = 0; i < NH; ++i) gh[i] = g_head[i];
+        }
+        // the head image shares its 8 KB with the gradient staging buffer: the last bulk reduction must have read it
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
+        if (is_traj) {
             uint8_t* base = c.ghead_p + c.t * 16;              // [G1 | G2], two 8-feature groups each
             split2_store8(gh, base, base + 2 * kTcGroupBytes);
             split2_store8(gh + 8, base + kTcGroupBytes, base + 3 * kTcGroupBytes);
@@ -1136,6 +1170,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         TCP_T1();
         tc_flush_grad(M, Lh, c, slab);
         tc_drained(c);
+        tc_flush_commit(Lh, c, slab);
         TCP_ADD1(c, TCP_TAIL);
     }
     // ---------------- steps l = n-2 .. 1
@@ -1209,6 +1244,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         TCP_T1();
         tc_flush_grad(M, Lp, c, slab);
         tc_drained(c);
+        tc_flush_commit(Lp, c, slab);
         TCP_ADD1(c, TCP_TAIL);
     }
     // ---------------- step 0
@@ -1217,6 +1253,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
     {
         TCP_T1();
         tc_flush_grad(M, Ls[0], c, slab);
+        tc_flush_commit(Ls[0], c, slab);
         if (kTcSlots > 1) {
             if (!is_traj) {
                 tc_st16(tm_x + 16 * (c.h - 1), pdx);
@@ -1261,6 +1298,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         mbar_init(&mbar, 1);
         mbar_init(&mbar_b, 1);
         mbar_init(&mbar2, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&head_scratch.bar[i >> 2][i & 3], kTcSlots > 1 ? kTcSlots - 1 : 1);
     }
     if (threadIdx.x < 32) tc_tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
@@ -1284,6 +1322,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     c.abuf2_p = smem + M.off_abuf2;
     c.phase_b = 0;
     c.phase2 = 0;
+    c.phase_h[0] = c.phase_h[1] = 0;
+    c.stage_p = smem + M.off_stage;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -1299,8 +1339,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     const TcChain chain_a{c.abuf2_p, c.bar2, (uint32_t)(M.tm_fwd + M.tm_acc_stride), kTcBarOperands2};
 
     // the operand buffers feed MN-major (K = trajectory) products: start from finite contents
-    for (int i = threadIdx.x; i < (M.off_abuf - M.off_ghead + M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
-        reinterpret_cast<uint4*>(smem + M.off_ghead)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (M.off_abuf - M.off_stage + M.abuf_bytes + M.dbuf_bytes) / 16; i += kTcThreads)
+        reinterpret_cast<uint4*>(smem + M.off_stage)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
     float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1467,6 +1507,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         }
     }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // gradient reductions have landed
     tc_prof_dump(c);
     tc_fence_before();
     __syncthreads();

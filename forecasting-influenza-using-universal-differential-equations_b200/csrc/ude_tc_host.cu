@@ -114,7 +114,11 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     // shared memory
     M.off_w = 0;
     M.off_bias = M.w_bytes;
-    M.off_ghead = (int)align_up(M.blob_bytes, 1024);
+    // [staging of the gradient bulk reductions: (64 max_in + 64) floats, its LAST 8 KB double as the head image]
+    // (the head image is dead once W_{n-1} has completed, i.e. before the first gradient flush of the net)
+    const int stage_bytes = (64 * 64 + 64) * 4;
+    M.off_stage = (int)align_up(M.blob_bytes, 128);
+    M.off_ghead = M.off_stage + stage_bytes - 4 * kTcGroupBytes;
     M.off_abuf = M.off_ghead + 4 * kTcGroupBytes;       // the M = 64 view of the image over-reads into Abuf (finite data)
     M.sweep_buf_bytes = (2 * (max_in / 8) + 1) * kTcGroupBytes;
     M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;               // forward image [a2|a1|ones|a3]

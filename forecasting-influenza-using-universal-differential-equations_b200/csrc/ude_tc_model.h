@@ -69,6 +69,7 @@ struct TcModel {
     int off_w, off_bias, off_abuf, off_dbuf;
     int off_ghead;          // [G1 | G2] image of the head cotangent (16 wide), read by the head's weight-gradient products
     int w0_stride;          // 8 (D0 <= 8) or 16
+    int off_stage;          // backward: staging buffer of the gradient bulk reductions (64 x 64 floats + 64 bias sums)
     int off_abuf2;          // forward image of the aug chain (aliases the sweep buffers / Dbuf region in the backward kernel)
     int n_mma;              // entries of the MMA table (kernel parameter)
     int abuf_bytes, dbuf_bytes;
