@@ -537,8 +537,8 @@ struct TcChain {
 constexpr int kTcBarSweep = 12;     // named barriers 12..15: backward sweep, lane quarter q
 constexpr int kTcBarFlush = 4;      // backward sweep: gradient staging buffer (the 8 epilogue warps)
 struct TcHeadScratch {
-    float4 p[2][kTcSlots > 1 ? kTcSlots - 1 : 1][kTcTile];
-    uint64_t bar[2][4];             // helper warps -> trajectory warp of the lane quarter, per chain (count kTcSlots - 1)
+    uint64_t bar[2][4];             // helper warps -> trajectory warp of the lane quarter, per chain (count kTcSlots - 1);
+                                    // the partial sums themselves travel through the chain's (idle) TMEM accumulator
 };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -600,7 +600,13 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
 #pragma unroll
             for (int o = 0; o < NH; ++o) head[o] = acc[o];
         } else {
-            hs->p[chain][c.h - 1][c.t] = make_float4(acc[0], acc[1], NH > 2 ? acc[NH - 1] : 0.f, 0.f);
+            float pv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pv[i] = 0.f;
+#pragma unroll
+            for (int o = 0; o < NH; ++o) pv[o] = acc[o];
+            tc_st16(d0 + 16 * (c.h - 1), pv);
+            tc_fence_before();
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&hs->bar[chain][c.q]);
         }
@@ -610,11 +616,13 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
 }
 // trajectory warps: head = own partial + helpers' partials + bias
 template <int NH>
-__device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, TcCtx& c, TcHeadScratch* hs, uint32_t& phase, float (&head)[NH]) {
+__device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, const TcChain& ch_, TcCtx& c, TcHeadScratch* hs, uint32_t& phase,
+                                               float (&head)[NH]) {
     if (c.h != 0) return;
     if (kTcSlots > 1) {
         mbar_wait(&hs->bar[chain][c.q], phase);
         phase ^= 1u;
+        tc_fence_after();
     }
     const float* bias = c.bias + Lh.b_off;
     float s[NH];
@@ -622,10 +630,10 @@ __device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, TcC
     for (int o = 0; o < NH; ++o) s[o] = 0.f;
 #pragma unroll
     for (int k = 0; k + 1 < kTcSlots; ++k) {
-        const float4 p = hs->p[chain][k][c.t];
-        s[0] += p.x;
-        if (NH > 1) s[NH > 1 ? 1 : 0] += p.y;
-        if (NH > 2) s[NH > 2 ? 2 : 0] += p.z;
+        float pv[16];
+        tc_ld16(c.tmem + c.lane_addr + ch_.acc_col + 16 * k, pv);
+#pragma unroll
+        for (int o = 0; o < NH; ++o) s[o] += pv[o];
     }
 #pragma unroll
     for (int o = 0; o < NH; ++o) head[o] = (head[o] + s[o]) + bias[o];
@@ -644,9 +652,9 @@ __device__ __forceinline__ void tc_nets_forward(const TcModel& M, const TcChain&
     const int np = M.n_rate > M.n_aug ? M.n_rate : M.n_aug;
     for (int p = 0; p < np; ++p) {
         if (p < M.n_rate - 1) tc_fwd_epilogue<SAVE, 2 * R>(M.rate[p], p == M.n_rate - 2 ? &M.rate[p + 1] : nullptr, 0, cr, c.phase, c, hs, o_r);
-        else if (p == M.n_rate - 1) tc_head_finish<2 * R>(M.rate[p], 0, c, hs, c.phase_h[0], o_r);
+        else if (p == M.n_rate - 1) tc_head_finish<2 * R>(M.rate[p], 0, cr, c, hs, c.phase_h[0], o_r);
         if (p < M.n_aug - 1) tc_fwd_epilogue<SAVE, 3 * R>(M.aug[p], p == M.n_aug - 2 ? &M.aug[p + 1] : nullptr, 1, ca, c.phase2, c, hs, o_a);
-        else if (p == M.n_aug - 1) tc_head_finish<3 * R>(M.aug[p], 1, c, hs, c.phase_h[1], o_a);
+        else if (p == M.n_aug - 1) tc_head_finish<3 * R>(M.aug[p], 1, ca, c, hs, c.phase_h[1], o_a);
     }
 }
 

@@ -13,7 +13,7 @@ static inline int round16(int x) { return (x + 15) & ~15; }
 // below this the 128-trajectory tiles cannot fill the 148 SMs and the FFMA engine (32/64-trajectory
 // tiles) is the better fit.
 static const long long kTcMinBatch = 148LL * kTcTile;
-static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit minus the static part
+static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit minus the static part (~1.2 KB) and alignment slack
 
 static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes, int head_elu, int& th) {
     if (n == 0) return true;
