@@ -15,10 +15,10 @@ importable alias of this package.
 from ._lib import UdeError, build, lib  # noqa: F401
 from .funcs import Fa, FaFp, Fp, FuncInfo, UnsupportedFunc, describe_func  # noqa: F401
 from . import dist  # noqa: F401
-from .odeint import odeint, posterior_rows, rk4_grid_tables  # noqa: F401
+from .odeint import odeint, odeint_groups, posterior_rows, rk4_grid_tables  # noqa: F401
 
 odeint_adjoint = odeint   # torchdiffeq exports both; the fused backward IS the discrete adjoint
 
-__all__ = ["odeint", "odeint_adjoint", "Fp", "Fa", "FaFp", "describe_func", "build", "lib", "UdeError",
+__all__ = ["odeint", "odeint_groups", "odeint_adjoint", "Fp", "Fa", "FaFp", "describe_func", "build", "lib", "UdeError",
            "UnsupportedFunc", "rk4_grid_tables", "posterior_rows"]
 __version__ = "0.1.0"

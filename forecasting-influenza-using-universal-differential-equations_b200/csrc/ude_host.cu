@@ -263,7 +263,17 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     int st = check_desc(desc);
     if (st != UDE_OK || !plan || n_steps < 0) return UDE_ERR_INVALID;
     if (method != UDE_METHOD_RK4 && method != UDE_METHOD_DOPRI5) return UDE_ERR_INVALID;
-    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    if (desc->n_groups != 1) {
+        // G independent weight sets: G single-group solves side by side (group-major layouts, see ude_rk4_forward)
+        if (method != UDE_METHOD_RK4) return UDE_ERR_UNSUPPORTED;
+        UdeDesc d1 = *desc;
+        d1.n_groups = 1;
+        d1.batch = desc->batch / desc->n_groups;
+        if ((st = ude_plan(&d1, method, n_steps, plan)) != UDE_OK) return st;
+        plan->workspace_bytes = align_up(plan->workspace_bytes, 256) * desc->n_groups;
+        plan->tape_bytes = align_up(plan->tape_bytes, 256) * desc->n_groups;
+        return UDE_OK;
+    }
     ModelP Pf, Pb;      // pure host arithmetic: works without a GPU (148 SMs assumed then)
     if ((st = choose_plan(desc, Pf, n_state_for(method, false), n_rbuf_for(method, false), false)) != UDE_OK) return st;
     if ((st = choose_plan(desc, Pb, n_state_for(method, true), n_rbuf_for(method, true), true)) != UDE_OK) return st;
@@ -376,6 +386,65 @@ static int launch_pack(const ModelP& P, const float* theta, float* wpacked, cuda
     return UDE_OK;
 }
 
+}  // extern "C"
+
+// ----------------------------------------------------------------------------------
+// Weight-set groups (BASELINE configs[4]: tuning/tune_node.py-style sweeps, G independent Fp models trained side
+// by side).  The reference trains every configuration in its own process with its own odeint call
+// (tuning/tune_node.py:204,227); here ONE call carries G of them in group-major layouts
+//   theta [G][n_theta], y0 [G][B_g][R][L], y_out [G][n_out][B_g][R][L], tape / workspace [G][per-group bytes of the plan],
+//   side [G][8], g_side [G][5], g_theta [G][n_theta]
+// and fans the G single-group launch sets out over an internal pool of streams that fork from / join into the
+// caller's stream (event edges only: legal inside stream capture).  A group is 32 tiles of 64 trajectories at the
+// reference's 64 x 32 samples: eight in flight fill the 148 SMs.
+// ----------------------------------------------------------------------------------
+constexpr int kFan = 8;
+struct GroupFan {
+    int dev = -1;
+    cudaStream_t s[kFan];
+    cudaEvent_t fork, join[kFan];
+};
+static int group_fan(GroupFan** out) {
+    static thread_local GroupFan fan;
+    int dev = 0;
+    UDE_CUDA(cudaGetDevice(&dev));
+    if (fan.dev != dev) {
+        for (int i = 0; i < kFan; ++i) {
+            UDE_CUDA(cudaStreamCreateWithFlags(&fan.s[i], cudaStreamNonBlocking));
+            UDE_CUDA(cudaEventCreateWithFlags(&fan.join[i], cudaEventDisableTiming));
+        }
+        UDE_CUDA(cudaEventCreateWithFlags(&fan.fork, cudaEventDisableTiming));
+        fan.dev = dev;
+    }
+    *out = &fan;
+    return UDE_OK;
+}
+template <class F>
+static int for_each_group(const UdeDesc* desc, int n_steps, cudaStream_t user, F&& launch_one) {
+    const int G = desc->n_groups;
+    UdeDesc d1 = *desc;
+    d1.n_groups = 1;
+    d1.batch = desc->batch / G;
+    UdePlan p1;
+    int st = ude_plan(&d1, UDE_METHOD_RK4, n_steps, &p1);
+    if (st != UDE_OK) return st;
+    const long long ws_g = align_up(p1.workspace_bytes, 256), tape_g = align_up(p1.tape_bytes, 256);
+    GroupFan* fan = nullptr;
+    if ((st = group_fan(&fan)) != UDE_OK) return st;
+    const int n_fan = G < kFan ? G : kFan;
+    UDE_CUDA(cudaEventRecord(fan->fork, user));
+    for (int i = 0; i < n_fan; ++i) UDE_CUDA(cudaStreamWaitEvent(fan->s[i], fan->fork, 0));
+    for (int g = 0; g < G; ++g)
+        if ((st = launch_one(d1, p1, g, ws_g, tape_g, fan->s[g % n_fan])) != UDE_OK) break;
+    for (int i = 0; i < n_fan; ++i) {       // always join, also after a failed launch
+        cudaEventRecord(fan->join[i], fan->s[i]);
+        cudaStreamWaitEvent(user, fan->join[i], 0);
+    }
+    return st;
+}
+
+extern "C" {
+
 int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, int32_t n_steps, const float* dt,
                     int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w, float* y_out,
                     float* tape, double* side, void* workspace, int64_t workspace_bytes, void* stream) {
@@ -383,8 +452,19 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (st != UDE_OK) return st;
     if (!theta || !y0 || !dt || !out_step || !out_kind || !out_w || !y_out || !side || !workspace) return UDE_ERR_INVALID;
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
-    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    if (desc->n_groups != 1) {
+        const long long n_theta = ude_theta_size(desc), row = (long long)desc->n_regions * desc->latent_dim;
+        return for_each_group(desc, n_steps, reinterpret_cast<cudaStream_t>(stream),
+                              [&](const UdeDesc& d1, const UdePlan& p1, int g, long long ws_g, long long tape_g, cudaStream_t sg) {
+                                  const long long Bg = d1.batch;
+                                  return ude_rk4_forward(&d1, theta + g * n_theta, y0 + g * Bg * row, n_steps, dt, n_out, out_step, out_kind,
+                                                         out_w, y_out + g * (long long)n_out * Bg * row,
+                                                         tape ? reinterpret_cast<float*>(reinterpret_cast<char*>(tape) + g * tape_g) : nullptr,
+                                                         side + g * 8, reinterpret_cast<char*>(workspace) + g * ws_g,
+                                                         workspace_bytes - g * ws_g < p1.workspace_bytes ? 0 : p1.workspace_bytes, sg);
+                              });
+    }
     {
         TcModel Mt;
         const int path = tc_choose(desc, Mt);
@@ -434,8 +514,20 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (!theta || !y0 || !dt || !out_step || !out_kind || !out_w || !tape || !g_out || !g_y0 || !g_theta || !workspace)
         return UDE_ERR_INVALID;
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
-    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    if (desc->n_groups != 1) {
+        const long long n_theta = ude_theta_size(desc), row = (long long)desc->n_regions * desc->latent_dim;
+        return for_each_group(desc, n_steps, reinterpret_cast<cudaStream_t>(stream),
+                              [&](const UdeDesc& d1, const UdePlan& p1, int g, long long ws_g, long long tape_g, cudaStream_t sg) {
+                                  const long long Bg = d1.batch;
+                                  return ude_rk4_backward(&d1, theta + g * n_theta, y0 + g * Bg * row, n_steps, dt, n_out, out_step, out_kind,
+                                                          out_w, reinterpret_cast<const float*>(reinterpret_cast<const char*>(tape) + g * tape_g),
+                                                          g_out + g * (long long)n_out * Bg * row, g_side ? g_side + g * 5 : nullptr,
+                                                          g_y0 + g * Bg * row, g_theta + g * n_theta,
+                                                          reinterpret_cast<char*>(workspace) + g * ws_g,
+                                                          workspace_bytes - g * ws_g < p1.workspace_bytes ? 0 : p1.workspace_bytes, sg);
+                              });
+    }
     {
         TcModel Mt;
         const int path = tc_choose(desc, Mt);

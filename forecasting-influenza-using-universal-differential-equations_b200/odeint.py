@@ -152,6 +152,64 @@ class _Rk4Solve(torch.autograd.Function):
         return g_theta, g_y0, None, None, None, None, None
 
 
+class _Rk4SolveGroups(torch.autograd.Function):
+    """G independent weight sets in one call (C ABI ``n_groups = G``, group-major layouts):
+    (theta [G, n_theta], y0 [G, B_g, R, L]) -> (y_out [G, T, B_g, R, L], side [G, 8] fp64)."""
+
+    @staticmethod
+    def forward(ctx, theta, y0, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool):
+        L = _lib.lib()
+        dev = y0.device
+        G, Bg, R, Ld = y0.shape
+        desc = info.desc(G * Bg, n_groups=G)
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
+            theta_c = theta.detach().contiguous()
+            y0_c = y0.detach().contiguous()
+            y_out = torch.empty((G, n_out, Bg, R, Ld), dtype=torch.float32, device=dev)
+            side = torch.empty((G, 8), dtype=torch.float64, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            dt, out_step, out_kind, out_w = tables
+            st = L.ude_rk4_forward(C.byref(desc), _ptr(theta_c), _ptr(y0_c), n_steps, _ptr(dt), n_out,
+                                   _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(y_out), _ptr(tape), _ptr(side),
+                                   _ptr(ws), int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward (groups)")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out = info, tables, n_steps, n_out
+        ctx.plan_ws = int(plan.workspace_bytes)
+        ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev))
+        ctx.has_tape = tape is not None
+        return y_out, side
+
+    @staticmethod
+    def backward(ctx, g_out, g_side):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_c, y0_c, tape = ctx.saved_tensors
+        info: FuncInfo = ctx.info
+        dev = y0_c.device
+        G, Bg = y0_c.shape[0], y0_c.shape[1]
+        desc = info.desc(G * Bg, n_groups=G)
+        with torch.cuda.device(dev):
+            if g_out is None:
+                g_out = torch.zeros((G, ctx.n_out, *y0_c.shape[1:]), dtype=torch.float32, device=dev)
+            g_out = g_out.contiguous().float()
+            gs = None
+            if g_side is not None:
+                gs = g_side[:, :5].to(torch.float32).contiguous()
+            g_y0 = torch.empty_like(y0_c)
+            g_theta = torch.empty_like(theta_c)
+            ws = torch.empty(ctx.plan_ws, dtype=torch.uint8, device=dev)
+            dt, out_step, out_kind, out_w = ctx.tables
+            st = L.ude_rk4_backward(C.byref(desc), _ptr(theta_c), _ptr(y0_c), ctx.n_steps, _ptr(dt), ctx.n_out,
+                                    _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(tape), _ptr(g_out), _ptr(gs),
+                                    _ptr(g_y0), _ptr(g_theta), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward (groups)")
+        return g_theta, g_y0, None, None, None, None, None
+
+
 # ---------------------------------------------------------------------------------------
 # side channels -> the reference's python-list protocol
 # ---------------------------------------------------------------------------------------
@@ -234,4 +292,45 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         from .dist import all_reduce_side
         side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
+    return y_out
+
+
+def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
+    """G independent UDE models integrated side by side (BASELINE configs[4]: the hyper-parameter sweeps of
+    tuning/tune_node.py train every configuration with its own ``odeint`` call, :204,227 — here they share ONE).
+
+    ``funcs``: G modules of identical architecture (own weights each); ``y0``: ``[G, B_g, R, L]``; returns
+    ``[G, len(t), B_g, R, L]``, i.e. ``out[g] == odeint(funcs[g], y0[g], t, ...)``.  Gradients flow to every
+    module's parameters and to ``y0``; each module receives its own side-channel entries (``params`` / ``tracker``).
+    Fixed-grid rk4 only (the method of every live call site of the reference)."""
+    if method != "rk4":
+        raise NotImplementedError("grouped solves implement the reference's method, rk4")
+    funcs = list(funcs)
+    if not funcs:
+        raise ValueError("funcs is empty")
+    if not isinstance(y0, torch.Tensor) or y0.dim() != 4 or y0.shape[0] != len(funcs):
+        raise ValueError(f"y0 must be [G={len(funcs)}, B_g, R, L]")
+    infos = [_check_common(f, y0[g], t, method, None) for g, f in enumerate(funcs)]
+    i0 = infos[0]
+    sig0 = (i0.kind, i0.n_regions, i0.latent_dim, [l.weight.shape for l in i0.linears()], float(i0.fa_w),
+            i0.rate_head_elu, i0.aug_head_elu)
+    for i in infos[1:]:
+        sig = (i.kind, i.n_regions, i.latent_dim, [l.weight.shape for l in i.linears()], float(i.fa_w), i.rate_head_elu,
+               i.aug_head_elu)
+        if sig != sig0:
+            raise ValueError("all funcs of a grouped solve must share one architecture (and Fa_w)")
+    options = {} if options is None else dict(options)
+    i0.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)
+    unknown = set(options) - {"step_size"}
+    if unknown:
+        raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
+    t_cpu = t.detach().to("cpu")
+    if not bool((t_cpu[1:] > t_cpu[:-1]).all()):
+        raise ValueError("t must be strictly increasing")
+    (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
+    theta = torch.stack([i.theta() for i in infos])
+    need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
+    y_out, side = _Rk4SolveGroups.apply(theta, y0, i0, tables, n_steps, int(t.numel()), need_tape)
+    for g, (f, i) in enumerate(zip(funcs, infos)):
+        install_side_channels(f, i, side[g])
     return y_out

@@ -78,7 +78,13 @@ typedef struct UdeDesc {
     int32_t n_aug_layers;                 /* Linear layers of the Fa net, 0 for Fp           */
     int32_t aug_sizes[UDE_MAX_LAYERS];    /* out width of each; last must be 3R              */
     float   fa_w;                         /* FaFp.Fa_w (lib/models.py:225,249); runtime      */
-    int32_t n_groups;                     /* G independent weight sets (tuning sweeps); >= 1 */
+    int32_t n_groups;                     /* G independent weight sets (tuning sweeps); >= 1.
+                                           * G > 1 (rk4 only): every array is GROUP-MAJOR --
+                                           * theta [G][n_theta], y0 [G][B/G][R][L],
+                                           * y_out / g_out [G][n_out][B/G][R][L], side [G][8],
+                                           * g_side [G][5], g_y0 like y0, g_theta like theta,
+                                           * tape / workspace [G][per-group bytes] -- and the call
+                                           * equals G single-set calls (ude_plan returns the totals) */
     int32_t flags;                        /* UDE_FLAG_*                                      */
     int64_t batch;                        /* B, all groups together; B % G == 0              */
 } UdeDesc;

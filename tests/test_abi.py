@@ -113,3 +113,25 @@ def test_descriptor_validation_and_plan(built_lib):
     assert plan.tape_bytes >= (1 << 20) * 8 * 4 * 3 * 4
     assert plan.smem_bytes_bwd <= 227 * 1024 and plan.smem_bytes_fwd <= 227 * 1024
     assert built_lib.ude_plan(None, 0, 8, C.byref(plan)) == -1
+
+
+def test_group_plan_is_g_single_group_plans(built_lib):
+    """n_groups = G (BASELINE configs[4]): workspace and tape are G per-group blocks of the single-set plan
+    (group-major layouts, include/ude_b200.h), theta size stays per group; batch must divide by G."""
+    from ude_b200 import _lib
+    one = _desc("Fp", 1, 8, [32, 32, 2], [], B=2048)
+    p1 = _lib.UdePlan()
+    assert built_lib.ude_plan(C.byref(one), _lib.METHOD["rk4"], 56, C.byref(p1)) == 0
+    grp = _desc("Fp", 1, 8, [32, 32, 2], [], B=512 * 2048)
+    grp.n_groups = 512
+    pg = _lib.UdePlan()
+    assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) == 0
+    up = lambda v: (v + 255) // 256 * 256
+    assert pg.workspace_bytes == 512 * up(p1.workspace_bytes)
+    assert pg.tape_bytes == 512 * up(p1.tape_bytes)
+    assert pg.n_theta == p1.n_theta == built_lib.ude_theta_size(C.byref(grp))
+    assert pg.tile_traj == p1.tile_traj
+    grp.batch = 512 * 2048 + 1
+    assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) != 0
+    grp.batch = 512 * 2048
+    assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["dopri5"], 56, C.byref(pg)) == -2      # UDE_ERR_UNSUPPORTED
