@@ -350,10 +350,12 @@ int main() {
             {"delta  M128 N64  K-major/MN-major", 128, 64, 0, 1}, {"dW     M64  N72  MN/MN", 64, 72, 1, 1},
             {"dW     M64  N40  MN/MN", 64, 40, 1, 1},             {"dW     M64  N16  MN/MN", 64, 16, 1, 1},
             {"dW     M128 N72  MN/MN", 128, 72 + 8, 1, 1},
+            {"dW     M64  N136 MN/MN", 64, 136, 1, 1},            {"dW     M128 N144 MN/MN", 128, 144, 1, 1},
+            {"dW     M128 N128 MN/MN", 128, 128, 1, 1},           {"dW     M128 N144 K-major A/MN B", 128, 144, 0, 1},
             {"chain  M128 N192 K-major/K-major", 128, 192, 0, 0}, {"chain  M128 N256 K-major/K-major", 128, 256, 0, 0},
             {"chain  M64 N64 K-major/K-major", 64, 64, 0, 0},{"chain  M64 N256 K-major/K-major", 64, 256, 0, 0},
         };
-        std::vector<uint8_t> ai(128 * 128 * 2, 0), bi(128 * 128 * 2, 0);
+        std::vector<uint8_t> ai(128 * 128 * 2, 0), bi(160 * 128 * 2, 0);
         for (const Shape& s : shapes) {
             ProbeCfg c{};
             c.M = s.M; c.N = s.N; c.n_mma = 4; c.a_mn = s.a_mn; c.b_mn = s.b_mn;
