@@ -251,8 +251,9 @@ __host__ __device__ __forceinline__ void tc_issue_delta(const TcLayer& Lp, uint3
 // tests pin it).  The activation images are [a2 | a1 | ones] in one of two alternating sweep buffers, so the
 // B-operand addresses here are relative to the sweep buffer (tc_issue_table adds the buffer offset).
 template <class Emit>
-__host__ __device__ __forceinline__ void tc_issue_dw(const TcLayer& Lp, uint32_t dbuf, uint32_t abuf, uint32_t q_addr, Emit&& tc_mma) {
-    const uint32_t g_arr = (Lp.out_p >> 3) * kTcGroupBytes;
+__host__ __device__ __forceinline__ void tc_issue_dw(const TcLayer& Lp, uint32_t dbuf, uint32_t abuf, uint32_t q_addr, int g_groups,
+                                                     Emit&& tc_mma) {
+    const uint32_t g_arr = (uint32_t)g_groups * kTcGroupBytes;      // distance of the G2 array from the G1 array
     const int in_p = Lp.in_p;
     const uint32_t id_full = tc_idesc(64, 2 * in_p + 8, 1, 1), id_a1 = tc_idesc(64, in_p + 8, 1, 1);
     const uint32_t b_a1 = abuf + abuf_group(0, in_p) * kTcGroupBytes;
@@ -402,7 +403,7 @@ __device__ __forceinline__ void tc_issuer_forward(const TcTable& tab, const TcLa
 // weight-gradient products W_l of every layer share one accumulator and wait for the previous one to be drained.
 __device__ __forceinline__ void tc_issuer_net_backward(const TcTable& tab, const TcLayer* Ls, int n, uint32_t smem_base16, uint32_t tmem,
                                                        uint64_t* bar, uint64_t* bar_b, uint32_t buf16, uint32_t& par) {
-    tc_issuer_wait_operands();                                   // step H1: head image + image of a_{n-2}
+    tc_issuer_wait_operands(kTcBarOperands2);                    // step H1: head image + image of a_{n-2}
     tc_issue_table(tab, Ls[n - 1].mma_w, Ls[n - 1].n_w, smem_base16, tmem, par ? buf16 : 0u);
     tc_commit_elect(bar_b);
     par ^= 1u;
@@ -605,7 +606,9 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
             for (int i = 0; i < 16; ++i) pv[i] = 0.f;
 #pragma unroll
             for (int o = 0; o < NH; ++o) pv[o] = acc[o];
-            tc_st16(d0 + 16 * (c.h - 1), pv);
+            // into the columns of this warp's OWN first chunk (already consumed by itself): the trajectory warp of the
+            // quarter may still be reading its chunks of the same accumulator
+            tc_st16(d0 + 16 * c.h, pv);
             tc_fence_before();
             __syncwarp();
             if (c.lane == 0) mbar_arrive(&hs->bar[chain][c.q]);
@@ -631,7 +634,7 @@ __device__ __forceinline__ void tc_head_finish(const TcLayer& Lh, int chain, con
 #pragma unroll
     for (int k = 0; k + 1 < kTcSlots; ++k) {
         float pv[16];
-        tc_ld16(c.tmem + c.lane_addr + ch_.acc_col + 16 * k, pv);
+        tc_ld16(c.tmem + c.lane_addr + ch_.acc_col + 16 * (k + 1), pv);
 #pragma unroll
         for (int o = 0; o < NH; ++o) s[o] += pv[o];
     }
@@ -1029,43 +1032,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
 //   step l=n-2..1  : image for W_{l-1};  ELU'(a_{l-1});  wait C_l;  G_{l-1} -> registers (l = 1: partial W0^T G_0);
 //                    wait W_l;  G_{l-1} -> Dbuf;  ready -> issuer: C_{l-1} (l >= 2), W_{l-1};  flush W_l
 //   step 0         : wait W_0, flush;  partial dx of the helper warps -> trajectory warps (through TMEM)
-// Gradients of one layer, TMEM -> staging buffer -> ONE bulk reduction into the CTA slab
-// (cp.reduce.async.bulk.add.f32, SASS UBLKRED): the L2 atomics run on the copy engine in the background instead of
-// backing up the LSU behind 16-byte reductions.  Staging/slab layout of a layer: [in_p / 4][64 rows] float4, then
-// [64] bias sums (rows 16q .. 16q+15 of the M = 64 accumulator live in lanes 0..15 of quarter q).
+// Gradients of one layer, TMEM -> per-warp staging slice -> bulk reductions into the CTA slab
+// (cp.reduce.async.bulk.add.f32, SASS UBLKRED): the L2 atomics run on the copy engine in the background, and because
+// every warp stages and hands over its OWN rows (16q .. 16q+15 of the M = 64 accumulator live in lanes 0..15 of
+// quarter q) and column chunks, the flush needs no CTA-wide barrier at all.
+// Slab layout of a layer: [quarter q][chunk][4][16 rows] float4 (one contiguous KB per warp and chunk), then [64] bias sums.
 // Returns after the accumulator has been read; the caller releases it to the issuer ("drained").
+constexpr int kTcStageSlice = kTcChunksPerWarp * 1024 + 64;      // bytes per warp: its chunks + 16 bias sums
 __device__ __forceinline__ void tc_flush_grad(const TcModel& M, const TcLayer& Lp, TcCtx& c, float* slab) {
-    const int m = 16 * c.q + c.lane;
+    if (16 * c.q >= Lp.out) return;              // no real output row in this lane quarter (heads, 32-wide layers)
     const bool act = c.lane < 16;
     const uint32_t q0 = c.tmem + c.lane_addr + M.tm_q;
-    float4* st = reinterpret_cast<float4*>(c.stage_p);
-    // the previous bulk reduction must have read the staging buffer
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
-    for (int ch = c.h; ch < (Lp.in_p >> 4); ch += kTcSlots) {
-        float u[16], v[16];
-        tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
-        if (act) {
+    uint8_t* slice = c.stage_p + (size_t)c.warp * kTcStageSlice;
+    // this warp's previous bulk reductions must have read the slice -- and must have LANDED: reductions of consecutive
+    // evaluations hit the same slab addresses, and only completion order makes the fp32 sums bit-reproducible
+    // (they were issued a whole phase ago: the wait is short)
+    if (c.lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-                st[(4 * ch + (i >> 2)) * 64 + m] = make_float4(u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
+    for (int j = 0; j < kTcChunksPerWarp; ++j) {
+        const int ch = c.h + kTcSlots * j;
+        if (ch < (Lp.in_p >> 4)) {
+            float u[16], v[16];
+            tc_ld16x2(q0 + 16 * ch, q0 + Lp.in_p + 16 * ch, u, v);
+            if (act) {
+                float4* st = reinterpret_cast<float4*>(slice + j * 1024);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    st[(i >> 2) * 16 + c.lane] = make_float4(u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
+            }
         }
     }
     if (c.h == 0) {
         float u[16];
         tc_ld16(q0 + 2 * Lp.in_p, u);            // 8 columns of the ones group (+8 unused columns of the region)
-        if (act) reinterpret_cast<float*>(c.stage_p)[64 * Lp.in_p + m] = u[0];
+        if (act) reinterpret_cast<float*>(slice + kTcChunksPerWarp * 1024)[c.lane] = u[0];
     }
 }
 // second half: hand the staged gradients to the copy engine (call after tc_drained)
 __device__ __forceinline__ void tc_flush_commit(const TcLayer& Lp, TcCtx& c, float* slab) {
+    if (16 * c.q >= Lp.out) return;
     tc_proxy_fence();
-    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
-    if (threadIdx.x == 0) {
-        const uint32_t bytes = (uint32_t)(64 * Lp.in_p + 64) * 4u;
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(slab + Lp.slab_off),
-                     "r"(smem_u32(c.stage_p)), "r"(bytes)
-                     : "memory");
+    __syncwarp();
+    if (c.lane == 0) {
+        const int n_chunks = Lp.in_p >> 4;
+        float* base = slab + Lp.slab_off;
+        const uint32_t slice = smem_u32(c.stage_p + (size_t)c.warp * kTcStageSlice);
+#pragma unroll
+        for (int j = 0; j < kTcChunksPerWarp; ++j) {
+            const int ch = c.h + kTcSlots * j;
+            if (ch < n_chunks)
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                                 base + (size_t)(c.q * n_chunks + ch) * 256),
+                             "r"(slice + j * 1024), "n"(1024)
+                             : "memory");
+        }
+        if (c.h == 0)
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                             base + 64 * Lp.in_p + 16 * c.q),
+                         "r"(slice + kTcChunksPerWarp * 1024), "n"(64)
+                         : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 }
@@ -1117,13 +1143,10 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
 #pragma unroll
             for (int i = 0; i < NH; ++i) gh[i] = g_head[i];
         }
-        // the head image shares its 8 KB with the gradient staging buffer: the last bulk reduction must have read it
-        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, %1;" ::"n"(kTcBarFlush), "n"(32 * kTcEpiWarps) : "memory");
         if (is_traj) {
-            uint8_t* base = c.ghead_p + c.t * 16;              // [G1 | G2], two 8-feature groups each
-            split2_store8(gh, base, base + 2 * kTcGroupBytes);
-            split2_store8(gh + 8, base + kTcGroupBytes, base + 3 * kTcGroupBytes);
+            static_assert(NH <= 8, "head cotangent image: one 8-feature group per split array");
+            uint8_t* base = c.ghead_p + c.t * 16;              // [G1 | G2], ONE 8-feature group each
+            split2_store8(gh, base, base + kTcGroupBytes);
             if (kTcSlots > 1) {
                 tc_st16(tm_x, gh);
                 tc_fence_before();
@@ -1143,7 +1166,10 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
             tc_store_sweep16(c, par, sv, ch, Lh.in_p);
         }
         if (c.h == 0) tc_store_sweep_ones(c, par, Lh.in_p);
-        tc_operands_ready(c);
+        // NOT the barrier of H2's hand-off: the arrivals are non-blocking and nothing blocks between H1 and H2, so a warp
+        // that runs ahead (the helper warps skip the tail VJP) would otherwise arrive twice in one barrier generation and
+        // release the issuer before a slow warp has written its part of the operands
+        tc_operands_ready(c, kTcBarOperands2);
         // H2 (behind W_{n-1}): G_{n-2} = (Wh^T g) * ELU'(a_{n-2}) on the FMA pipe, image of a_{n-3}
         const float* hw = c.bias + Lh.hw_off;
         for (int ch = c.h; ch < (Lh.in_p >> 4); ch += kTcSlots) {
@@ -1515,7 +1541,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         }
     }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // gradient reductions have landed
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // gradient reductions have landed
     tc_prof_dump(c);
     tc_fence_before();
     __syncthreads();
@@ -1583,7 +1609,7 @@ __global__ void tc_reduce_dtheta_kernel(const __grid_constant__ TcModel M, const
         if (e >= Lp.th_w && e < Lp.th_w + Lp.in * Lp.out) {
             const int k = e - Lp.th_w;
             const int row = k / Lp.in, col = k - row * Lp.in;
-            sidx = Lp.slab_off + ((col >> 2) * 64 + row) * 4 + (col & 3);
+            sidx = Lp.slab_off + (((((row >> 4) * (Lp.in_p >> 4) + (col >> 4)) * 4 + ((col & 15) >> 2)) * 16 + (row & 15)) * 4 + (col & 3));
             break;
         }
         if (e >= Lp.th_b && e < Lp.th_b + Lp.out) {

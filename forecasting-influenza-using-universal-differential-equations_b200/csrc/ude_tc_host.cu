@@ -106,7 +106,7 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     M.tm_dd = M.tm_q + M.tm_q_cols;
     M.tm_fwd = M.tm_q;
     M.tm_acc_fwd = 0;
-    M.tm_acc_stride = max_out;
+    M.tm_acc_stride = max_out > 16 * kTcSlots ? max_out : 16 * kTcSlots;      // >= one 16-column block per column slot (head partial sums)
     const int bwd_cols = (M.tm_dd + max_in) > (M.tm_fwd + 2 * max_out) ? (M.tm_dd + max_in) : (M.tm_fwd + 2 * max_out);
     if (bwd_cols > 512 || 2 * max_out > 128) return false;
     M.tm_cols_fwd = 128;
@@ -114,12 +114,10 @@ static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     // shared memory
     M.off_w = 0;
     M.off_bias = M.w_bytes;
-    // [staging of the gradient bulk reductions: (64 max_in + 64) floats, its LAST 8 KB double as the head image]
-    // (the head image is dead once W_{n-1} has completed, i.e. before the first gradient flush of the net)
-    const int stage_bytes = (64 * 64 + 64) * 4;
+    // [per-warp staging slices of the gradient bulk reductions] [head-cotangent image [G1|G2]]
     M.off_stage = (int)align_up(M.blob_bytes, 128);
-    M.off_ghead = M.off_stage + stage_bytes - 4 * kTcGroupBytes;
-    M.off_abuf = M.off_ghead + 4 * kTcGroupBytes;       // the M = 64 view of the image over-reads into Abuf (finite data)
+    M.off_ghead = (int)align_up(M.off_stage + kTcEpiWarps * kTcStageSlice, 128);
+    M.off_abuf = M.off_ghead + 2 * kTcGroupBytes;       // the M = 64 view of the image over-reads into Abuf (finite data)
     M.sweep_buf_bytes = (2 * (max_in / 8) + 1) * kTcGroupBytes;
     M.abuf_bytes = (3 * (max_in / 8) + 1) * kTcGroupBytes;               // forward image [a2|a1|ones|a3]
     if (2 * M.sweep_buf_bytes > M.abuf_bytes) M.abuf_bytes = 2 * M.sweep_buf_bytes;
@@ -159,7 +157,8 @@ static void tc_build_table(const TcModel& M, TcTable& T, bool backward) {
                 tc_issue_delta(Lp, (uint32_t)M.off_dbuf, (uint32_t)M.off_w, (uint32_t)M.tm_dd, rc);
             }
             TcRecorder rw{T.e + Lp.mma_w, 0};
-            tc_issue_dw(Lp, (uint32_t)(head ? M.off_ghead : M.off_dbuf), (uint32_t)M.off_abuf, (uint32_t)M.tm_q, rw);
+            tc_issue_dw(Lp, (uint32_t)(head ? M.off_ghead : M.off_dbuf), (uint32_t)M.off_abuf, (uint32_t)M.tm_q,
+                        head ? 1 : Lp.out_p / 8, rw);
         }
     }
 }

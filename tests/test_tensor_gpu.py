@@ -125,7 +125,7 @@ def test_ragged_tiles_match_oracle(B):
 
 @pytest.mark.parametrize("kind,L,nets,aug", [
     ("Fp", 8, (64, 64), ()), ("Fp", 4, (32, 32), ()), ("Fa", 16, (), (64, 64)), ("FaFp", 4, (32, 32), (32, 32)),
-    ("FaFp", 16, (64, 64, 32), (64, 64)), ("Fp", 8, (20, 20), ()),
+    ("FaFp", 16, (32, 32), (32, 32)), ("Fp", 16, (64, 64, 32), ()), ("Fp", 8, (20, 20), ()),
 ])
 def test_model_shapes_match_oracle(kind, L, nets, aug):
     """Single-net kinds (only one chain runs), tune_node-style widths (tuning/tune_node.py:170), every latent_dim
@@ -139,6 +139,21 @@ def test_model_shapes_match_oracle(kind, L, nets, aug):
     assert rel_err(y, yr) <= RTOL_PARITY
     assert rel_err(dy0, dy0r) <= RTOL_PARITY
     assert rel_err(dth, dthr) <= RTOL_PARITY
+
+
+def test_largest_model_falls_back_to_the_ffma_engine():
+    """FaFp with latent_dim 16 AND the 64-wide nets needs 2.7 KB more shared memory than an SM has (the fp32 first-layer
+    weights of the FMA-pipe W0^T delta0 double with D0): the library must pick the FFMA engine for it, and pinning the
+    tensor family must fail loudly instead of silently running something else."""
+    import ude_b200
+    from oracle.ude_rhs import UdeSpec, init_theta
+    spec = UdeSpec("FaFp", 1, 16, (64, 64, 32), (64, 64))
+    mod = module_from_spec(spec, init_theta(spec, seed=0), 1.0, "cuda")
+    assert _path(mod, 1 << 20) == 0
+    assert _path(mod, 1 << 20, "tensor") < 0
+    with pytest.raises(ude_b200.UdeError):
+        ude_b200.odeint(mod, torch.zeros(256, 1, 16, device="cuda"), torch.arange(3.), method="rk4",
+                        options=dict(step_size=1.0, kernels="tensor"))
 
 
 def test_library_picks_tensor_path_for_the_ensemble_and_matches_oracle():

@@ -32,7 +32,7 @@ mod = module_from_spec(spec, init_theta(spec, 0), 1.0, "cuda")
 y0 = synth_y0(B, 1, 8, seed=1).cuda()
 t = torch.arange(9.)
 L = ude_b200.lib()
-names = ["sync", "image+elu'", "wait", "epi_fwd", "delta_epi", "flush", "total", "-"]
+names = ["sync", "image+elu'+stepH", "wait", "epi_fwd", "delta_epi", "flush+dx", "total", "-"]
 
 
 def dump(tag):
