@@ -226,3 +226,33 @@ def test_clamped_trajectories():
     assert rel_err(y, yr.detach()) <= RTOL_PARITY
     assert rel_err(dy0, y0r.grad) <= RTOL_PARITY
     assert rel_err(dth, f.theta.grad) <= RTOL_PARITY
+
+
+@pytest.mark.parametrize("kind,L,nets,aug", [
+    ("FaFp", 8, (16, 16), (16, 16)),            # thinnest legal nets: every phase is short, hand-offs are back to back
+    ("FaFp", 4, (32, 16), (64, 32)),            # unequal chains: the lock step runs out of rate layers first
+    ("FaFp", 16, (32, 32), (32, 32)),
+    ("Fp", 8, (64, 16, 64), ()),
+    ("Fa", 8, (), (32, 64, 32)),
+    ("FaFp", 8, (64, 64, 32), (64, 64)),
+])
+def test_shapes_agree_with_ffma_family_over_several_tiles_per_cta(kind, L, nets, aug):
+    """Timing-sensitive coverage: 40 000 trajectories = 313 tiles on 148 CTAs (2-3 tiles each, ragged tail), short
+    nets, both kernel families on the same inputs, and a bit-identical rerun of the tensor family."""
+    from oracle.ude_rhs import UdeSpec, init_theta, synth_y0
+    spec = UdeSpec(kind, 1, L, nets, aug)
+    theta = init_theta(spec, seed=13)
+    B = 40_000
+    y0 = synth_y0(B, 1, L, seed=14)
+    t = torch.arange(5.)
+    G = torch.randn(5, B, 1, L, generator=torch.Generator().manual_seed(15))
+    a = _fused_case(spec, theta, y0, G, t, 1.0, "tensor")
+    a2 = _fused_case(spec, theta, y0, G, t, 1.0, "tensor")
+    b = _fused_case(spec, theta, y0, G, t, 1.0, "ffma")
+    for u, v in zip(a, a2):
+        assert torch.equal(u, v)
+    assert rel_err(a[0], b[0]) <= RTOL_PARITY
+    assert rel_err(a[2], b[2]) <= RTOL_PARITY
+    scale = float(b[1].abs().max())
+    row_err = (a[1] - b[1]).abs().amax(dim=(1, 2)) / scale
+    assert int((row_err > RTOL_PARITY).sum()) <= max(1, B // 20_000)
