@@ -328,9 +328,21 @@ def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
     if not bool((t_cpu[1:] > t_cpu[:-1]).all()):
         raise ValueError("t must be strictly increasing")
     (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
-    theta = torch.stack([i.theta() for i in infos])
+    # one cat over all G x (W, b) tensors, one batched side-channel computation: the glue must not cost G x a dozen launches
+    theta = torch.cat([p.reshape(-1) for i in infos for l in i.linears() for p in (l.weight, l.bias)]).view(len(funcs), -1)
     need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
     y_out, side = _Rk4SolveGroups.apply(theta, y0, i0, tables, n_steps, int(t.numel()), need_tape)
-    for g, (f, i) in enumerate(zip(funcs, infos)):
-        install_side_channels(f, i, side[g])
+    if i0.rate_layers:
+        n = side[:, 5:6]
+        mean = side[:, 0:2] / n
+        half = torch.sqrt(torch.clamp((side[:, 2:4] - n * mean * mean) / (n - 1.0), min=0.0)) / math.sqrt(2.0)
+        rows = torch.stack([mean - half, mean + half], dim=1).to(torch.float32)          # [G, 2, 2], see posterior_rows
+        for g, f in enumerate(funcs):
+            if isinstance(getattr(f, "params", None), list):
+                f.params.append(rows[g])
+    if i0.aug_layers:
+        norms = torch.sqrt(side[:, 4]).to(torch.float32)
+        for g, f in enumerate(funcs):
+            if isinstance(getattr(f, "tracker", None), list):
+                f.tracker.append(norms[g])
     return y_out
