@@ -140,12 +140,51 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 on register pairs).  The epilogues are bound by issue slots
+// on dependent instruction streams, not by pipe throughput: one instruction per PAIR of activations where the
+// scalar code needs two.  Same IEEE round-to-nearest results as the scalar operations.
+__device__ __forceinline__ void sub2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void mul2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// (x, y) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void fma2(float& x, float& y, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(x), "=f"(y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+// ELU'(h) from the ELU output a (a > 0 ? 1 : a + 1), two at a time
+// (= min(a, 0) + 1: one FMNMX each and one FADD2 instead of add, compare and select; same values)
+__device__ __forceinline__ void elu_grad2(float& g0, float& g1, float a0, float a1) {
+    add2(g0, g1, fminf(a0, 0.f), fminf(a1, 0.f), 1.0f, 1.0f);
+}
+
 // ELU(alpha=1) with exp(h) = ex2.approx.ftz(h * log2 e): the same MUFU.EX2 the FFMA engine's __expf uses,
 // minus its denormal-range rescaling (h < -87 flushes to exp = 0, i.e. ELU = -1 exactly as it rounds anyway).
 __device__ __forceinline__ float tc_elu(float h) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(h * 1.4426950408889634f));
     return h > 0.f ? h : e - 1.0f;
+}
+// two at a time (same values as tc_elu)
+// ELU(h) = max(h, 0) + (exp(min(h, 0)) - 1): for h > 0 the second term is exactly 0, for h <= 0 the first one --
+// the same values as the select, with min / max (ALU) and packed arithmetic instead of compare + select
+__device__ __forceinline__ void tc_elu2(float& h0, float& h1) {
+    float s0, s1, e0, e1;
+    mul2(s0, s1, fminf(h0, 0.f), fminf(h1, 0.f), 1.4426950408889634f, 1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+    add2(e0, e1, e0, e1, -1.0f, -1.0f);
+    add2(h0, h1, fmaxf(h0, 0.f), fmaxf(h1, 0.f), e0, e1);
 }
 
 // ----------------------------------------------------------------------------------
@@ -155,15 +194,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&p);
 }
+// (a, b) - (bf16 pair h as fp32): the residual of one split level, both lanes in one FADD2
+__device__ __forceinline__ void split_residual(float& ra, float& rb, float a, float b, uint32_t h) {
+    sub2(ra, rb, a, b, __uint_as_float(h << 16), __uint_as_float(h & 0xFFFF0000u));
+}
 __device__ __forceinline__ void split3_store8(const float* v /*8 values*/, uint8_t* p0, uint8_t* p1, uint8_t* p2) {
     uint32_t h0[4], h1[4], h2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = v[2 * j], b = v[2 * j + 1];
+        float ra, rb, sa, sb;
         h0[j] = pack_bf16x2(a, b);
-        const float ra = a - __uint_as_float(h0[j] << 16), rb = b - __uint_as_float(h0[j] & 0xFFFF0000u);
+        split_residual(ra, rb, a, b, h0[j]);
         h1[j] = pack_bf16x2(ra, rb);
-        const float sa = ra - __uint_as_float(h1[j] << 16), sb = rb - __uint_as_float(h1[j] & 0xFFFF0000u);
+        split_residual(sa, sb, ra, rb, h1[j]);
         h2[j] = pack_bf16x2(sa, sb);
     }
     *reinterpret_cast<uint4*>(p0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
@@ -179,10 +223,11 @@ __device__ __forceinline__ void split3_pack16(const float (&v)[16], uint4 (&p)[6
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float a = v[8 * g + 2 * j], b = v[8 * g + 2 * j + 1];
+            float ra, rb, sa, sb;
             h0[j] = pack_bf16x2(a, b);
-            const float ra = a - __uint_as_float(h0[j] << 16), rb = b - __uint_as_float(h0[j] & 0xFFFF0000u);
+            split_residual(ra, rb, a, b, h0[j]);
             h1[j] = pack_bf16x2(ra, rb);
-            const float sa = ra - __uint_as_float(h1[j] << 16), sb = rb - __uint_as_float(h1[j] & 0xFFFF0000u);
+            split_residual(sa, sb, ra, rb, h1[j]);
             h2[j] = pack_bf16x2(sa, sb);
         }
         p[0 + g] = make_uint4(h0[0], h0[1], h0[2], h0[3]);
@@ -478,8 +523,10 @@ __device__ __forceinline__ void split2_store8(const float* v, uint8_t* p0, uint8
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float a = v[2 * j], b = v[2 * j + 1];
+        float ra, rb;
         h0[j] = pack_bf16x2(a, b);
-        h1[j] = pack_bf16x2(a - __uint_as_float(h0[j] << 16), b - __uint_as_float(h0[j] & 0xFFFF0000u));
+        split_residual(ra, rb, a, b, h0[j]);
+        h1[j] = pack_bf16x2(ra, rb);
     }
     *reinterpret_cast<uint4*>(p0) = make_uint4(h0[0], h0[1], h0[2], h0[3]);
     *reinterpret_cast<uint4*>(p1) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
@@ -549,14 +596,14 @@ __device__ __forceinline__ void tc_head_partial(const float* hw, int in_p, int c
 #pragma unroll
     for (int o = 0; o < NH; ++o) {
         const float4* w4 = reinterpret_cast<const float4*>(hw + o * in_p + 16 * ch);
+        float a0 = 0.f, a1 = 0.f;                  // even / odd features (packed FFMA2), summed at the end
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 w = w4[i];
-            acc[o] = fmaf(v[4 * i + 0], w.x, acc[o]);
-            acc[o] = fmaf(v[4 * i + 1], w.y, acc[o]);
-            acc[o] = fmaf(v[4 * i + 2], w.z, acc[o]);
-            acc[o] = fmaf(v[4 * i + 3], w.w, acc[o]);
+            fma2(a0, a1, v[4 * i + 0], v[4 * i + 1], w.x, w.y, a0, a1);
+            fma2(a0, a1, v[4 * i + 2], v[4 * i + 3], w.z, w.w, a0, a1);
         }
+        acc[o] += a0 + a1;
     }
 }
 // epilogue of hidden layer Lp of one chain: accumulator -> bias, ELU -> (saved activation) -> image of the next
@@ -583,11 +630,12 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             const float4 b = *reinterpret_cast<const float4*>(bias + 16 * ch + i);
-            v0[i + 0] += b.x; v0[i + 1] += b.y; v0[i + 2] += b.z; v0[i + 3] += b.w;
+            add2(v0[i + 0], v0[i + 1], v0[i + 0], v0[i + 1], b.x, b.y);
+            add2(v0[i + 2], v0[i + 3], v0[i + 2], v0[i + 3], b.z, b.w);
         }
         if (Lp.elu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v0[i] = tc_elu(v0[i]);
+            for (int i = 0; i < 16; i += 2) tc_elu2(v0[i], v0[i + 1]);
         }
         if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
         if (Lhead) tc_head_partial<NH>(c.bias + Lhead->hw_off, Lhead->in_p, ch, v0, acc);
@@ -1059,7 +1107,12 @@ __device__ __forceinline__ void tc_flush_grad(const TcModel& M, const TcLayer& L
                 float4* st = reinterpret_cast<float4*>(slice + j * 1024);
 #pragma unroll
                 for (int i = 0; i < 16; i += 4)
-                    st[(i >> 2) * 16 + c.lane] = make_float4(u[i] + v[i], u[i + 1] + v[i + 1], u[i + 2] + v[i + 2], u[i + 3] + v[i + 3]);
+                {
+                    float4 t;
+                    add2(t.x, t.y, u[i], u[i + 1], v[i], v[i + 1]);
+                    add2(t.z, t.w, u[i + 2], u[i + 3], v[i + 2], v[i + 3]);
+                    st[(i >> 2) * 16 + c.lane] = t;
+                }
             }
         }
     }
@@ -1182,17 +1235,19 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 w = w4[i];
-                    d[4 * i + 0] = fmaf(gh[o], w.x, d[4 * i + 0]);
-                    d[4 * i + 1] = fmaf(gh[o], w.y, d[4 * i + 1]);
-                    d[4 * i + 2] = fmaf(gh[o], w.z, d[4 * i + 2]);
-                    d[4 * i + 3] = fmaf(gh[o], w.w, d[4 * i + 3]);
+                    fma2(d[4 * i + 0], d[4 * i + 1], gh[o], gh[o], w.x, w.y, d[4 * i + 0], d[4 * i + 1]);
+                    fma2(d[4 * i + 2], d[4 * i + 3], gh[o], gh[o], w.z, w.w, d[4 * i + 2], d[4 * i + 3]);
                 }
             }
             if (Lq.elu) {
                 float sv[16];
                 tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) d[i] *= elu_grad_from_out(sv[i]);
+                for (int i = 0; i < 16; i += 2) {
+                    float e0, e1;
+                    elu_grad2(e0, e1, sv[i], sv[i + 1]);
+                    mul2(d[i], d[i + 1], d[i], d[i + 1], e0, e1);
+                }
             }
             tc_store_delta16(c, d, ch, Lh.in_p);
         }
@@ -1225,7 +1280,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                         float sv[16];
                         tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) ef[j][i] = elu_grad_from_out(sv[i]);
+                        for (int i = 0; i < 16; i += 2) elu_grad2(ef[j][i], ef[j][i + 1], sv[i], sv[i + 1]);
                     }
                 }
             }
@@ -1243,7 +1298,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                     tc_ld16(dd + 16 * ch, d);
                     if (Lq.elu) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) d[i] *= ef[j][i];
+                        for (int i = 0; i < 16; i += 2) mul2(d[i], d[i + 1], d[i], d[i + 1], ef[j][i], ef[j][i + 1]);
                     }
                     if (l == 1) {               // W0^T G_0 on the FMA pipe (fp32 rows of W0, broadcast loads)
                         const float* w0 = c.bias + Lq.w0_off + (size_t)(16 * ch) * M.w0_stride;
@@ -1252,10 +1307,8 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
 #pragma unroll
                             for (int k4 = 0; k4 < (D0 + 3) / 4; ++k4) {
                                 const float4 w = *reinterpret_cast<const float4*>(w0 + i * M.w0_stride + 4 * k4);
-                                pdx[4 * k4 + 0] = fmaf(d[i], w.x, pdx[4 * k4 + 0]);
-                                pdx[4 * k4 + 1] = fmaf(d[i], w.y, pdx[4 * k4 + 1]);
-                                pdx[4 * k4 + 2] = fmaf(d[i], w.z, pdx[4 * k4 + 2]);
-                                pdx[4 * k4 + 3] = fmaf(d[i], w.w, pdx[4 * k4 + 3]);
+                                fma2(pdx[4 * k4 + 0], pdx[4 * k4 + 1], d[i], d[i], w.x, w.y, pdx[4 * k4 + 0], pdx[4 * k4 + 1]);
+                                fma2(pdx[4 * k4 + 2], pdx[4 * k4 + 3], d[i], d[i], w.z, w.w, pdx[4 * k4 + 2], pdx[4 * k4 + 3]);
                             }
                         }
                     }
