@@ -1268,22 +1268,9 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         const TcLayer& Lq = Ls[l - 1];
         par ^= 1u;                              // W_l reads sweep buffer `par`
         uint4 sg[kTcChunksPerWarp][6];
-        float ef[kTcChunksPerWarp][16];
         {
             TCP_T0();
             tc_sweep_image<D0>(Ls, l - 1, par ^ 1u, c, x, is_traj);
-            if (Lq.elu) {
-#pragma unroll
-                for (int j = 0; j < kTcChunksPerWarp; ++j) {
-                    const int ch = c.h + kTcSlots * j;
-                    if (ch < (Lp.in_p >> 4)) {
-                        float sv[16];
-                        tc_ld16(c.tmem + c.lane_addr + Lq.save_col + 16 * ch, sv);
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) elu_grad2(ef[j][i], ef[j][i + 1], sv[i], sv[i + 1]);
-                    }
-                }
-            }
             TCP_ADD(c, TCP_ISSUE);
         }
         tc_wait_mma(c);                         // C_l
@@ -1295,10 +1282,17 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
                 const int ch = c.h + kTcSlots * j;
                 if (ch < (Lp.in_p >> 4)) {
                     float d[16];
-                    tc_ld16(dd + 16 * ch, d);
                     if (Lq.elu) {
+                        float sv[16];
+                        tc_ld16x2(dd + 16 * ch, c.tmem + c.lane_addr + Lq.save_col + 16 * ch, d, sv);
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) mul2(d[i], d[i + 1], d[i], d[i + 1], ef[j][i], ef[j][i + 1]);
+                        for (int i = 0; i < 16; i += 2) {
+                            float e0, e1;
+                            elu_grad2(e0, e1, sv[i], sv[i + 1]);
+                            mul2(d[i], d[i + 1], d[i], d[i + 1], e0, e1);
+                        }
+                    } else {
+                        tc_ld16(dd + 16 * ch, d);
                     }
                     if (l == 1) {               // W0^T G_0 on the FMA pipe (fp32 rows of W0, broadcast loads)
                         const float* w0 = c.bias + Lq.w0_off + (size_t)(16 * ch) * M.w0_stride;
