@@ -136,6 +136,27 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// split issue / wait variants: several TMEM accesses in flight, one wait
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16_issue(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(
+            __float_as_uint(v[0])),
+        "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+        "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
+        "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -637,10 +658,11 @@ __device__ __forceinline__ void tc_fwd_epilogue(const TcLayer& Lp, const TcLayer
 #pragma unroll
             for (int i = 0; i < 16; i += 2) tc_elu2(v0[i], v0[i + 1]);
         }
-        if (SAVE) tc_st16(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);
+        if (SAVE) tc_st16_issue(c.tmem + c.lane_addr + Lp.save_col + 16 * ch, v0);      // completion awaited once, below
         if (Lhead) tc_head_partial<NH>(c.bias + Lhead->hw_off, Lhead->in_p, ch, v0, acc);
         else tc_store_act16(c, ch_.img, v0, ch, Lp.out_p);
     }
+    if (SAVE) tc_wait_st();
     TCP_ADD(c, TCP_EPI_FWD);
     if (!Lhead) {
         tc_operands_ready(c, ch_.bar_id);
