@@ -37,6 +37,15 @@ struct GridTables {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Packed fp32 FMA (sm_100 FFMA2 on register pairs): (x, y) = (a0, a1) * (b0, b1) + (x, y).  Two independent IEEE fmas,
+// i.e. the same bits as two fmaf calls, in ONE issue slot -- the micro-kernels below are bound by issue slots
+// (shared-memory operand loads + FMAs), not by the FMA pipe.
+__device__ __forceinline__ void ffma2(float& x, float& y, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(x), "+f"(y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // ELU(alpha=1) (lib/models.py:122 nn.ELU).  exp via MUFU.EX2: absolute error ~1e-7,
 // far inside the 1e-5 parity budget; the backward uses the SAME value (a + 1).
 __device__ __forceinline__ float elu_f(float h) { return h > 0.f ? h : (__expf(h) - 1.0f); }
@@ -127,22 +136,14 @@ __device__ __forceinline__ void fwd_unit(const LayerP& Lp, const float* __restri
 #pragma unroll
         for (int q = 0; q < TN; ++q) {
             const float4 w = ld4(W + wofs[q] + k);
-            acc[q][0] = fmaf(a0.x, w.x, acc[q][0]);
-            acc[q][1] = fmaf(a0.y, w.x, acc[q][1]);
-            acc[q][2] = fmaf(a0.z, w.x, acc[q][2]);
-            acc[q][3] = fmaf(a0.w, w.x, acc[q][3]);
-            acc[q][0] = fmaf(a1.x, w.y, acc[q][0]);
-            acc[q][1] = fmaf(a1.y, w.y, acc[q][1]);
-            acc[q][2] = fmaf(a1.z, w.y, acc[q][2]);
-            acc[q][3] = fmaf(a1.w, w.y, acc[q][3]);
-            acc[q][0] = fmaf(a2.x, w.z, acc[q][0]);
-            acc[q][1] = fmaf(a2.y, w.z, acc[q][1]);
-            acc[q][2] = fmaf(a2.z, w.z, acc[q][2]);
-            acc[q][3] = fmaf(a2.w, w.z, acc[q][3]);
-            acc[q][0] = fmaf(a3.x, w.w, acc[q][0]);
-            acc[q][1] = fmaf(a3.y, w.w, acc[q][1]);
-            acc[q][2] = fmaf(a3.z, w.w, acc[q][2]);
-            acc[q][3] = fmaf(a3.w, w.w, acc[q][3]);
+            ffma2(acc[q][0], acc[q][1], a0.x, a0.y, w.x, w.x);
+            ffma2(acc[q][2], acc[q][3], a0.z, a0.w, w.x, w.x);
+            ffma2(acc[q][0], acc[q][1], a1.x, a1.y, w.y, w.y);
+            ffma2(acc[q][2], acc[q][3], a1.z, a1.w, w.y, w.y);
+            ffma2(acc[q][0], acc[q][1], a2.x, a2.y, w.z, w.z);
+            ffma2(acc[q][2], acc[q][3], a2.z, a2.w, w.z, w.z);
+            ffma2(acc[q][0], acc[q][1], a3.x, a3.y, w.w, w.w);
+            ffma2(acc[q][2], acc[q][3], a3.z, a3.w, w.w, w.w);
         }
     }
     const float* __restrict__ bias = Wp + Lp.b_off;
@@ -187,24 +188,16 @@ __device__ __forceinline__ void bwd_unit(const LayerP& Lp, const LayerP* prev, c
     for (int k = 0; k < K; ++k) {
         const float4 a = ld4(Dl + k * TBP);
         const float4 w0 = ld4(W + k * ldw);
-        acc[0][0] = fmaf(a.x, w0.x, acc[0][0]); acc[0][1] = fmaf(a.y, w0.x, acc[0][1]);
-        acc[0][2] = fmaf(a.z, w0.x, acc[0][2]); acc[0][3] = fmaf(a.w, w0.x, acc[0][3]);
-        acc[1][0] = fmaf(a.x, w0.y, acc[1][0]); acc[1][1] = fmaf(a.y, w0.y, acc[1][1]);
-        acc[1][2] = fmaf(a.z, w0.y, acc[1][2]); acc[1][3] = fmaf(a.w, w0.y, acc[1][3]);
-        acc[2][0] = fmaf(a.x, w0.z, acc[2][0]); acc[2][1] = fmaf(a.y, w0.z, acc[2][1]);
-        acc[2][2] = fmaf(a.z, w0.z, acc[2][2]); acc[2][3] = fmaf(a.w, w0.z, acc[2][3]);
-        acc[3][0] = fmaf(a.x, w0.w, acc[3][0]); acc[3][1] = fmaf(a.y, w0.w, acc[3][1]);
-        acc[3][2] = fmaf(a.z, w0.w, acc[3][2]); acc[3][3] = fmaf(a.w, w0.w, acc[3][3]);
+        ffma2(acc[0][0], acc[0][1], a.x, a.y, w0.x, w0.x); ffma2(acc[0][2], acc[0][3], a.z, a.w, w0.x, w0.x);
+        ffma2(acc[1][0], acc[1][1], a.x, a.y, w0.y, w0.y); ffma2(acc[1][2], acc[1][3], a.z, a.w, w0.y, w0.y);
+        ffma2(acc[2][0], acc[2][1], a.x, a.y, w0.z, w0.z); ffma2(acc[2][2], acc[2][3], a.z, a.w, w0.z, w0.z);
+        ffma2(acc[3][0], acc[3][1], a.x, a.y, w0.w, w0.w); ffma2(acc[3][2], acc[3][3], a.z, a.w, w0.w, w0.w);
         if (TN == 8) {
             const float4 w1 = ld4(W + k * ldw + 16);
-            acc[TN - 4][0] = fmaf(a.x, w1.x, acc[TN - 4][0]); acc[TN - 4][1] = fmaf(a.y, w1.x, acc[TN - 4][1]);
-            acc[TN - 4][2] = fmaf(a.z, w1.x, acc[TN - 4][2]); acc[TN - 4][3] = fmaf(a.w, w1.x, acc[TN - 4][3]);
-            acc[TN - 3][0] = fmaf(a.x, w1.y, acc[TN - 3][0]); acc[TN - 3][1] = fmaf(a.y, w1.y, acc[TN - 3][1]);
-            acc[TN - 3][2] = fmaf(a.z, w1.y, acc[TN - 3][2]); acc[TN - 3][3] = fmaf(a.w, w1.y, acc[TN - 3][3]);
-            acc[TN - 2][0] = fmaf(a.x, w1.z, acc[TN - 2][0]); acc[TN - 2][1] = fmaf(a.y, w1.z, acc[TN - 2][1]);
-            acc[TN - 2][2] = fmaf(a.z, w1.z, acc[TN - 2][2]); acc[TN - 2][3] = fmaf(a.w, w1.z, acc[TN - 2][3]);
-            acc[TN - 1][0] = fmaf(a.x, w1.w, acc[TN - 1][0]); acc[TN - 1][1] = fmaf(a.y, w1.w, acc[TN - 1][1]);
-            acc[TN - 1][2] = fmaf(a.z, w1.w, acc[TN - 1][2]); acc[TN - 1][3] = fmaf(a.w, w1.w, acc[TN - 1][3]);
+            ffma2(acc[TN - 4][0], acc[TN - 4][1], a.x, a.y, w1.x, w1.x); ffma2(acc[TN - 4][2], acc[TN - 4][3], a.z, a.w, w1.x, w1.x);
+            ffma2(acc[TN - 3][0], acc[TN - 3][1], a.x, a.y, w1.y, w1.y); ffma2(acc[TN - 3][2], acc[TN - 3][3], a.z, a.w, w1.y, w1.y);
+            ffma2(acc[TN - 2][0], acc[TN - 2][1], a.x, a.y, w1.z, w1.z); ffma2(acc[TN - 2][2], acc[TN - 2][3], a.z, a.w, w1.z, w1.z);
+            ffma2(acc[TN - 1][0], acc[TN - 1][1], a.x, a.y, w1.w, w1.w); ffma2(acc[TN - 1][2], acc[TN - 1][3], a.z, a.w, w1.w, w1.w);
         }
     }
     float* __restrict__ dst = smem + (prev ? prev->act_off : gx_off) + m_off;
