@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
-        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed_hot, &wbar, wphase);
         Wp = smem + P.off_W;
     }
-    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+    for (int i = threadIdx.x; i < (P.Dn_p - P.Dn) * TBP; i += kThreads) smem[P.off_X + P.Dn * TBP + i] = 0.f;
 
     const int SS = P.Dn_p * TBP;
     float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         const long long b0 = tile * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         __syncthreads();
-        load_y0_tile(P, smem, a.y0, b0, nvalid);
+        load_y0_tile(P, smem, a.y0, b0, nvalid, true, P.hoist != 0);
         for (int i = threadIdx.x; i < 5 * RS; i += kThreads) SA[i] = 0.f;
         if (threadIdx.x < TB) {
             const int b = threadIdx.x;
@@ -178,12 +178,16 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             s_acc[b] = 0;
         }
         __syncthreads();
+        hoist_c0(P, a.wpacked, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
-            const float* X = smem + P.off_X + (r * L) * TBP + b;
+            const float* X = smem + P.off_X + (3 * r) * TBP + b;
             float v[3] = {X[0], X[TBP], X[2 * TBP]};
             for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = v[c];
-            if (b < nvalid) store_out_row(P, smem, a.y_out + ((b0 + b) * R + r) * (long long)L, r, b, v);
+            if (b < nvalid) {
+                const long long row = ((b0 + b) * R + r) * (long long)L;
+                store_out_row(P, a.y0 + row, a.y_out + row, v);
+            }
         }
         __syncthreads();
         eval_into(SK, 1, nvalid);                                   // f0 = func(t0, y0): first stage of the first step
@@ -192,10 +196,11 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             // ---- torchdiffeq _select_initial_step (order p = 4), per trajectory
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
                 const int r = idx >> P.tb_shift, b = idx & (TB - 1);
-                const float* X = smem + P.off_X + (r * L) * TBP + b;
+                const float* X = smem + P.off_X + (3 * r) * TBP + b;
+                const float* y0row = a.y0 + ((b0 + b) * R + r) * (long long)L;      // constants: straight from the caller's y0
                 float s0 = 0.f, s1 = 0.f;
                 for (int l = 0; l < L; ++l) {
-                    const float y = X[l * TBP];
+                    const float y = l < 3 ? X[l * TBP] : (b < nvalid ? __ldg(y0row + l) : 0.f);
                     const float scale = __fadd_rn(atol, __fmul_rn(fabsf(y), rtol));
                     const float q0 = y / scale;
                     s0 += q0 * q0;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
                 const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 for (int c = 0; c < 3; ++c)
-                    smem[P.off_X + (r * L + c) * TBP + b] =
+                    smem[P.off_X + (3 * r + c) * TBP + b] =
                         __fadd_rn(SY[(3 * r + c) * TBP + b], __fmul_rn(s_h0[b], SK[(3 * r + c) * TBP + b]));
             }
             __syncthreads();
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 }
                 PART[r * TBP + b] = s2;
                 SA[0 * RS + r * TBP + b] = 0.f;
-                for (int c = 0; c < 3; ++c) smem[P.off_X + (r * L + c) * TBP + b] = SY[(3 * r + c) * TBP + b];
+                for (int c = 0; c < 3; ++c) smem[P.off_X + (3 * r + c) * TBP + b] = SY[(3 * r + c) * TBP + b];
             }
             __syncthreads();
             if (threadIdx.x < TB) {
@@ -275,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                         }
                         v[c] = s_status[b] == 0 ? total : __int_as_float(0x7fc00000);
                     }
-                    store_out_row(P, smem, a.y_out + (((long long)jj * B + b0 + b) * R + r) * (long long)L, r, b, v);
+                    store_out_row(P, a.y0 + ((b0 + b) * R + r) * (long long)L,
+                                  a.y_out + (((long long)jj * B + b0 + b) * R + r) * (long long)L, v);
                     ++jj;
                 }
             }
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                     const float dt = (float)s_dt[b];
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        smem[P.off_X + (r * L + c) * TBP + b] = rk_combine(SK, SS, row, c_beta[st], st, dt, SY[row]);
+                        smem[P.off_X + row] = rk_combine(SK, SS, row, c_beta[st], st, dt, SY[row]);
                     }
                 }
                 __syncthreads();
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 float s = 0.f;
                 for (int c = 0; c < 3; ++c) {
                     const int row = (3 * r + c) * TBP + b;
-                    const float y0v = SY[row], y1v = smem[P.off_X + (r * L + c) * TBP + b];
+                    const float y0v = SY[row], y1v = smem[P.off_X + row];
                     const float err = __fsub_rn(rk_combine(SK, SS, row, c_err, 7, dt, 0.f), 0.f);
                     const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y0v), fabsf(y1v))));
                     const float q = err / tol;
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                     const int step = s_nacc[b];
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        const float y0v = SY[row], y1v = smem[P.off_X + (r * L + c) * TBP + b];
+                        const float y0v = SY[row], y1v = smem[P.off_X + row];
                         const float f0 = SK[row], f1 = SK[6 * SS + row];
                         if (a.tape_x) {
                             float* tp = a.tape_x + ((long long)step * kDopriStages) * stage_sz + (long long)(3 * r + c) * B + b0 + b;
@@ -444,12 +450,14 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
-        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed_hot, &wbar, wphase);
         Wp = smem + P.off_W;
     }
-    float* G = SMEM_G ? smem + P.off_G : a.slabs + (long long)blockIdx.x * P.n_packed;
-    for (int i = threadIdx.x; i < P.n_packed; i += kThreads) G[i] = 0.f;
-    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+    float* Gslab = a.slabs + (long long)blockIdx.x * P.n_packed;      // see rk4_bwd_kernel
+    float* G = SMEM_G ? smem + P.off_G : Gslab;
+    for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) G[i] = 0.f;
+    for (int i = P.n_packed_hot + threadIdx.x; i < P.n_packed; i += kThreads) Gslab[i] = 0.f;
+    for (int i = threadIdx.x; i < (P.Dn_p - P.Dn) * TBP; i += kThreads) smem[P.off_X + P.Dn * TBP + i] = 0.f;
     float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (a.g_side) {
 #pragma unroll
@@ -461,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     float* Y0B = SB + P.off_S + DB_Y0B * SS;
     float* KB = SB + P.off_S + DB_KB1 * SS;          // KB + i*SS = kbar_{i+1}
     float* GX = smem + P.off_GX;
-    float* CB = SB + P.off_CB;
+    float* DL = smem + P.off_DL;
     const long long B = a.B;
     const long long n_tiles = (B + TB - 1) / TB;
     const long long stage_sz = (long long)Dn * B;
@@ -475,9 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             float xb[3];
             rhs_tail_vjp(P, smem, r, b, (b < nvalid) && s_act[b], gs, KB[ki * SS + row], KB[ki * SS + row + TBP],
                          KB[ki * SS + row + 2 * TBP], xb);
-            float* gx = GX + (r * L) * TBP + b;
+            float* gx = GX + (3 * r) * TBP + b;
             gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
-            for (int l = 3; l < L; ++l) gx[l * TBP] = 0.f;
         }
         __syncthreads();
         rhs_backward_layers(P, Wp, smem, G, warp, lane);
@@ -487,11 +494,20 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         const long long b0 = tile * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         __syncthreads();
-        load_y0_tile(P, smem, a.y0, b0, nvalid);
+        load_y0_tile(P, smem, a.y0, b0, nvalid, false, P.hoist != 0);
         for (int i = threadIdx.x; i < DB_NSTATE * SS; i += kThreads) SB[P.off_S + i] = 0.f;
-        for (int i = threadIdx.x; i < P.D_p * TBP; i += kThreads) { CB[i] = 0.f; GX[i] = 0.f; }
+        for (int i = threadIdx.x; i < P.Dn_p * TBP; i += kThreads) GX[i] = 0.f;
+        for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
+        for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {      // dL/dy0 starts from the cotangent of output 0
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+            if (b < nvalid) {
+                const long long row = ((b0 + b) * R + r) * (long long)L;
+                for (int l = 0; l < L; ++l) a.g_y0[row + l] = __ldg(a.g_out + row + l);
+            }
+        }
         if (threadIdx.x == 0) s_max = 0;
         __syncthreads();
+        hoist_c0(P, a.wpacked, smem, warp, lane);
         if (threadIdx.x < TB) {
             const int b = threadIdx.x;
             s_nacc[b] = b < nvalid ? a.counts[(b0 + b) * 4 + 0] : 0;
@@ -524,11 +540,11 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
                         const float x = (float)((a.t_out[jj] - t0) / (t1 - t0));
                         const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
                         const float* gp = a.g_out + (((long long)jj * B + b0 + b) * R + r) * (long long)L;
-                        for (int l = 0; l < L; ++l) {
+                        for (int l = 0; l < 3; ++l) {
                             const float g = __ldg(gp + l);
-                            if (l < 3) { ce[l] += g; cd[l] += x * g; cc[l] += x2 * g; cbv[l] += x3 * g; ca[l] += x4 * g; }
-                            else CB[(r * L + l) * TBP + b] += g;
+                            ce[l] += g; cd[l] += x * g; cc[l] += x2 * g; cbv[l] += x3 * g; ca[l] += x4 * g;
                         }
+                        add_const_cotangent(a.g_y0 + ((b0 + b) * R + r) * (long long)L, gp, L);
                     }
                 }
                 for (int c = 0; c < 3; ++c) {
@@ -549,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
                     LAM1[row] += y1_b;
                     Y0B[row] = y0_b;
                     // stage input of the k_7 evaluation: y_{s+1} = x_1 of step s+1 (or the final state)
-                    smem[P.off_X + (r * L + c) * TBP + b] =
+                    smem[P.off_X + row] =
                         __ldg(a.tape_x + ((long long)(s + 1) * kDopriStages) * stage_sz + (long long)(3 * r + c) * B + b0 + b);
                 }
             }
@@ -569,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
                     const float dt = act ? s_dt[b] : 0.f;
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        const int xrow = (r * L + c) * TBP + b;
+                        const int xrow = row;
                         if (act) {
                             float xb = GX[xrow];
                             if (st == 6) {                       // x_7 = y_1: close lambda_1, then y_1 = y_0 + dt sum c_i k_i
@@ -587,8 +603,6 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
                                                              (long long)(3 * r + c) * B + b0 + b);
                         }
                     }
-                    if (act)
-                        for (int l = 3; l < L; ++l) CB[(r * L + l) * TBP + b] += GX[(r * L + l) * TBP + b];
                 }
                 __syncthreads();
             }
@@ -598,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             for (int c = 0; c < 3; ++c)
-                smem[P.off_X + (r * L + c) * TBP + b] =
+                smem[P.off_X + (3 * r + c) * TBP + b] =
                     (b < nvalid) ? __ldg(a.y0 + ((b0 + b) * R + r) * (long long)L + c) : 0.f;
         }
         __syncthreads();
@@ -606,22 +620,19 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
-                const float* gp = a.g_out + ((b0 + b) * R + r) * (long long)L;
-                float* dst = a.g_y0 + ((b0 + b) * R + r) * (long long)L;
-                for (int l = 0; l < L; ++l) {
-                    const float g = __ldg(gp + l);
-                    const int xrow = (r * L + l) * TBP + b;
-                    const float acc = l < 3 ? LAM1[(3 * r + l) * TBP + b] + GX[xrow] : CB[xrow] + GX[xrow];
-                    dst[l] = acc + g;
+                float* dst = a.g_y0 + ((b0 + b) * R + r) * (long long)L;      // holds the cotangent of output 0 (+ constants' sums)
+                for (int l = 0; l < 3; ++l) {
+                    const int row = (3 * r + l) * TBP + b;
+                    dst[l] = (LAM1[row] + GX[row]) + dst[l];
                 }
             }
         }
+        __syncthreads();
+        hoist_backward_epilogue(P, a.wpacked, smem, Gslab, a.y0, a.g_y0, b0, nvalid, warp, lane);
     }
     __syncthreads();
-    if (SMEM_G) {
-        float* slab = a.slabs + (long long)blockIdx.x * P.n_packed;
-        for (int i = threadIdx.x; i < P.n_packed; i += kThreads) slab[i] = G[i];
-    }
+    if (SMEM_G)
+        for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
 }
 
 }  // namespace ude

@@ -2,7 +2,8 @@
 //
 // One CTA owns a tile of TB trajectories for a whole integration.  All per-tile
 // data lives in shared memory as ROWS of TB floats (row stride TBP = TB + 4):
-//   X    [D_p ][TBP]  MLP input u = vec(x), row r*L + l        (lib/models.py:119 Flatten)
+//   X    [Dn_p][TBP]  LIVE part of the MLP input u = vec(x): row r*3 + c, c < 3 (lib/models.py:119 Flatten; the
+//                     constant components l >= 3 are hoisted out of the first layers, see ModelP)
 //   ACT_l[n_out_p][TBP] output of every nn.Linear (after ELU where the reference has one)
 //   S_k  [Dn_p][TBP]  solver state rows (y, k_i, adjoints), row r*3 + c
 // so that a trajectory is a COLUMN: threads that walk along a row touch
@@ -149,12 +150,19 @@ __device__ __forceinline__ void fwd_unit(const LayerP& Lp, const float* __restri
     const float* __restrict__ bias = Wp + Lp.b_off;
     float* __restrict__ out = smem + Lp.act_off + m_off;
     const bool elu = Lp.elu != 0;
+    const bool hoisted = Lp.c0_off >= 0;          // per-trajectory constant part (W0_const . x_const + b0) instead of the bias
 #pragma unroll
     for (int q = 0; q < TN; ++q) {
         const int n = n0 + ty + 4 * q;
         if (n < Lp.n_out_p) {
-            const float b = bias[n];
-            float4 v = make_float4(acc[q][0] + b, acc[q][1] + b, acc[q][2] + b, acc[q][3] + b);
+            float4 v;
+            if (hoisted) {
+                const float4 c = ld4(smem + Lp.c0_off + n * TBP + m_off);
+                v = make_float4(acc[q][0] + c.x, acc[q][1] + c.y, acc[q][2] + c.z, acc[q][3] + c.w);
+            } else {
+                const float b = bias[n];
+                v = make_float4(acc[q][0] + b, acc[q][1] + b, acc[q][2] + b, acc[q][3] + b);
+            }
             if (elu) {
                 v.x = elu_f(v.x);
                 v.y = elu_f(v.y);
@@ -252,7 +260,7 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
 #pragma unroll
         for (int p = 0; p < TM; ++p) acc[q][p] = 0.f;
     }
-    const bool with_bias = mt == 0;       // warp-uniform
+    const bool with_bias = mt == 0 && !Lp.no_db;       // warp-uniform
 #pragma unroll 2
     for (int k = 0; k < TB; k += 4) {
         float4 av[TM], dv[TN];
@@ -404,6 +412,17 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
         const LayerP* La = la >= 0 ? &P.aug[la] : nullptr;
         // ---- phase A: weight and bias gradients of this depth
         {
+            // hoisted constants: D += delta_0 (the adjoint of W0[:, const] . x_const runs once per tile on the sum)
+            if (P.hoist && lr == 0) {
+                float* __restrict__ dl = smem + P.off_DL;
+                const float* __restrict__ d0 = smem + Lr->act_off;
+                for (int i = threadIdx.x; i < Lr->n_out_p * P.TBP; i += kThreads) dl[i] += d0[i];
+            }
+            if (P.hoist && la == 0) {
+                float* __restrict__ dl = smem + P.off_DL + (P.n_rate > 0 ? P.rate[0].n_out_p * P.TBP : 0);
+                const float* __restrict__ d0 = smem + La->act_off;
+                for (int i = threadIdx.x; i < La->n_out_p * P.TBP; i += kThreads) dl[i] += d0[i];
+            }
             const int w0 = Lr ? dw_units(*Lr) : 0;
             const int w1 = La ? dw_units(*La) : 0;
             for (int u = warp; u < w0 + w1; u += kWarps) {
@@ -450,7 +469,7 @@ struct SideAcc {
 __device__ __forceinline__ void rhs_tail(const ModelP& P, const float* __restrict__ smem, const int r, const int b,
                                          const bool valid, SideAcc& side, float (&f)[3]) {
     const int TBP = P.TBP;
-    const float* X = smem + P.off_X + (r * P.L) * TBP + b;
+    const float* X = smem + P.off_X + (3 * r) * TBP + b;
     const float x0 = X[0], x1 = X[TBP], x2 = X[2 * TBP];
     f[0] = f[1] = f[2] = 0.f;
     if (P.n_rate > 0) {
@@ -491,7 +510,7 @@ __device__ __forceinline__ void rhs_tail_vjp(const ModelP& P, float* __restrict_
                                              const bool valid, const float (&gs)[5], float g0, float g1, float g2,
                                              float (&xb)[3]) {
     const int TBP = P.TBP;
-    const float* X = smem + P.off_X + (r * P.L) * TBP + b;
+    const float* X = smem + P.off_X + (3 * r) * TBP + b;
     const float x0 = X[0], x1 = X[TBP], x2 = X[2 * TBP];
     if (x0 > 2.f || x0 < -1.f) g0 = 0.f;
     if (x1 > 2.f || x1 < -1.f) g1 = 0.f;

@@ -38,14 +38,16 @@ static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int 
     for (int i = 0; i < n; ++i) {
         LayerP& Lp = Ls[i];
         memset(&Lp, 0, sizeof(Lp));
-        Lp.n_in = n_in;
+        const bool split = i == 0 && P.hoist;        // first layer: the packed block holds the LIVE columns only
+        Lp.n_in = split ? P.Dn : n_in;
+        Lp.th_ld = n_in;
         Lp.n_out = sizes[i];
         Lp.n_in_p = round4(Lp.n_in);
         Lp.n_out_p = round4(Lp.n_out);
         Lp.ldw = Lp.n_in_p;
         if (Lp.ldw % 32 == 0) Lp.ldw += 4;     // keep the 4 rows a warp reads at once in distinct banks
         Lp.th_w = th;
-        th += Lp.n_in * Lp.n_out;
+        th += n_in * Lp.n_out;
         Lp.th_b = th;
         th += Lp.n_out;
         Lp.w_off = pk;
@@ -53,8 +55,29 @@ static void fill_layers(ModelP& P, LayerP* Ls, int n, const int32_t* sizes, int 
         Lp.b_off = pk;
         pk += Lp.n_out_p;
         Lp.elu = (i <= n - 3 + (head_elu ? 1 : 0)) ? 1 : 0;   // lib/models.py: no ELU before the head
+        Lp.c0_off = -1;
         n_in = Lp.n_out;
     }
+}
+
+// constant block of a first layer (ModelP: "Hoisting"): same rows, the (L-3)R constant columns
+static void fill_const_block(const ModelP& P, const LayerP& L0, LayerP& Lc, int& pk) {
+    memset(&Lc, 0, sizeof(Lc));
+    Lc.n_in = P.Dc;
+    Lc.th_ld = L0.th_ld;
+    Lc.n_out = L0.n_out;
+    Lc.n_in_p = P.Dc_p;
+    Lc.n_out_p = L0.n_out_p;
+    Lc.ldw = Lc.n_in_p;
+    if (Lc.ldw % 32 == 0) Lc.ldw += 4;
+    Lc.th_w = L0.th_w;
+    Lc.th_b = L0.th_b;
+    Lc.w_off = pk;
+    pk += Lc.n_out_p * Lc.ldw;
+    Lc.b_off = L0.b_off;          // c0 = W0[:, const] . x_const + b0
+    Lc.elu = 0;
+    Lc.c0_off = -1;
+    Lc.no_db = 1;                 // the live block's units own the bias gradient
 }
 
 static void base_model(const UdeDesc* d, ModelP& P) {
@@ -66,6 +89,9 @@ static void base_model(const UdeDesc* d, ModelP& P) {
     P.D_p = round4(P.D);
     P.Dn = 3 * P.R;
     P.Dn_p = round4(P.Dn);
+    P.Dc = (P.L - 3) * P.R;
+    P.Dc_p = round4(P.Dc);
+    P.hoist = P.Dc > 0;
     P.R_p = round4(P.R);
     P.n_rate = d->n_rate_layers;
     P.n_aug = d->n_aug_layers;
@@ -74,7 +100,25 @@ static void base_model(const UdeDesc* d, ModelP& P) {
     fill_layers(P, P.rate, P.n_rate, d->rate_sizes, d->flags & UDE_FLAG_RATE_HEAD_ELU, th, pk);
     fill_layers(P, P.aug, P.n_aug, d->aug_sizes, d->flags & UDE_FLAG_AUG_HEAD_ELU, th, pk);
     P.n_theta = th;
+    P.n_packed_hot = pk;
+    if (P.hoist) {
+        if (P.n_rate > 0) fill_const_block(P, P.rate[0], P.rate_c, pk);
+        if (P.n_aug > 0) fill_const_block(P, P.aug[0], P.aug_c, pk);
+    }
     P.n_packed = pk + kPadTail;
+    if (!P.hoist) P.n_packed_hot = P.n_packed;
+}
+
+static void tile_shapes(LayerP& Lp, int m_tiles, int want) {
+    if (Lp.n_out_p <= 4) Lp.tn_fwd = 1;
+    else Lp.tn_fwd = (m_tiles * ((Lp.n_out_p + 31) / 32) >= want) ? 8 : 4;
+    Lp.tn_bwd = (m_tiles * ((Lp.n_in_p + 31) / 32) >= want) ? 8 : 4;
+    Lp.tm_dw = Lp.n_in_p > 8 ? 4 : 1;
+    Lp.tn_dw = Lp.n_out_p > 4 ? 4 : 1;
+    Lp.fwd_nt = (Lp.n_out_p + 4 * Lp.tn_fwd - 1) / (4 * Lp.tn_fwd);
+    Lp.bwd_nt = (Lp.n_in_p + 4 * Lp.tn_bwd - 1) / (4 * Lp.tn_bwd);
+    Lp.dw_mt = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
+    Lp.dw_nt = (Lp.n_out_p + 4 * Lp.tn_dw - 1) / (4 * Lp.tn_dw);
 }
 
 // Shared-memory plan for a given tile size; returns the arena size in floats.
@@ -88,11 +132,12 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
     P.n_state = n_state;
     int off = 0;
     P.off_W = off;
-    if (w_smem) off += P.n_packed;
+    if (w_smem) off += P.n_packed_hot;
     P.off_G = off;
-    if (g_smem) off += P.n_packed;
+    if (g_smem) off += P.n_packed_hot;
     P.off_X = off;
-    off += P.D_p * P.TBP;
+    off += P.Dn_p * P.TBP;
+    const int act0 = off;
     for (int net = 0; net < 2; ++net) {
         LayerP* Ls = net == 0 ? P.rate : P.aug;
         const int n = net == 0 ? P.n_rate : P.n_aug;
@@ -101,6 +146,25 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
             Ls[i].act_off = off;
             off += Ls[i].n_out_p * P.TBP;
         }
+    }
+    // constants of the tile: alias the ACT rows (only alive in the tile prologue / epilogue)
+    P.off_XC = act0;
+    if (off - act0 < P.Dc_p * P.TBP) off = act0 + P.Dc_p * P.TBP;
+    // hoisted first-layer parts: c0 rows (both directions), D rows (adjoint)
+    P.dl_rows = 0;
+    if (P.hoist) {
+        for (int net = 0; net < 2; ++net) {
+            LayerP* Ls = net == 0 ? P.rate : P.aug;
+            LayerP& Lc = net == 0 ? P.rate_c : P.aug_c;
+            if ((net == 0 ? P.n_rate : P.n_aug) == 0) continue;
+            Ls[0].c0_off = off;
+            Lc.in_off = P.off_XC;
+            Lc.act_off = off;
+            off += Ls[0].n_out_p * P.TBP;
+            P.dl_rows += Ls[0].n_out_p;
+        }
+        P.off_DL = off;
+        if (bwd) off += P.dl_rows * P.TBP;
     }
     // solver-state rows: in shared memory, or (large R) in a per-CTA global scratch ("cold")
     int coff = 0;
@@ -111,11 +175,9 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
     P.off_RB = soff;
     P.n_rbuf = n_rbuf;
     soff += n_rbuf * P.R_p * P.TBP;
-    P.off_CB = soff;
-    if (bwd) soff += P.D_p * P.TBP;
     P.cold_floats = coff + 8;
     P.off_GX = off;
-    if (bwd) off += P.D_p * P.TBP;
+    if (bwd) off += P.Dn_p * P.TBP;
     off += 8;    // slack
     P.smem_floats = off;
     // tile shapes: aim at >= kWarps units per phase (both nets run in the same phase)
@@ -125,18 +187,11 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
     for (int net = 0; net < 2; ++net) {
         LayerP* Ls = net == 0 ? P.rate : P.aug;
         const int n = net == 0 ? P.n_rate : P.n_aug;
-        for (int i = 0; i < n; ++i) {
-            LayerP& Lp = Ls[i];
-            if (Lp.n_out_p <= 4) Lp.tn_fwd = 1;
-            else Lp.tn_fwd = (m_tiles * ((Lp.n_out_p + 31) / 32) >= want) ? 8 : 4;
-            Lp.tn_bwd = (m_tiles * ((Lp.n_in_p + 31) / 32) >= want) ? 8 : 4;
-            Lp.tm_dw = Lp.n_in_p > 8 ? 4 : 1;
-            Lp.tn_dw = Lp.n_out_p > 4 ? 4 : 1;
-            Lp.fwd_nt = (Lp.n_out_p + 4 * Lp.tn_fwd - 1) / (4 * Lp.tn_fwd);
-            Lp.bwd_nt = (Lp.n_in_p + 4 * Lp.tn_bwd - 1) / (4 * Lp.tn_bwd);
-            Lp.dw_mt = (Lp.n_in_p + 8 * Lp.tm_dw - 1) / (8 * Lp.tm_dw);
-            Lp.dw_nt = (Lp.n_out_p + 4 * Lp.tn_dw - 1) / (4 * Lp.tn_dw);
-        }
+        for (int i = 0; i < n; ++i) tile_shapes(Ls[i], m_tiles, want);
+    }
+    if (P.hoist) {
+        if (P.n_rate > 0) tile_shapes(P.rate_c, m_tiles, want);
+        if (P.n_aug > 0) tile_shapes(P.aug_c, m_tiles, want);
     }
     return off;
 }
@@ -254,8 +309,9 @@ int64_t ude_macs_per_eval(const UdeDesc* desc) {
     ModelP P;
     base_model(desc, P);
     int64_t macs = 0;
-    for (int i = 0; i < P.n_rate; ++i) macs += (int64_t)P.rate[i].n_in * P.rate[i].n_out;
-    for (int i = 0; i < P.n_aug; ++i) macs += (int64_t)P.aug[i].n_in * P.aug[i].n_out;
+    // algorithmic count of the reference's layers (the first layers at their full R*L width, hoisting or not)
+    for (int i = 0; i < P.n_rate; ++i) macs += (int64_t)P.rate[i].th_ld * P.rate[i].n_out;
+    for (int i = 0; i < P.n_aug; ++i) macs += (int64_t)P.aug[i].th_ld * P.aug[i].n_out;
     return macs;
 }
 
@@ -381,7 +437,7 @@ int ude_rk4_grid(const float* t, int32_t n_t, float step_size, int32_t use_step_
 }
 
 static int launch_pack(const ModelP& P, const float* theta, float* wpacked, cudaStream_t s) {
-    pack_theta_kernel<<<P.n_rate + P.n_aug + 1, 256, 0, s>>>(P, theta, wpacked);
+    pack_theta_kernel<<<P.n_rate + P.n_aug + 3, 256, 0, s>>>(P, theta, wpacked);
     UDE_CUDA(cudaGetLastError());
     return UDE_OK;
 }

@@ -34,19 +34,33 @@ struct LayerP {
     int tm_dw, tn_dw;       // 4 | 1 each, weight-gradient micro-kernel
     int fwd_nt, bwd_nt;     // n-tiles of the forward / delta micro-kernels (host-computed: no device divisions)
     int dw_mt, dw_nt;       // m- / n-tiles of the weight-gradient micro-kernel
+    int c0_off;             // >= 0: smem rows [n_out_p][TBP] added INSTEAD of the bias (first layers with hoisted constants)
+    int th_ld;              // row stride of W inside theta (== n_in except for the split first layer, where it is R*L)
+    int no_db;              // weight-gradient units skip the bias gradient (constant block: the live block owns it)
 };
 
 struct ModelP {
     int kind;               // UdeKind
     int R, L;
-    int D, D_p;             // R*L and padded to 4  : rows of X (MLP input, row = r*L + l)
-    int Dn, Dn_p;           // 3R and padded to 4   : rows of the dynamic state (row = r*3 + c)
+    int D, D_p;             // R*L and padded to 4  : width of the reference's MLP input u = vec(x) (lib/models.py:119)
+    int Dn, Dn_p;           // 3R and padded to 4   : rows of the dynamic state AND of X (row = r*3 + c), see "hoisting"
+    int Dc, Dc_p;           // (L-3)*R and padded   : constant inputs (row = r*(L-3) + l-3)
     int R_p;                // R padded to 4        : rows of per-region scratch
     int n_rate, n_aug;
     LayerP rate[kMaxLayers];
     LayerP aug[kMaxLayers];
+    // Hoisting (lib/models.py:144,184,249: d/dt of components l >= 3 is identically zero).  Only 3 of the L latent
+    // components of a region move, so W0 . u splits into a LIVE product over the 3R dynamic inputs (every RHS
+    // evaluation) and a CONSTANT product over the (L-3)R others, done ONCE per tile and solve:
+    //     c0 = W0[:, const] . x_const + b0          (rows [n_out_p][TBP] at LayerP::c0_off of the first layers)
+    // and in the adjoint  dL/dx_const = W0[:, const]^T . D,  dW0[:, const] = D (x) x_const  with  D = sum over
+    // evaluations of delta_0 (off_DL).  rate[0] / aug[0] describe the live block, rate_c / aug_c the constant one.
+    LayerP rate_c, aug_c;
+    int hoist;              // Dc > 0
     int n_theta;            // floats of one weight set (PyTorch layout)
     int n_packed;           // floats of the packed blob incl. kPadTail
+    int n_packed_hot;       // leading part used by every RHS evaluation (all but the constant blocks of the first layers)
+    int dl_rows;            // rows of off_DL
     float fa_w;
     // ---- shared-memory plan (float offsets into the dynamic smem arena) ----
     int TB, TBP;            // trajectories per tile (32 | 64), padded row stride (TB + 4)
@@ -55,10 +69,11 @@ struct ModelP {
     int w_in_smem;          // packed weights resident in smem
     int g_in_smem;          // (bwd) dtheta accumulators resident in smem
     int off_W, off_G;       // valid when the flags above are set
-    int off_X;              // [D_p][TBP]
+    int off_X;              // [Dn_p][TBP] live inputs
+    int off_XC;             // [Dc_p][TBP] constant inputs of the tile (aliases the ACT rows: tile prologue / epilogue only)
+    int off_DL;             // (bwd) [n0_rate_p + n0_aug_p][TBP] sum over evaluations of the first layers' deltas
     int off_S;              // state rows: n_state buffers of [Dn_p][TBP]
-    int off_GX;             // (bwd) dL/du of one RHS evaluation, [D_p][TBP]
-    int off_CB;             // (bwd) running cotangent of the constant inputs, [D_p][TBP]
+    int off_GX;             // (bwd) dL/dx_live of one RHS evaluation, [Dn_p][TBP]
     int n_state;
     int off_RB, n_rbuf;     // per-region scratch: n_rbuf buffers of [R_p][TBP] (dopri5)
     int cold_global;        // solver-state rows (off_S, off_RB, off_CB) live in a per-CTA global scratch

@@ -44,42 +44,114 @@ __device__ __forceinline__ void copy_model_to_smem(ModelP* dst, const ModelP& sr
     for (int i = threadIdx.x; i < (int)(sizeof(ModelP) / sizeof(int)); i += kThreads) d[i] = s[i];
 }
 
-// Load the y0 tile into X (all R*L rows); invalid columns get zeros.
+// Load the y0 tile: live components -> X rows (3r + c); `consts`: constant components -> XC rows (r*(L-3) + l-3,
+// padding rows zeroed: XC aliases the ACT rows and is rebuilt whenever it is needed).  Invalid columns get zeros.
 __device__ __forceinline__ void load_y0_tile(const ModelP& P, float* smem, const float* __restrict__ y0, long long b0,
-                                             int nvalid) {
-    const int TB = P.TB, TBP = P.TBP, L = P.L;
+                                             int nvalid, bool live, bool consts) {
+    const int TB = P.TB, TBP = P.TBP, L = P.L, Lc = P.L - 3;
     for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
         const int r = idx >> P.tb_shift, b = idx & (TB - 1);
-        float* X = smem + P.off_X + (r * L) * TBP + b;
+        float* X = smem + P.off_X + (3 * r) * TBP + b;
+        float* XC = smem + P.off_XC + (r * Lc) * TBP + b;
         if (b < nvalid) {
             const float* src = y0 + ((b0 + b) * P.R + r) * (long long)L;
             if ((L & 3) == 0) {
                 for (int l = 0; l < L; l += 4) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(src + l));
-                    X[(l + 0) * TBP] = v.x; X[(l + 1) * TBP] = v.y; X[(l + 2) * TBP] = v.z; X[(l + 3) * TBP] = v.w;
+                    if (l == 0) {
+                        if (live) { X[0] = v.x; X[TBP] = v.y; X[2 * TBP] = v.z; }
+                        if (consts) XC[0] = v.w;
+                    } else if (consts) {
+                        XC[(l - 3) * TBP] = v.x; XC[(l - 2) * TBP] = v.y; XC[(l - 1) * TBP] = v.z; XC[l * TBP] = v.w;
+                    }
                 }
             } else {
-                for (int l = 0; l < L; ++l) X[l * TBP] = __ldg(src + l);
+                if (live) { X[0] = __ldg(src); X[TBP] = __ldg(src + 1); X[2 * TBP] = __ldg(src + 2); }
+                if (consts)
+                    for (int l = 3; l < L; ++l) XC[(l - 3) * TBP] = __ldg(src + l);
             }
         } else {
-            for (int l = 0; l < L; ++l) X[l * TBP] = 0.f;
+            if (live) { X[0] = 0.f; X[TBP] = 0.f; X[2 * TBP] = 0.f; }
+            if (consts)
+                for (int l = 0; l < Lc; ++l) XC[l * TBP] = 0.f;
         }
+    }
+    if (consts)
+        for (int i = threadIdx.x; i < (P.Dc_p - P.Dc) * TBP; i += kThreads) smem[P.off_XC + P.Dc * TBP + i] = 0.f;
+}
+
+// Store one output row (r, b): dynamic comps from v[], constants straight from the caller's y0 row (L2-resident).
+__device__ __forceinline__ void store_out_row(const ModelP& P, const float* __restrict__ y0row, float* __restrict__ dst,
+                                              const float (&v)[3]) {
+    const int L = P.L;
+    if ((L & 3) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(y0row));
+        st4(dst, make_float4(v[0], v[1], v[2], a.w));
+        for (int l = 4; l < L; l += 4) st4(dst + l, __ldg(reinterpret_cast<const float4*>(y0row + l)));
+    } else {
+        dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
+        for (int l = 3; l < L; ++l) dst[l] = __ldg(y0row + l);
     }
 }
 
-// Store one output row (r, b): dynamic comps from v[], constants from X.
-__device__ __forceinline__ void store_out_row(const ModelP& P, const float* smem, float* __restrict__ dst, int r, int b,
-                                              const float (&v)[3]) {
-    const int TBP = P.TBP, L = P.L;
-    const float* X = smem + P.off_X + (r * L) * TBP + b;
-    if ((L & 3) == 0) {
-        st4(dst, make_float4(v[0], v[1], v[2], X[3 * TBP]));
-        for (int l = 4; l < L; l += 4)
-            st4(dst + l, make_float4(X[l * TBP], X[(l + 1) * TBP], X[(l + 2) * TBP], X[(l + 3) * TBP]));
-    } else {
-        dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
-        for (int l = 3; l < L; ++l) dst[l] = X[l * TBP];
+// ---- hoisted constants (ModelP: "Hoisting") -----------------------------------------------------------------------
+// c0 rows of both first layers: W0[:, const] . x_const + b0.  Pre: XC loaded and synced.  Post: synced.
+// The constant blocks are read from the packed blob in GLOBAL memory (used twice per tile and solve).
+__device__ __forceinline__ void hoist_c0(const ModelP& P, const float* __restrict__ Wg, float* smem, int warp, int lane) {
+    if (!P.hoist) return;
+    const int u0 = P.n_rate > 0 ? fwd_units(P.rate_c, P.mt_shift) : 0;
+    const int u1 = P.n_aug > 0 ? fwd_units(P.aug_c, P.mt_shift) : 0;
+    for (int u = warp; u < u0 + u1; u += kWarps) {
+        if (u < u0) fwd_run(P.rate_c, Wg, smem, P.TBP, P.mt_shift, u, lane);
+        else fwd_run(P.aug_c, Wg, smem, P.TBP, P.mt_shift, u - u0, lane);
     }
+    __syncthreads();
+}
+
+// Adjoint of the hoisted product, once per tile: with D = sum over evaluations of delta_0 (off_DL rows)
+//   dW0[:, const] += D (x) x_const   (global CTA slab)      dL/dx_const += W0[:, const]^T D   (into g_y0)
+// Pre: all warps are done with the ACT rows (synced).  Post: synced.
+__device__ __forceinline__ void hoist_backward_epilogue(const ModelP& P, const float* __restrict__ Wg, float* smem,
+                                                        float* __restrict__ Gg, const float* __restrict__ y0,
+                                                        float* __restrict__ g_y0, long long b0, int nvalid, int warp, int lane) {
+    if (!P.hoist) return;
+    const int TB = P.TB, TBP = P.TBP, L = P.L, Lc = P.L - 3;
+    load_y0_tile(P, smem, y0, b0, nvalid, false, true);
+    __syncthreads();
+    LayerP Lr = P.rate_c, La = P.aug_c;
+    Lr.act_off = P.off_DL;
+    La.act_off = P.off_DL + (P.n_rate > 0 ? P.rate[0].n_out_p * TBP : 0);
+    const int w0 = P.n_rate > 0 ? dw_units(Lr) : 0, w1 = P.n_aug > 0 ? dw_units(La) : 0;
+    for (int u = warp; u < w0 + w1; u += kWarps) {
+        if (u < w0) dw_run(Lr, smem, Gg, TB, TBP, u, lane);
+        else dw_run(La, smem, Gg, TB, TBP, u - w0, lane);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.Dc_p * TBP; i += kThreads) smem[P.off_XC + i] = 0.f;
+    __syncthreads();
+    if (P.n_rate > 0) {
+        for (int u = warp; u < bwd_units(Lr, P.mt_shift); u += kWarps) bwd_run(Lr, nullptr, Wg, smem, TBP, P.off_XC, P.mt_shift, u, lane);
+        __syncthreads();
+    }
+    if (P.n_aug > 0) {
+        for (int u = warp; u < bwd_units(La, P.mt_shift); u += kWarps) bwd_run(La, nullptr, Wg, smem, TBP, P.off_XC, P.mt_shift, u, lane);
+        __syncthreads();
+    }
+    for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+        const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+        if (b < nvalid) {
+            float* dst = g_y0 + ((b0 + b) * P.R + r) * (long long)L;
+            const float* src = smem + P.off_XC + (r * Lc) * TBP + b;
+            for (int l = 3; l < L; ++l) dst[l] += src[(l - 3) * TBP];
+        }
+    }
+    __syncthreads();
+}
+
+// cotangent of the constant components of one output row: straight into the caller's g_y0 row (each row is owned by one
+// thread; the lines stay in L2) -- the running sum needs no shared-memory rows
+__device__ __forceinline__ void add_const_cotangent(float* __restrict__ dst, const float* __restrict__ gp, int L) {
+    for (int l = 3; l < L; ++l) dst[l] += __ldg(gp + l);
 }
 
 // ===================================================================================
@@ -100,11 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
-        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed_hot, &wbar, wphase);
         Wp = smem + P.off_W;
     }
-    // zero the padding rows of X once (they feed layer 0 with K = D_p)
-    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+    // zero the padding rows of X once (they feed layer 0 with K = Dn_p)
+    for (int i = threadIdx.x; i < (P.Dn_p - P.Dn) * TBP; i += kThreads) smem[P.off_X + P.Dn * TBP + i] = 0.f;
 
     float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;    // base of the state rows
     float* SY = SB + P.off_S + F_Y * P.Dn_p * TBP;
@@ -122,18 +194,22 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long b0 = tile * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
-        __syncthreads();                                       // previous tile done with X
-        load_y0_tile(P, smem, a.y0, b0, nvalid);
+        __syncthreads();                                       // previous tile done with X and the ACT rows
+        load_y0_tile(P, smem, a.y0, b0, nvalid, true, P.hoist != 0);
         __syncthreads();
+        hoist_c0(P, a.wpacked, smem, warp, lane);              // constant part of both first layers, once per tile
         // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
-            const float* X = smem + P.off_X + (r * L) * TBP + b;
+            const float* X = smem + P.off_X + (3 * r) * TBP + b;
             float v[3] = {X[0], X[TBP], X[2 * TBP]};
             SY[(3 * r + 0) * TBP + b] = v[0];
             SY[(3 * r + 1) * TBP + b] = v[1];
             SY[(3 * r + 2) * TBP + b] = v[2];
-            if (b < nvalid) store_out_row(P, smem, a.y_out + ((b0 + b) * P.R + r) * (long long)L, r, b, v);
+            if (b < nvalid) {
+                const long long row = ((b0 + b) * P.R + r) * (long long)L;
+                store_out_row(P, a.y0 + row, a.y_out + row, v);
+            }
         }
         // (each thread only re-reads rows it wrote itself below, no sync needed here)
         int j = 1;
@@ -149,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
                     const bool valid = b < nvalid;
                     float f[3];
                     rhs_tail(P, smem, r, b, valid, side, f);
-                    float* X = smem + P.off_X + (r * L) * TBP + b;
+                    float* X = smem + P.off_X + (3 * r) * TBP + b;
                     float* tp = a.tape ? a.tape + ((long long)(n * 4 + stage) * tape_stage + (long long)(3 * r) * B + b0 + b) : nullptr;
                     float xn[3];
 #pragma unroll
@@ -188,7 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
                                         v[c] = kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(xn[c], y)));
                                     }
                                 }
-                                store_out_row(P, smem, a.y_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L, r, b, v);
+                                store_out_row(P, a.y0 + ((b0 + b) * P.R + r) * (long long)L,
+                                              a.y_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L, v);
                             }
                             ++jj;
                         }
@@ -232,12 +309,16 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
-        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed, &wbar, wphase);
+        stage_weights_tma(smem + P.off_W, a.wpacked, P.n_packed_hot, &wbar, wphase);
         Wp = smem + P.off_W;
     }
-    float* G = SMEM_G ? smem + P.off_G : a.slabs + (long long)blockIdx.x * P.n_packed;
-    for (int i = threadIdx.x; i < P.n_packed; i += kThreads) G[i] = 0.f;
-    for (int i = threadIdx.x; i < (P.D_p - P.D) * TBP; i += kThreads) smem[P.off_X + P.D * TBP + i] = 0.f;
+    // dtheta accumulators: the hot part (every evaluation) in shared memory when it fits, else in the CTA's global slab;
+    // the constant blocks of the first layers (once per tile) always in the global slab
+    float* Gslab = a.slabs + (long long)blockIdx.x * P.n_packed;
+    float* G = SMEM_G ? smem + P.off_G : Gslab;
+    for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) G[i] = 0.f;
+    for (int i = P.n_packed_hot + threadIdx.x; i < P.n_packed; i += kThreads) Gslab[i] = 0.f;
+    for (int i = threadIdx.x; i < (P.Dn_p - P.Dn) * TBP; i += kThreads) smem[P.off_X + P.Dn * TBP + i] = 0.f;
 
     float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if (a.g_side) {
@@ -250,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     float* LAM = SB + P.off_S + B_LAM * SS;
     float* KB = SB + P.off_S + B_KB1 * SS;          // KB[s] = KB + s*SS, s = 0..3
     float* GX = smem + P.off_GX;
-    float* CB = SB + P.off_CB;
+    float* DL = smem + P.off_DL;
 
     const long long B = a.B;
     const long long n_tiles = (B + TB - 1) / TB;
@@ -261,10 +342,21 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
         const long long b0 = tile * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         __syncthreads();
-        load_y0_tile(P, smem, a.y0, b0, nvalid);        // constants of X; dynamic rows reloaded per stage
+        load_y0_tile(P, smem, a.y0, b0, nvalid, false, P.hoist != 0);     // constants only; the dynamic rows come from the tape
         for (int i = threadIdx.x; i < SS; i += kThreads) LAM[i] = 0.f;
-        for (int i = threadIdx.x; i < P.D_p * TBP; i += kThreads) { CB[i] = 0.f; GX[i] = 0.f; }
+        for (int i = threadIdx.x; i < P.Dn_p * TBP; i += kThreads) GX[i] = 0.f;
+        for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
+        // dL/dy0 starts from the cotangent of output 0 (= y0 itself); the constant components then collect the other
+        // outputs' cotangents as they are visited, the live ones are overwritten at the end
+        for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+            const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+            if (b < nvalid) {
+                const long long row = ((b0 + b) * P.R + r) * (long long)L;
+                for (int l = 0; l < L; ++l) a.g_y0[row + l] = __ldg(a.g_out + row + l);
+            }
+        }
         __syncthreads();
+        hoist_c0(P, a.wpacked, smem, warp, lane);
 
         int j = a.g.n_out - 1;
         for (int n = n_steps - 1; n >= 0; --n) {
@@ -287,16 +379,14 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                         const int kind = __ldg(a.g.out_kind + jj);
                         const float w = __ldg(a.g.out_w + jj);
                         const float* gp = a.g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
-                        for (int l = 0; l < L; ++l) {
+#pragma unroll
+                        for (int l = 0; l < 3; ++l) {
                             const float g = __ldg(gp + l);
-                            if (l < 3) {
-                                if (kind == 1) lam[l] += g;
-                                else if (kind == 0) pend[l] += g;
-                                else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
-                            } else {
-                                CB[(r * L + l) * TBP + b] += g;
-                            }
+                            if (kind == 1) lam[l] += g;
+                            else if (kind == 0) pend[l] += g;
+                            else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
                         }
+                        add_const_cotangent(a.g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L);
                     }
                 }
                 const float c8 = dt * 0.125f;
@@ -310,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                     KB[3 * SS + row] = base;
                     LAM[row] = lam[c] + pend[c];    // becomes lambda_n once the four stage VJPs are added
                     // stage input of stage 4
-                    float* X = smem + P.off_X + (r * L + c) * TBP + b;
+                    float* X = smem + P.off_X + (3 * r + c) * TBP + b;
                     *X = valid ? __ldg(a.tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
                 }
             }
@@ -327,9 +417,8 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                     float xb[3];
                     rhs_tail_vjp(P, smem, r, b, b < nvalid, gs, KB[stage * SS + row], KB[stage * SS + row + TBP],
                                  KB[stage * SS + row + 2 * TBP], xb);
-                    float* gx = GX + (r * L) * TBP + b;     // GX := direct term; the layer-0 deltas accumulate on top
+                    float* gx = GX + (3 * r) * TBP + b;     // GX := direct term; the layer-0 deltas accumulate on top
                     gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
-                    for (int l = 3; l < L; ++l) gx[l * TBP] = 0.f;
                 }
                 UDE_PROF_WORK_DONE();
                 __syncthreads();
@@ -343,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        const int xrow = (r * L + c) * TBP + b;
+                        const int xrow = row;
                         const float xb = GX[xrow];
                         const float u = xb * dt;
                         if (stage == 3) {            // x4 = y + dt*((k1 - k2) + k3)
@@ -358,55 +447,63 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                         if (stage > 0)
                             smem[P.off_X + xrow] = valid ? __ldg(a.tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
                     }
-                    for (int l = 3; l < L; ++l) {
-                        const int xrow = (r * L + l) * TBP + b;
-                        CB[xrow] += GX[xrow];
-                    }
                 }
                 UDE_PROF_WORK_DONE();
                 __syncthreads();
                 UDE_PROF_PHASE_END(21);
             }
         }
-        // ---- output 0 (= y0 itself) and the final store of dL/dy0
+        // ---- output 0 (= y0 itself, already in g_y0) + lambda_0; then the hoisted constants' share
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
-                const float* gp = a.g_out + ((b0 + b) * P.R + r) * (long long)L;
                 float* dst = a.g_y0 + ((b0 + b) * P.R + r) * (long long)L;
-                for (int l = 0; l < L; ++l) {
-                    const float g = __ldg(gp + l);
-                    const float acc = l < 3 ? LAM[(3 * r + l) * TBP + b] : CB[(r * L + l) * TBP + b];
-                    dst[l] = acc + g;
-                }
+#pragma unroll
+                for (int l = 0; l < 3; ++l) dst[l] = LAM[(3 * r + l) * TBP + b] + dst[l];
             }
         }
+        __syncthreads();
+        hoist_backward_epilogue(P, a.wpacked, smem, Gslab, a.y0, a.g_y0, b0, nvalid, warp, lane);
     }
     __syncthreads();
-    if (SMEM_G) {
-        float* slab = a.slabs + (long long)blockIdx.x * P.n_packed;
-        for (int i = threadIdx.x; i < P.n_packed; i += kThreads) slab[i] = G[i];
-    }
+    if (SMEM_G)
+        for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
 }
 
 // ===================================================================================
 // small utility kernels
 // ===================================================================================
-// theta (PyTorch layout) -> packed blob (padded rows, zero fill).  One block per layer.
+// Column of theta's W0 row that feeds packed column `col` of the live (c = 0) / constant (c = 1) block of a first layer:
+// live d = 3r + c  <-  u = r*L + c;   constant e = r*(L-3) + k  <-  u = r*L + 3 + k   (u = index into vec(x), lib/models.py:119)
+__device__ __forceinline__ int first_layer_src_col(const ModelP& P, int col, bool constant) {
+    if (!constant) { const int r = col / 3; return r * P.L + (col - 3 * r); }
+    const int Lc = P.L - 3, r = col / Lc;
+    return r * P.L + 3 + (col - Lc * r);
+}
+
+// theta (PyTorch layout) -> packed blob (padded rows, zero fill).  One block per layer, then one per constant
+// block of the first layers (ModelP: "Hoisting"), then the tail padding.
 __global__ void pack_theta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ theta, float* __restrict__ packed) {
-    const int li = blockIdx.x;
-    if (li == P.n_rate + P.n_aug) {       // tail padding
+    const int li = blockIdx.x, nl = P.n_rate + P.n_aug;
+    if (li == nl + 2) {       // tail padding
         for (int i = threadIdx.x; i < kPadTail; i += blockDim.x) packed[P.n_packed - kPadTail + i] = 0.f;
         return;
     }
-    const LayerP& Lp = li < P.n_rate ? P.rate[li] : P.aug[li - P.n_rate];
+    const bool constant = li >= nl;
+    if (constant && (!P.hoist || (li == nl ? P.n_rate == 0 : P.n_aug == 0))) return;
+    const LayerP& Lp = constant ? (li == nl ? P.rate_c : P.aug_c) : (li < P.n_rate ? P.rate[li] : P.aug[li - P.n_rate]);
+    const bool first = constant || li == 0 || li == P.n_rate;
     const int nW = Lp.n_out_p * Lp.ldw;
     for (int i = threadIdx.x; i < nW; i += blockDim.x) {
         const int row = i / Lp.ldw, col = i - row * Lp.ldw;
-        packed[Lp.w_off + i] = (row < Lp.n_out && col < Lp.n_in) ? theta[Lp.th_w + row * Lp.n_in + col] : 0.f;
+        float v = 0.f;
+        if (row < Lp.n_out && col < Lp.n_in)
+            v = theta[Lp.th_w + row * Lp.th_ld + (first && P.hoist ? first_layer_src_col(P, col, constant) : col)];
+        packed[Lp.w_off + i] = v;
     }
-    for (int i = threadIdx.x; i < Lp.n_out_p; i += blockDim.x)
-        packed[Lp.b_off + i] = i < Lp.n_out ? theta[Lp.th_b + i] : 0.f;
+    if (!constant)
+        for (int i = threadIdx.x; i < Lp.n_out_p; i += blockDim.x)
+            packed[Lp.b_off + i] = i < Lp.n_out ? theta[Lp.th_b + i] : 0.f;
 }
 
 // g_theta[e] = sum over CTA slabs (fixed order => deterministic) of the packed accumulators.
@@ -418,10 +515,17 @@ __global__ void reduce_dtheta_kernel(const __grid_constant__ ModelP P, const flo
     const int nl = P.n_rate + P.n_aug;
     for (int li = 0; li < nl; ++li) {
         const LayerP& Lp = li < P.n_rate ? P.rate[li] : P.aug[li - P.n_rate];
-        if (e >= Lp.th_w && e < Lp.th_w + Lp.n_in * Lp.n_out) {
+        const bool first = li == 0 || li == P.n_rate;
+        if (e >= Lp.th_w && e < Lp.th_w + Lp.th_ld * Lp.n_out) {
             const int k = e - Lp.th_w;
-            const int row = k / Lp.n_in, col = k - row * Lp.n_in;
-            pidx = Lp.w_off + row * Lp.ldw + col;
+            const int row = k / Lp.th_ld, u = k - row * Lp.th_ld;
+            if (first && P.hoist) {
+                const int r = u / P.L, l = u - r * P.L;
+                const LayerP& Lc = li == 0 && P.n_rate > 0 ? P.rate_c : P.aug_c;
+                pidx = l < 3 ? Lp.w_off + row * Lp.ldw + 3 * r + l : Lc.w_off + row * Lc.ldw + r * (P.L - 3) + (l - 3);
+            } else {
+                pidx = Lp.w_off + row * Lp.ldw + u;
+            }
             break;
         }
         if (e >= Lp.th_b && e < Lp.th_b + Lp.n_out) {

@@ -46,6 +46,8 @@ def _opts(rtol, atol, options) -> "_lib.UdeDopri5Opts":
 
 
 class _Dopri5Solve(torch.autograd.Function):
+    last_steps = None
+
     @staticmethod
     def forward(ctx, theta, y0, info: FuncInfo, t_dev, opts, need_tape: bool):
         L = _lib.lib()
@@ -72,6 +74,12 @@ class _Dopri5Solve(torch.autograd.Function):
         ctx.has_tape = tape is not None
         ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev), counts)
         ctx.mark_non_differentiable(counts)
+        # accepted-step record (t0, dt) per trajectory, fp64: the tail of the tape (csrc/ude_host.cu: dopri_tape_x_bytes)
+        ctx.steps = None
+        if tape is not None:
+            x_bytes = ((opts.max_steps + 1) * 6 * 3 * R * B * 4 + 255) // 256 * 256
+            ctx.steps = tape[x_bytes:x_bytes + opts.max_steps * B * 16].view(torch.float64).view(opts.max_steps, B, 2)
+        _Dopri5Solve.last_steps = ctx.steps
         return y_out, side, counts
 
     @staticmethod
@@ -99,11 +107,13 @@ class _Dopri5Solve(torch.autograd.Function):
 class Dopri5Stats:
     """Per-trajectory controller statistics of the last fused solve."""
 
-    def __init__(self, counts: torch.Tensor):
+    def __init__(self, counts: torch.Tensor, steps=None):
         self.n_accept = counts[:, 0]
         self.n_reject = counts[:, 1]
         self.status = counts[:, 2]
         self.n_attempts = counts[:, 3]
+        self.steps = steps          # [max_accepted_steps, B, 2] fp64 (t0, dt) of every accepted step (rows >= n_accept unused);
+                                    # None when the solve kept no tape (no input required grad)
 
 
 def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
@@ -121,5 +131,5 @@ def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
         side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
     if options.get("return_stats", False):
-        return y_out, Dopri5Stats(counts)
+        return y_out, Dopri5Stats(counts, _Dopri5Solve.last_steps)
     return y_out

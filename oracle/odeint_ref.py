@@ -14,6 +14,9 @@ algorithm is restated here (PARITY UNPINNED, see oracle/__init__.py):
   Dormand-Prince tableau, FSAL, fp64 time keeping, RMS error norm over the whole
   tensor, 4th-order dense output (torchdiffeq/_impl/rk_common.py, dopri5.py,
   interp.py, misc.py).
+* ``options['replay_dt']`` (NOT in torchdiffeq; needs ``per_trajectory``): a ``[n, B]`` fp64 table of step sizes;
+  trajectory ``b`` takes ``replay_dt[k, b]`` as its k-th step and accepts it -- the integrator and the dense output
+  with the controller taken out, so that two implementations can be compared on the SAME step sequence.
 * ``options['per_trajectory']=True`` (NOT in torchdiffeq): the same Dopri5
   controller applied to every trajectory (row of the leading batch axis) on its
   own, i.e. exactly what torchdiffeq does when called with B=1 — the semantics of
@@ -222,13 +225,19 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
     ifactor = float(options.get("ifactor", 10.0))
     dfactor = float(options.get("dfactor", 0.2))
     stats: Optional[Dopri5Stats] = options.get("stats", None)
+    replay = options.get("replay_dt", None)
+    if replay is not None:
+        assert per_traj, "replay_dt needs per_trajectory=True"
+        replay = replay.to(torch.float64)
     B = y0.shape[0]
     sdt = y0.dtype
     t64 = t.to(torch.float64)
     nb = B if per_traj else 1
 
     f0 = func(t[0], y0)
-    if first_step is None:
+    if replay is not None:
+        dt = replay[0].clone()
+    elif first_step is None:
         dt = _select_initial_step(func, t[0], y0, 4, rtol, atol, f0, per_traj).reshape(nb)
     else:
         dt = torch.full((nb,), float(first_step), dtype=torch.float64)
@@ -268,6 +277,10 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
                 ratio = _rms(err / tol, per_traj).abs().reshape(nb)
                 accept = (ratio <= 1) & active
                 dt_next = _optimal_step_size(dt, ratio, safety, ifactor, dfactor, 5)
+                if replay is not None:          # controller taken out: every step of the table is accepted as is
+                    accept = active
+                    k_next = torch.clamp(n_acc + accept.long(), max=replay.shape[0] - 1)
+                    dt_next = replay.gather(0, k_next.reshape(1, -1)).reshape(nb)
             y_mid = y_cur + _weighted_sum(ks, DOPRI5_C_MID, dts)
             new_coeffs = _interp_fit(y_cur, y1, y_mid, ks[0], f1, dts)
             acc_b = _bc(accept, y_cur, per_traj)

@@ -38,6 +38,21 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max()) / denom
 
 
+def scaled_err(a: torch.Tensor, b: torch.Tensor, rtol: float = 1e-5, atol_frac: float = 1e-7) -> float:
+    """Element-wise scaled error: max over elements of |a-b| / (rtol*|b| + atol_frac*max|b|) (b = reference).
+    <= 1 means every element is inside its own tolerance -- unlike rel_err, a small component (I ~ 0.02 next to
+    S ~ 0.9, a small dtheta entry) is judged at its OWN magnitude plus an fp32-noise floor tied to the tensor's scale.
+    Trajectories use atol_frac = 1e-7 (~ one fp32 ulp of the largest entry); gradients are fp32 SUMS over
+    trajectories x stages, whose round-off floor is a few 1e-7 of the largest entry in ANY fp32 implementation
+    (the oracle's own autograd included), so gradient tests state a wider atol_frac explicitly."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    scale = rtol * b.abs() + atol_frac * float(b.abs().max())
+    if float(scale.max()) == 0.0:
+        return float((a - b).abs().max())
+    return float(((a - b).abs() / scale.clamp_min(1e-300)).max())
+
+
 def module_from_spec(spec: UdeSpec, theta: torch.Tensor, fa_w: float = 1.0, device="cpu"):
     """Build this package's Fp/Fa/FaFp with the weights of a flat theta."""
     import ude_b200
