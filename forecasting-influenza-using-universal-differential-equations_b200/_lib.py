@@ -75,7 +75,7 @@ _UNIT_DEPS = {
 _UNITS = list(_UNIT_DEPS)
 _SOURCES = _UNITS + sorted({d for deps in _UNIT_DEPS.values() for d in deps})
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-split-compile", "0",
     "-Xcompiler", "-fPIC,-ffp-contract=off",
 ]
 

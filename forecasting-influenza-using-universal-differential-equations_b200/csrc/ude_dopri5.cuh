@@ -441,12 +441,23 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     __shared__ double s_t0[kMaxTB], s_t1[kMaxTB];
     __shared__ float s_dt[kMaxTB];
     __shared__ int s_j[kMaxTB], s_nacc[kMaxTB], s_act[kMaxTB], s_max;
+    __shared__ uint32_t tmem_slot;
 
     copy_model_to_smem(&P, Pg);
     if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn, R = P.R;
+    const bool tm_acc = COLD && P.tm_acc;          // see rk4_bwd_kernel
+    uint32_t tmem = 0u;
+    if (tm_acc) {
+        if (warp == 0) tm_alloc512(&tmem_slot);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = tmem_slot;
+        dw_tm_clear(P, smem + P.off_GB, tmem, warp);
+    }
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
@@ -487,7 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
         }
         __syncthreads();
-        rhs_backward_layers(P, Wp, smem, G, warp, lane);
+        if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
+        else rhs_backward_layers<false>(P, Wp, smem, G, warp, lane);
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -633,6 +645,12 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     __syncthreads();
     if (SMEM_G)
         for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
+    if (tm_acc) {
+        dw_tm_flush(P, smem + P.off_GB, Gslab, tmem, warp, lane);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) tm_free512(tmem);
+    }
 }
 
 }  // namespace ude

@@ -57,6 +57,75 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------
+// Tensor memory as accumulator scratch.  The FFMA engine issues no tcgen05.mma, but the 256 KB of TMEM per SM are
+// the only on-chip place left for the weight-gradient accumulators of the wide models (R = 49: 166 KB of dtheta next
+// to 157 KB of activations in shared memory): with the 32x32b access shape a thread owns TMEM lane
+// 32 * (warp % 4) + lane and reads / writes N consecutive 32-bit columns as N registers, so every thread gets a
+// private, runtime-indexed scratch of up to 512 words that costs no shared-memory bandwidth.
+// ----------------------------------------------------------------------------------
+template <int N> struct TmIo;
+template <> struct TmIo<16> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    }
+    static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(
+                __float_as_uint(v[0])),
+            "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+            "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+            "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
+            "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+};
+template <> struct TmIo<4> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t r[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+    }
+    static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0,%1,%2,%3};" ::"r"(__float_as_uint(v[0])),
+                     "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+};
+template <> struct TmIo<1> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t r;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        v[0] = __uint_as_float(r);
+    }
+    static __device__ __forceinline__ void st(uint32_t taddr, const float* v) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%1], {%0};" ::"r"(__float_as_uint(v[0])), "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+};
+// whole-TMEM allocation by one warp (1 CTA per SM on every path that uses it); the base address lands in *slot
+__device__ __forceinline__ void tm_alloc512(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tm_free512(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base));
+}
+constexpr int kTmSlot = 16;          // columns of one weight-gradient unit (4 x 4 accumulators per thread)
+
+// ----------------------------------------------------------------------------------
 // TMA bulk staging of the packed weights (global -> shared), once per CTA (or per
 // weight-set change).  cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP.
 // ----------------------------------------------------------------------------------
@@ -234,9 +303,13 @@ __device__ __forceinline__ void bwd_unit(const LayerP& Lp, const LayerP* prev, c
 // dW:  G[n][m] += sum_b d[n][b] * in[m][b]    (m = input feature, n = output feature, k = trajectory)
 // m = m0 + tx + 8p, n = n0 + ty + 4q.  Each (n, m) is owned by exactly one thread of one
 // unit, so the accumulators are updated with plain read-modify-writes (deterministic).
-template <int TM, int TN>
+// TM_ACC: the accumulators live in the thread's TMEM columns at `tm` across ALL evaluations, tiles and steps of the
+// launch (dw_flush_unit writes them to the CTA slab once, at the end) and the bias sums in the shared-memory array
+// `G` (indexed by LayerP::bc_off); otherwise `G` is the packed accumulator blob (shared memory or the global slab).
+template <int TM, int TN, bool TM_ACC>
 __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restrict__ smem, float* __restrict__ G,
-                                        const int TB, const int TBP, const int mt, const int nt, const int lane) {
+                                        const int TB, const int TBP, const int mt, const int nt, const int lane,
+                                        const uint32_t tm = 0u) {
     const int tx = lane & 7, ty = lane >> 3;
     const int m0 = mt * (8 * TM), n0 = nt * (4 * TN);
     int aofs[TM], dofs[TN];
@@ -254,11 +327,14 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
     }
     float acc[TN][TM];
     float accb[TN];                       // bias gradient: sum_b d[n][b] (kept by the units of m-tile 0)
+    if (TM_ACC) TmIo<TM * TN>::ld(tm, &acc[0][0]);
 #pragma unroll
     for (int q = 0; q < TN; ++q) {
         accb[q] = 0.f;
+        if (!TM_ACC) {
 #pragma unroll
-        for (int p = 0; p < TM; ++p) acc[q][p] = 0.f;
+            for (int p = 0; p < TM; ++p) acc[q][p] = 0.f;
+        }
     }
     const bool with_bias = mt == 0 && !Lp.no_db;       // warp-uniform
 #pragma unroll 2
@@ -293,8 +369,13 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
 #pragma unroll
         for (int q = 0; q < TN; ++q) {
             const int n = n0 + ty + 4 * q;
-            if (n < Lp.n_out) G[Lp.b_off + n] += accb[q];
+            if (n < Lp.n_out) G[(TM_ACC ? Lp.bc_off : Lp.b_off) + n] += accb[q];
         }
+    }
+    if (TM_ACC) {
+        __syncwarp();                      // .sync.aligned: the bias branch above diverged
+        TmIo<TM * TN>::st(tm, &acc[0][0]);
+        return;
     }
     float* __restrict__ Gw = G + Lp.w_off;
 #pragma unroll
@@ -304,6 +385,26 @@ __device__ __forceinline__ void dw_unit(const LayerP& Lp, const float* __restric
         for (int p = 0; p < TM; ++p) {
             const int m = m0 + tx + 8 * p;
             if (n < Lp.n_out && m < Lp.n_in) Gw[n * Lp.ldw + m] += acc[q][p];
+        }
+    }
+}
+
+// TM_ACC epilogue: this thread's accumulators of unit (mt, nt) -> the packed CTA slab (same element ownership as dw_unit)
+template <int TM, int TN>
+__device__ __forceinline__ void dw_flush_unit(const LayerP& Lp, float* __restrict__ Gslab, const int mt, const int nt,
+                                              const int lane, const uint32_t tm) {
+    const int tx = lane & 7, ty = lane >> 3;
+    const int m0 = mt * (8 * TM), n0 = nt * (4 * TN);
+    float acc[TN][TM];
+    TmIo<TM * TN>::ld(tm, &acc[0][0]);
+    float* __restrict__ Gw = Gslab + Lp.w_off;
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+        const int n = n0 + ty + 4 * q;
+#pragma unroll
+        for (int p = 0; p < TM; ++p) {
+            const int m = m0 + tx + 8 * p;
+            if (n < Lp.n_out && m < Lp.n_in) Gw[n * Lp.ldw + m] = acc[q][p];
         }
     }
 }
@@ -381,13 +482,28 @@ __device__ __forceinline__ void rhs_forward_layers(const ModelP& P, const float*
 }
 
 __device__ __forceinline__ int dw_units(const LayerP& Lp) { return Lp.dw_mt * Lp.dw_nt; }
-__device__ __forceinline__ void dw_run(const LayerP& Lp, const float* smem, float* G, int TB, int TBP, int u, int lane) {
+template <bool TM_ACC = false>
+__device__ __forceinline__ void dw_run(const LayerP& Lp, const float* smem, float* G, int TB, int TBP, int u, int lane,
+                                       uint32_t tm = 0u) {
     int mt = u, nt = 0;                                  // u -> (mt, nt) without a division (dw_mt is tiny)
     while (mt >= Lp.dw_mt) { mt -= Lp.dw_mt; ++nt; }
-    if (Lp.tm_dw == 4 && Lp.tn_dw == 4) dw_unit<4, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
-    else if (Lp.tm_dw == 1 && Lp.tn_dw == 4) dw_unit<1, 4>(Lp, smem, G, TB, TBP, mt, nt, lane);
-    else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_unit<4, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
-    else dw_unit<1, 1>(Lp, smem, G, TB, TBP, mt, nt, lane);
+    if (Lp.tm_dw == 4 && Lp.tn_dw == 4) dw_unit<4, 4, TM_ACC>(Lp, smem, G, TB, TBP, mt, nt, lane, tm);
+    else if (Lp.tm_dw == 1 && Lp.tn_dw == 4) dw_unit<1, 4, TM_ACC>(Lp, smem, G, TB, TBP, mt, nt, lane, tm);
+    else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_unit<4, 1, TM_ACC>(Lp, smem, G, TB, TBP, mt, nt, lane, tm);
+    else dw_unit<1, 1, TM_ACC>(Lp, smem, G, TB, TBP, mt, nt, lane, tm);
+}
+__device__ __forceinline__ void dw_flush_run(const LayerP& Lp, float* Gslab, int u, int lane, uint32_t tm) {
+    int mt = u, nt = 0;
+    while (mt >= Lp.dw_mt) { mt -= Lp.dw_mt; ++nt; }
+    if (Lp.tm_dw == 4 && Lp.tn_dw == 4) dw_flush_unit<4, 4>(Lp, Gslab, mt, nt, lane, tm);
+    else if (Lp.tm_dw == 1 && Lp.tn_dw == 4) dw_flush_unit<1, 4>(Lp, Gslab, mt, nt, lane, tm);
+    else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_flush_unit<4, 1>(Lp, Gslab, mt, nt, lane, tm);
+    else dw_flush_unit<1, 1>(Lp, Gslab, mt, nt, lane, tm);
+}
+// TMEM address of the accumulators of the `it`-th unit this warp runs in the weight-gradient phase of depth s:
+// warps w and w + 4 share a lane quarter, so their slots interleave
+__device__ __forceinline__ uint32_t dw_tm_addr(const ModelP& P, uint32_t tmem, int s, int it, int warp) {
+    return tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(P.tm_dw_base[s] + (it * (kWarps / 4) + (warp >> 2)) * kTmSlot);
 }
 __device__ __forceinline__ int bwd_units(const LayerP& Lp, int mt_shift) { return Lp.bwd_nt << mt_shift; }
 __device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, const float* Wp, float* smem, int TBP,
@@ -401,8 +517,9 @@ __device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, co
 // lockstep.  Pre: the head ACT rows hold dL/d(head output) (written by the caller),
 // every other ACT row still holds the forward activation, all synced.
 // GX rows pre-loaded with the direct dL/du.  Post: GX += W0^T delta0 of both nets; G accumulated.
+template <bool TM_ACC = false>
 __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float* Wp, float* smem, float* G, int warp,
-                                                    int lane) {
+                                                    int lane, uint32_t tmem = 0u) {
     const int m_tiles = P.mt_shift;
     const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
     UDE_PROF_DECL;
@@ -425,9 +542,11 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
             }
             const int w0 = Lr ? dw_units(*Lr) : 0;
             const int w1 = La ? dw_units(*La) : 0;
-            for (int u = warp; u < w0 + w1; u += kWarps) {
-                if (u < w0) dw_run(*Lr, smem, G, P.TB, P.TBP, u, lane);
-                else dw_run(*La, smem, G, P.TB, P.TBP, u - w0, lane);
+            int it = 0;
+            for (int u = warp; u < w0 + w1; u += kWarps, ++it) {
+                const uint32_t tm = TM_ACC ? dw_tm_addr(P, tmem, s, it, warp) : 0u;
+                if (u < w0) dw_run<TM_ACC>(*Lr, smem, G, P.TB, P.TBP, u, lane, tm);
+                else dw_run<TM_ACC>(*La, smem, G, P.TB, P.TBP, u - w0, lane, tm);
             }
         }
         UDE_PROF_WORK_DONE();
@@ -452,6 +571,37 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
         UDE_PROF_WORK_DONE();
         __syncthreads();
         UDE_PROF_PHASE_END(9 + 2 * s);
+    }
+}
+
+// TM_ACC: zero every accumulator column / write all of them (and the bias sums in shared memory) to the CTA slab.
+// Same unit -> (warp, slot) walk as rhs_backward_layers.
+__device__ __forceinline__ void dw_tm_clear(const ModelP& P, float* gb, uint32_t tmem, int warp) {
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c = (warp >> 2) * kTmSlot; c < P.tm_cols; c += (kWarps / 4) * kTmSlot) TmIo<16>::st(lane_base + c, z);
+    for (int i = threadIdx.x; i < P.n_bias_c; i += kThreads) gb[i] = 0.f;
+}
+__device__ __forceinline__ void dw_tm_flush(const ModelP& P, const float* gb, float* Gslab, uint32_t tmem, int warp, int lane) {
+    const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+    for (int s = 0; s < nl; ++s) {
+        const int lr = P.n_rate - 1 - s, la = P.n_aug - 1 - s;
+        const LayerP* Lr = lr >= 0 ? &P.rate[lr] : nullptr;
+        const LayerP* La = la >= 0 ? &P.aug[la] : nullptr;
+        const int w0 = Lr ? dw_units(*Lr) : 0, w1 = La ? dw_units(*La) : 0;
+        int it = 0;
+        for (int u = warp; u < w0 + w1; u += kWarps, ++it) {
+            const uint32_t tm = dw_tm_addr(P, tmem, s, it, warp);
+            if (u < w0) dw_flush_run(*Lr, Gslab, u, lane, tm);
+            else dw_flush_run(*La, Gslab, u - w0, lane, tm);
+        }
+        for (int net = 0; net < 2; ++net) {
+            const LayerP* Lp = net == 0 ? Lr : La;
+            if (Lp)
+                for (int n = threadIdx.x; n < Lp->n_out; n += kThreads) Gslab[Lp->b_off + n] = gb[Lp->bc_off + n];
+        }
     }
 }
 

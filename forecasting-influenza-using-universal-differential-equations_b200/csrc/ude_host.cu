@@ -179,7 +179,6 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
     P.off_GX = off;
     if (bwd) off += P.Dn_p * P.TBP;
     off += 8;    // slack
-    P.smem_floats = off;
     // tile shapes: aim at >= kWarps units per phase (both nets run in the same phase)
     const int nets = (P.n_rate > 0) + (P.n_aug > 0);
     const int want = kWarps / nets;
@@ -193,6 +192,42 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
         if (P.n_rate > 0) tile_shapes(P.rate_c, m_tiles, want);
         if (P.n_aug > 0) tile_shapes(P.aug_c, m_tiles, want);
     }
+    // weight-gradient accumulators in tensor memory: only on the plan of last resort (nothing else fits on chip),
+    // one 16-column slot per unit and warp, phases of depth s (heads first) side by side
+    P.tm_acc = 0;
+    P.tm_cols = 0;
+    P.n_bias_c = 0;
+    P.off_GB = off;
+    if (bwd && cold && !g_smem) {
+        int bc = 0;
+        for (int net = 0; net < 2; ++net) {
+            LayerP* Ls = net == 0 ? P.rate : P.aug;
+            const int n = net == 0 ? P.n_rate : P.n_aug;
+            for (int i = 0; i < n; ++i) { Ls[i].bc_off = bc; bc += Ls[i].n_out_p; }
+        }
+        const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+        int cols = 0;
+        bool ok = true;
+        for (int s = 0; s < nl; ++s) {
+            const int lr = P.n_rate - 1 - s, la = P.n_aug - 1 - s;
+            int units = 0;
+            for (int net = 0; net < 2; ++net) {
+                const int l = net == 0 ? lr : la;
+                if (l < 0) continue;
+                const LayerP& Lp = net == 0 ? P.rate[l] : P.aug[l];
+                units += Lp.dw_mt * Lp.dw_nt;
+            }
+            P.tm_dw_base[s] = cols;
+            cols += (units + kWarps - 1) / kWarps * (kWarps / 4) * 16;
+        }
+        if (ok && cols <= 512) {
+            P.tm_acc = 1;
+            P.tm_cols = cols;
+            P.n_bias_c = bc;
+            off += bc;
+        }
+    }
+    P.smem_floats = off;
     return off;
 }
 

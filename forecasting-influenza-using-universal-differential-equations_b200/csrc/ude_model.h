@@ -37,6 +37,7 @@ struct LayerP {
     int c0_off;             // >= 0: smem rows [n_out_p][TBP] added INSTEAD of the bias (first layers with hoisted constants)
     int th_ld;              // row stride of W inside theta (== n_in except for the split first layer, where it is R*L)
     int no_db;              // weight-gradient units skip the bias gradient (constant block: the live block owns it)
+    int bc_off;             // compact bias offset (sum of n_out_p of the layers before): bias sums of the TMEM-accumulator mode
 };
 
 struct ModelP {
@@ -76,6 +77,10 @@ struct ModelP {
     int off_GX;             // (bwd) dL/dx_live of one RHS evaluation, [Dn_p][TBP]
     int n_state;
     int off_RB, n_rbuf;     // per-region scratch: n_rbuf buffers of [R_p][TBP] (dopri5)
+    int tm_acc;             // (bwd) weight-gradient accumulators in tensor memory (ude_engine.cuh: TmIo), bias sums at off_GB
+    int tm_dw_base[kMaxLayers];   // first TMEM column of the weight-gradient phase of depth s (counted from the heads)
+    int tm_cols;            // columns in use
+    int n_bias_c, off_GB;   // compact bias array [n_bias_c] in shared memory
     int cold_global;        // solver-state rows (off_S, off_RB, off_CB) live in a per-CTA global scratch
     int cold_floats;        // size of that scratch per CTA
     int smem_floats;        // total arena size

@@ -300,12 +300,24 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
     __shared__ __align__(8) uint64_t wbar;
+    __shared__ uint32_t tmem_slot;
 
     copy_model_to_smem(&P, Pg);
     if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn;
+    // plan of last resort (wide models): the weight-gradient accumulators live in tensor memory for the whole launch
+    const bool tm_acc = COLD && P.tm_acc;
+    uint32_t tmem = 0u;
+    if (tm_acc) {
+        if (warp == 0) tm_alloc512(&tmem_slot);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = tmem_slot;
+        dw_tm_clear(P, smem + P.off_GB, tmem, warp);
+    }
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
@@ -423,7 +435,8 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                 UDE_PROF_WORK_DONE();
                 __syncthreads();
                 UDE_PROF_PHASE_END(20);
-                rhs_backward_layers(P, Wp, smem, G, warp, lane);
+                if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
+                else rhs_backward_layers<false>(P, Wp, smem, G, warp, lane);
                 UDE_PROF_RESTART();
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
@@ -468,6 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     __syncthreads();
     if (SMEM_G)
         for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
+    if (tm_acc) {
+        dw_tm_flush(P, smem + P.off_GB, Gslab, tmem, warp, lane);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) tm_free512(tmem);
+    }
 }
 
 // ===================================================================================
