@@ -4,15 +4,21 @@
 Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (torchrun for N>1)
 prints ONE JSON line on rank 0.  A "step" is one pass of the hot path over one batch of
 synthetic ILI-shaped input: the fused RK4 forward over the whole time grid followed by the
-fused discrete-adjoint backward (+ the NCCL all-reduce of dL/dtheta when N>1).
+fused discrete-adjoint backward (+ the NCCL all-reduces of the side sums and of dL/dtheta when N>1).
 
 Workload = BASELINE.json configs[3] (the configuration the metric is quoted on):
-  FaFp(R=1, L=8, net [64,64,32], aug [64,64]), B = 2**20 trajectories PER GPU (weak scaling:
-  trajectories are independent IVPs, sharded across ranks), t = [0..8] weeks, h = 1 (8 RK4 steps).
+  FaFp(R=1, L=8, net [64,64,32], aug [64,64]), B = 2**20 trajectories IN TOTAL, sharded by trajectory
+  over the N ranks (strong scaling, as the metric says: "B=1M ... trajectory-sharded at 2/4/8 GPUs");
+  t = [0..8] weeks, h = 1 (8 RK4 steps).  The weak-scaling figure (2**20 per GPU) rides along as a sub-record.
 
-``--impl reference`` times the reference's CPU path for the same metric/config on the host
-cores: the oracle port (oracle/odeint_ref.py driving the restated lib/models.py RHS with
-torch autograd — torchdiffeq itself is not installable offline), on a bounded sample.
+``secondary`` (N = 1 only) carries the other BASELINE configs: configs[0] single-trajectory latency, the
+reference's own training shape (B = 2048), configs[2] (49 states x 256 samples, 28 daily steps), configs[1]
+(49-state Dopri5 epoch) and configs[4] (64 weight-set groups per GPU).
+
+``--impl reference`` times the reference's CPU path for the same metric/config on the host cores: the real
+``lib.models`` classes when /root/reference is importable (kind "reference"), else the oracle port of them
+(kind "port"), driven by the oracle's restatement of torchdiffeq's rk4 (torchdiffeq itself is not installable
+offline) with torch autograd, on a bounded sample.
 """
 from __future__ import annotations
 
@@ -29,10 +35,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_STEPS_GRID = 8            # weekly RK4 steps, t = arange(9.)  (run_ode.py:93,147)
-B_PER_GPU = 1 << 20
+B_TOTAL = 1 << 20
 CPU_SAMPLE_B = 65536
 METRIC = "ude_trajectory_steps_per_sec_fwd_plus_adjoint"
 UNIT = "trajectory-steps/s"
+WORKLOAD = ("BASELINE configs[3]: synthetic ensemble, FaFp R=1 L=8 net [64,64,32] aug [64,64] (nn.Linear default init, "
+            "aug head scaled by aug_head_scale=0.05 so that trajectories stay inside the RHS clamp), RK4(3/8) t=[0..8] h=1 "
+            "(8 steps), fused forward + discrete-adjoint backward")
 
 
 def _spec():
@@ -56,6 +65,17 @@ def tensor_macs_per_tile_eval(spec) -> dict:
             dlt += 6 * 128 * i * o
             dw += 8 * 16 * 64 * ((2 * i + 8) + (i + 8))
     return {"fwd": fwd, "bwd": fwd + dlt + dw}
+
+
+def fma_pipe_macs_per_traj_eval(spec) -> dict:
+    """MACs of the tcgen05 kernels that stay on the fp32 FMA pipe (csrc/ude_tc.cuh): the head layers forward, the heads'
+    Wh^T g and the first layers' W0^T delta0 in the sweep."""
+    heads = first = 0
+    for sizes, head in ((spec.net_sizes, 2 * spec.n_regions), (spec.aug_sizes, 3 * spec.n_regions)):
+        if len(sizes):
+            heads += sizes[-1] * head
+            first += spec.n_regions * spec.latent_dim * sizes[0]
+    return {"fwd": heads, "bwd": heads + heads + first}
 
 
 def flops_per_traj_step(macs: int) -> dict:
@@ -117,32 +137,79 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------
-# CPU reference arm (oracle port; also the cpu_baseline leg of the GPU arm)
+# CPU reference arm (also the cpu_baseline leg of the GPU arm)
 # ---------------------------------------------------------------------------------------
-def cpu_reference_step(B: int, threads: int, reps: int):
-    """fwd + backward of the reference path on the host: returns median seconds per pass."""
+def reference_func(spec, theta, fa_w=1.0):
+    """(callable ODE func, kind, theta-ordered parameter list): the REAL reference class
+    (/root/reference/lib/models.py:109-265) holding `theta` when the reference tree is importable, else the oracle's
+    port of it.  Both follow the ODE-func protocol (params / tracker / posterior())."""
+    import torch
+    ref_root = "/root/reference"
+    if os.path.isdir(os.path.join(ref_root, "lib")):
+        try:
+            if ref_root not in sys.path:
+                sys.path.insert(0, ref_root)
+            import lib.models as ref_models
+            kw = {}
+            if spec.has_rate:
+                kw["net_sizes"] = list(spec.net_sizes)
+            if spec.has_aug:
+                kw["aug_net_sizes"] = list(spec.aug_sizes)
+            mod = getattr(ref_models, spec.kind)(spec.n_regions, spec.latent_dim, **kw)
+            nets = []
+            if spec.kind == "Fp":
+                nets = [mod.Fp_net]
+            elif spec.kind == "FaFp":
+                nets = [mod.net, mod.aug_net]
+            else:
+                nets = [mod.aug_net]
+            off = 0
+            plist = []
+            with torch.no_grad():
+                for net in nets:
+                    for m in net:
+                        if isinstance(m, torch.nn.Linear):
+                            for p in (m.weight, m.bias):
+                                p.copy_(theta[off:off + p.numel()].reshape(p.shape))
+                                off += p.numel()
+                                plist.append(p)
+            assert off == theta.numel()
+            if spec.kind == "FaFp":
+                mod.Fa_w = fa_w
+            return mod, "reference", plist
+        except Exception:
+            pass
+    from oracle.ude_rhs import OracleFunc
+    f = OracleFunc(spec, theta, fa_w)
+    return f, "port", [f.theta]
+
+
+def cpu_reference_step(B: int, threads: int, reps: int, spec=None, t=None, step_size=None):
+    """fwd + backward of the reference path on the host: returns (median seconds per pass, kind)."""
     import torch
     from oracle import odeint_ref
-    from oracle.ude_rhs import OracleFunc, init_theta, synth_y0
+    from oracle.ude_rhs import init_theta, synth_y0
     torch.set_num_threads(threads)
-    spec = _spec()
+    spec = spec or _spec()
     theta = init_theta(spec, seed=0)
-    y0 = synth_y0(B, 1, 8, seed=0)
-    t = torch.arange(float(N_STEPS_GRID + 1))
-    week = torch.arange(N_STEPS_GRID + 1, dtype=torch.float32)
+    y0 = synth_y0(B, spec.n_regions, spec.latent_dim, seed=0)
+    if t is None:
+        t = torch.arange(float(N_STEPS_GRID + 1))
+    h = (t[1] - t[0]) if step_size is None else step_size
+    week = t.clone()
     y_ili = (0.02 + 0.5 * torch.exp(-((week - 5.0) / 4.0) ** 2)).reshape(-1, 1, 1)
-    times = []
+    times, kind = [], "port"
     for i in range(reps + 1):
-        func = OracleFunc(spec, theta)
+        func, kind, _ = reference_func(spec, theta)
         y0g = y0.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        y = odeint_ref.odeint(func, y0g, t, method="rk4", options=dict(step_size=t[1] - t[0]))
+        y = odeint_ref.odeint(func, y0g, t, method="rk4", options=dict(step_size=h))
         loss = _loss(y, y_ili, func)
         loss.backward()
         dt = time.perf_counter() - t0
         if i > 0:
             times.append(dt)
-    return statistics.median(times)
+    return statistics.median(times), kind
 
 
 def _loss(y, y_ili, func):
@@ -155,11 +222,27 @@ def _loss(y, y_ili, func):
     mse = torch.mean((y[..., 1] - y_ili.to(y.device)) ** 2)
     reg = 0.1 * (torch.where(x < 0, x.abs(), torch.zeros_like(x)) +
                  torch.where(x > 1, (1 - x).abs(), torch.zeros_like(x))).sum() / y.shape[1]
-    post = func.posterior()
-    prior = Normal(torch.tensor([0.8, 0.55], device=y.device), torch.tensor([0.2, 0.2], device=y.device))
-    kl_p = kl_divergence(prior, post).mean()
-    fa_norm = 0.1 * torch.norm(torch.stack(func.tracker)) / (y.shape[1] ** 0.5)
-    return mse + reg + kl_p + fa_norm
+    loss = mse + reg
+    if getattr(func, "params", None):
+        post = func.posterior()
+        prior = Normal(torch.tensor([0.8, 0.55], device=y.device), torch.tensor([0.2, 0.2], device=y.device))
+        loss = loss + kl_divergence(prior, post).mean()
+    if getattr(func, "tracker", None):
+        loss = loss + 0.1 * torch.norm(torch.stack(func.tracker)) / (y.shape[1] ** 0.5)
+    return loss
+
+
+def cpu_baseline_record(threads_all: int):
+    """The reference path on the host at all threads and at the reference's own torch.set_num_threads(1)
+    (run_ode.py:28), on a bounded B = 65 536 sample of the bench workload."""
+    sec_all, kind = cpu_reference_step(CPU_SAMPLE_B, threads_all, 3)
+    sec_one, _ = cpu_reference_step(CPU_SAMPLE_B, 1, 1)
+    what = ("the real lib.models.FaFp" if kind == "reference" else "oracle port of lib/models.py (reference tree absent on this box)")
+    return {"value": CPU_SAMPLE_B * N_STEPS_GRID / sec_all, "unit": UNIT, "cores": threads_all, "kind": kind,
+            "sample": f"B={CPU_SAMPLE_B} x {N_STEPS_GRID} steps fwd+autograd backward, median of 3; {what} driven by the "
+                      f"oracle's torchdiffeq-rk4 restatement, {threads_all} torch threads",
+            "single_thread": {"value": CPU_SAMPLE_B * N_STEPS_GRID / sec_one, "cores": 1,
+                              "note": "torch.set_num_threads(1) as the reference sets it (run_ode.py:28); one pass"}}
 
 
 def run_reference(args):
@@ -167,22 +250,25 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    secs = []
+    secs, kind = [], "port"
     for _ in range(args.warmup):
         cpu_reference_step(CPU_SAMPLE_B, cores, 1)
-    t0 = time.perf_counter()
     for _ in range(args.steps):
-        secs.append(cpu_reference_step(CPU_SAMPLE_B, cores, 1))
+        s, kind = cpu_reference_step(CPU_SAMPLE_B, cores, 1)
+        secs.append(s)
     sec = statistics.median(secs)
     value = CPU_SAMPLE_B * N_STEPS_GRID / sec
-    sample = f"B={CPU_SAMPLE_B} trajectories x {N_STEPS_GRID} RK4 steps, fwd+autograd backward, {cores} torch threads"
+    sec_one, _ = cpu_reference_step(CPU_SAMPLE_B, 1, 1)
+    what = "the real lib.models.FaFp" if kind == "reference" else "oracle port of lib/models.py (reference tree absent on this box)"
+    sample = (f"B={CPU_SAMPLE_B} trajectories x {N_STEPS_GRID} RK4 steps, fwd+autograd backward, {what}, {cores} torch threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[3]: FaFp R=1 L=8 [64,64,32]/[64,64], RK4 8 weekly steps, "
-                               "fwd+adjoint; reference CPU path on a bounded sample", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + "; reference CPU path on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "single_thread": {"value": CPU_SAMPLE_B * N_STEPS_GRID / sec_one, "cores": 1,
+                                           "note": "torch.set_num_threads(1), run_ode.py:28"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,6 +278,192 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
+def _cuda_timed(fn, reps=3, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _wall_timed(fn, reps=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / reps * 1e3
+
+
+def _module(spec, theta, dev, fa_w=1.0):
+    import torch
+
+    import ude_b200
+    kw = {}
+    if spec.has_rate:
+        kw["net_sizes"] = list(spec.net_sizes)
+    if spec.has_aug:
+        kw["aug_net_sizes"] = list(spec.aug_sizes)
+    mod = getattr(ude_b200, spec.kind)(spec.n_regions, spec.latent_dim, **kw)
+    info = ude_b200.describe_func(mod)
+    off = 0
+    with torch.no_grad():
+        for lin in info.linears():
+            for p in (lin.weight, lin.bias):
+                p.copy_(theta[off:off + p.numel()].reshape(p.shape))
+                off += p.numel()
+    return mod.to(dev)
+
+
+def secondary_configs(dev, ffma_peak_tflops: float, with_cpu: bool) -> dict:
+    """The other BASELINE.json configs, through the public API (odeint + loss.backward()), 1 GPU.  Times are per
+    ITERATION (fused forward + fused adjoint + the autograd glue); `frac_ffma` = algorithmic flops (SURVEY 8d:
+    24 x MACs per trajectory-step, first layers at their full R*L width) / time / measured FFMA peak."""
+    import torch
+
+    import ude_b200
+    from oracle.ude_rhs import UdeSpec, init_theta, synth_y0
+    out = {}
+    peak = ffma_peak_tflops * 1e12
+
+    def fwd_bwd(mod, y0, t, **kw):
+        def step():
+            y0g = y0.clone().requires_grad_(True)
+            mod.clear_tracking()
+            mod.zero_grad(set_to_none=True)
+            y = ude_b200.odeint(mod, y0g, t, **kw)
+            (y[..., 1] ** 2).mean().backward()
+        return step
+
+    # ---- configs[0]: one trajectory, RK4 fwd + backprop: launch-latency bound by construction
+    spec1 = _spec()
+    mod1 = _module(spec1, init_theta(spec1, 0), dev)
+    lat = {}
+    for name, t in (("weekly_8_steps", torch.arange(9.)), ("daily_85_steps", torch.arange(86.) / 7)):
+        y0 = synth_y0(1, 1, 8, seed=5).to(dev)
+        n = t.numel() - 1
+        ms = _wall_timed(fwd_bwd(mod1, y0, t, method="rk4", options=dict(step_size=t[1] - t[0])), reps=10, warm=3)
+        rec = {"ms_per_solve_fwd_bwd": ms, "us_per_step": ms * 1e3 / n, "grid_steps": n}
+        if with_cpu:
+            sec, kind = cpu_reference_step(1, 1, 2, spec1, t)
+            rec["cpu_ms_per_solve_1_thread"] = sec * 1e3
+            rec["cpu_kind"] = kind
+        lat[name] = rec
+    out["configs[0] B=1 FaFp R=1 RK4 fwd+backprop (run_ode.py:93,130,147), host wall clock per call"] = lat
+
+    # ---- the reference's own training shape: 32 x 64 = 2048 trajectories, 7 weekly steps (run_ode.ipynb:206-213)
+    y0 = synth_y0(2048, 1, 8, seed=6).to(dev)
+    t = torch.arange(8.)
+    step = fwd_bwd(mod1, y0, t, method="rk4", options=dict(step_size=t[1] - t[0]))
+    rec = {"ms_per_iter_wall": _wall_timed(step, reps=10, warm=3), "ms_per_iter_device": _cuda_timed(step, reps=10, warm=3)}
+    rec["trajectory_steps_per_s"] = 2048 * 7 / (rec["ms_per_iter_wall"] * 1e-3)
+    if with_cpu:
+        sec, kind = cpu_reference_step(2048, 1, 2, spec1, t)
+        rec["cpu_ms_per_iter_1_thread"] = sec * 1e3
+        rec["cpu_kind"] = kind
+    out["training shape B=2048 FaFp R=1, 7 weekly RK4 steps, fwd+backprop"] = rec
+
+    # ---- configs[2]: 49 states x 256 latent samples (x b), 28 daily RK4 steps
+    spec49 = UdeSpec("FaFp", 49, 8, (64, 64, 32), (64, 64))
+    mod49 = _module(spec49, init_theta(spec49, 0), dev)
+    t = torch.arange(29.) / 7
+    for b in (1, 32):
+        B = 256 * b
+        y0 = synth_y0(B, 49, 8, seed=1).to(dev)
+        ms = _cuda_timed(fwd_bwd(mod49, y0, t, method="rk4", options=dict(step_size=t[1] - t[0])))
+        ts = B * 28 / (ms * 1e-3)
+        out[f"configs[2] FaFp R=49 y0 [{B},49,8] RK4 28 daily steps fwd+adjoint"] = {
+            "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * spec49.macs_per_eval() / peak}
+
+    # ---- configs[1]: 49-state regional batch, Dopri5 rtol 1e-5, one epoch = 153 iterations of [2048, 49, 8]
+    y0 = synth_y0(2048, 49, 8, seed=2).to(dev)
+    t = torch.arange(9.)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ms = _cuda_timed(fwd_bwd(mod49, y0, t, rtol=1e-5, atol=1e-9, method="dopri5", options=dict(per_trajectory=True)))
+        with torch.no_grad():
+            _, st = ude_b200.odeint(mod49, y0, t, rtol=1e-5, atol=1e-9, method="dopri5",
+                                    options=dict(per_trajectory=True, return_stats=True))
+    n_acc, n_att = float(st.n_accept.float().sum()), float(st.n_attempts.float().sum())
+    # forward: 6 evaluations per attempt (+ f0 + the initial-step probe) at 2 flop/MAC; adjoint: 6 per ACCEPTED step (+ f0) at 4
+    flops = (2 * (6 * n_att + 2 * 2048) + 4 * (6 * n_acc + 2048)) * spec49.macs_per_eval()
+    out["configs[1] FaFp R=49 y0 [2048,49,8] Dopri5 rtol 1e-5 atol 1e-9 t=[0..8] fwd+adjoint"] = {
+        "ms_per_iter": ms, "epoch_153_iters_s": ms * 153e-3, "accepted_steps_mean": n_acc / 2048, "attempted_steps_mean": n_att / 2048,
+        "accepted_trajectory_steps_per_s": n_acc / (ms * 1e-3), "frac_ffma": flops / (ms * 1e-3) / peak}
+
+    # ---- configs[4]: 64 weight-set groups per GPU (512 over 8), Fp hidden 32, 2048 trajectories each, 56 outputs
+    specg = UdeSpec("Fp", 1, 8, (32, 32), ())
+    G, Bg = 64, 2048
+    mods = [_module(specg, init_theta(specg, g), dev) for g in range(G)]
+    y0 = synth_y0(G * Bg, 1, 8, seed=3).reshape(G, Bg, 1, 8).to(dev)
+    t = torch.linspace(1, 56, 56) / 7
+
+    def step_g():
+        y0g = y0.clone().requires_grad_(True)
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=1.0))
+        (y[..., 1] ** 2).mean().backward()
+
+    ms = _cuda_timed(step_g)
+    ts = G * Bg * 8 / (ms * 1e-3)
+    out["configs[4] 64 groups x Fp(R=1,L=8,[32,32]) x 2048 trajectories, RK4 h=1 t=[1/7..8] (8 grid steps, 56 outputs) fwd+adjoint"] = {
+        "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * specg.macs_per_eval() / peak}
+    return out
+
+
+def dist_check(mod, dev, world, rank) -> str:
+    """Untimed: a 4096-trajectory batch solved SHARDED (side sums all-reduced through options['process_group'],
+    gradients through dist.all_reduce_grads) must give every rank the single-GPU gradient."""
+    import torch
+    import torch.distributed as dist
+
+    import ude_b200
+    from oracle.ude_rhs import synth_y0
+    n_samples, batch = 64, 64
+    y0 = synth_y0(n_samples * batch, 1, 8, seed=77).to(dev)
+    t = torch.arange(5.)
+    y_ili = (0.02 + 0.5 * torch.exp(-((t - 2.0) / 4.0) ** 2)).reshape(-1, 1, 1).to(dev)
+    # single-GPU result (every rank computes it: same inputs, same kernels)
+    mod.zero_grad(set_to_none=True)
+    mod.clear_tracking()
+    y = ude_b200.odeint(mod, y0.clone().requires_grad_(True), t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
+    (_loss(y, y_ili, mod) * 1.0).backward()
+    g_single = torch.cat([p.grad.reshape(-1) for p in mod.parameters()]).clone()
+    # sharded: per-rank mean terms are rescaled to the global batch, side-channel terms see the all-reduced sums
+    mod.zero_grad(set_to_none=True)
+    mod.clear_tracking()
+    y0s = ude_b200.dist.shard_flat(y0, n_samples, batch, world, rank).clone().requires_grad_(True)
+    ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=1.0, kernels="ffma", process_group=True))
+    x = ys[..., :3]
+    local = (torch.sum((ys[..., 1] - y_ili) ** 2) / (y.shape[1] * y.shape[0] * y.shape[2]) +
+             0.1 * (torch.where(x < 0, x.abs(), torch.zeros_like(x)) +
+                    torch.where(x > 1, (1 - x).abs(), torch.zeros_like(x))).sum() / y.shape[1])
+    from torch.distributions import Normal, kl_divergence
+    prior = Normal(torch.tensor([0.8, 0.55], device=dev), torch.tensor([0.2, 0.2], device=dev))
+    shared = kl_divergence(prior, mod.posterior()).mean() + 0.1 * torch.norm(torch.stack(mod.tracker)) / (y.shape[1] ** 0.5)
+    # `shared` is the same global scalar on every rank: its parameter gradients are per-rank PARTIAL sums already
+    # (all_reduce_side's backward is the identity), so it enters once per rank and the all-reduce completes it
+    (local + shared).backward()
+    ude_b200.dist.all_reduce_grads(mod.parameters())
+    g_shard = torch.cat([p.grad.reshape(-1) for p in mod.parameters()])
+    err = float((g_shard - g_single).abs().max() / g_single.abs().max())
+    flag = torch.tensor([err], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    err = float(flag)
+    return f"ok (max relative gradient difference {err:.1e})" if err <= 1e-5 else f"FAILED (max relative gradient difference {err:.3e})"
+
+
 def run_ours(args):
     import ctypes as C
 
@@ -215,111 +487,109 @@ def run_ours(args):
 
     L = ude_b200.lib()
     spec = _spec()
-    B = args.batch
-    theta_h = init_theta(spec, seed=0)
-    mod = ude_b200.FaFp(1, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    mod = _module(spec, init_theta(spec, seed=0), dev)
     info = ude_b200.describe_func(mod)
-    off = 0
-    with torch.no_grad():
-        for lin in info.linears():
-            for p in (lin.weight, lin.bias):
-                p.copy_(theta_h[off:off + p.numel()].reshape(p.shape))
-                off += p.numel()
-    mod = mod.to(dev)
-    info = ude_b200.describe_func(mod)
-    macs = int(L.ude_macs_per_eval(C.byref(info.desc(B))))
-    fl = flops_per_traj_step(macs)
-
-    # synthetic inputs: each rank owns its own shard of B trajectories (seeded by rank)
-    y0_host = synth_y0(B, 1, 8, seed=100 + rank).pin_memory()
-    y0 = y0_host.to(dev, non_blocking=True)
     t = torch.arange(float(N_STEPS_GRID + 1))
-    week = torch.arange(N_STEPS_GRID + 1, dtype=torch.float32)
-    y_ili = (0.02 + 0.5 * torch.exp(-((week - 5.0) / 4.0) ** 2)).reshape(-1, 1, 1).to(dev)
+    y_ili = (0.02 + 0.5 * torch.exp(-((t - 5.0) / 4.0) ** 2)).reshape(-1, 1, 1).to(dev)
     (tables, n_steps) = _grid_on_device(t, t[1] - t[0], dev)
     n_out = t.numel()
-
-    # ---- fixed cotangent for the device-resident leg: d(loss)/d(latent) of the synthetic loss
-    y0g = y0.clone().requires_grad_(True)
-    mod.clear_tracking()
-    y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=t[1] - t[0]))
-    side_rows = mod.params[-1]
-    loss = _loss(y, y_ili, mod)
-    g_out = torch.autograd.grad(loss, y, retain_graph=False)[0].contiguous()
-    g_side = torch.tensor([1e-8, -1e-8, 1e-9, 1e-9, 1e-9], dtype=torch.float32, device=dev)
-    del y, loss, y0g, side_rows
-
-    desc = info.desc(B)
-    plan = _lib.UdePlan()
-    _lib.check(L.ude_plan(C.byref(desc), 0, n_steps, C.byref(plan)), "ude_plan")
-    theta = info.theta().detach().contiguous()
-    y_out = torch.empty((n_out, B, 1, 8), dtype=torch.float32, device=dev)
-    side = torch.empty(8, dtype=torch.float64, device=dev)
-    ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
-    tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev)
-    g_y0 = torch.empty_like(y0)
-    g_theta = torch.empty_like(theta)
     dt_t, os_t, ok_t, ow_t = tables
     stream = _stream_ptr(dev)
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    def measure(B: int, steps: int, warmup: int, seed: int):
+        """Device-resident leg at B trajectories on this rank: returns (ms_per_step max over ranks, fwd ms, bwd ms, plan)."""
+        y0_host = synth_y0(B, 1, 8, seed=seed).pin_memory()
+        y0 = y0_host.to(dev, non_blocking=True)
+        # fixed cotangent: d(loss)/d(latent) of the synthetic loss
+        y0g = y0.clone().requires_grad_(True)
+        mod.clear_tracking()
+        y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=t[1] - t[0]))
+        loss = _loss(y, y_ili, mod)
+        g_out = torch.autograd.grad(loss, y, retain_graph=False)[0].contiguous()
+        g_side = torch.tensor([1e-8, -1e-8, 1e-9, 1e-9, 1e-9], dtype=torch.float32, device=dev)
+        del y, loss, y0g
+        desc = info.desc(B)
+        plan = _lib.UdePlan()
+        _lib.check(L.ude_plan(C.byref(desc), 0, n_steps, C.byref(plan)), "ude_plan")
+        theta = info.theta().detach().contiguous()
+        y_out = torch.empty((n_out, B, 1, 8), dtype=torch.float32, device=dev)
+        side = torch.empty(8, dtype=torch.float64, device=dev)
+        ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+        tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev)
+        g_y0 = torch.empty_like(y0)
+        g_theta = torch.empty_like(theta)
+        n_ev = steps
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_ev)]
 
-    def step_resident(timed: bool):
-        """One pass with every input resident in HBM: fwd launch, bwd launch, grad all-reduce."""
-        if timed:
-            ev[0].record()
-        st = L.ude_rk4_forward(C.byref(desc), _ptr(theta), _ptr(y0), n_steps, _ptr(dt_t), n_out, _ptr(os_t),
-                               _ptr(ok_t), _ptr(ow_t), _ptr(y_out), _ptr(tape), _ptr(side), _ptr(ws),
-                               int(plan.workspace_bytes), stream)
-        _lib.check(st, "fwd")
-        if timed:
-            ev[1].record()
-        st = L.ude_rk4_backward(C.byref(desc), _ptr(theta), _ptr(y0), n_steps, _ptr(dt_t), n_out, _ptr(os_t),
-                                _ptr(ok_t), _ptr(ow_t), _ptr(tape), _ptr(g_out), _ptr(g_side), _ptr(g_y0),
-                                _ptr(g_theta), _ptr(ws), int(plan.workspace_bytes), stream)
-        _lib.check(st, "bwd")
-        if timed:
-            ev[2].record()
+        def step(ev=None):
+            if ev:
+                ev[0].record()
+            st = L.ude_rk4_forward(C.byref(desc), _ptr(theta), _ptr(y0), n_steps, _ptr(dt_t), n_out, _ptr(os_t),
+                                   _ptr(ok_t), _ptr(ow_t), _ptr(y_out), _ptr(tape), _ptr(side), _ptr(ws),
+                                   int(plan.workspace_bytes), stream)
+            _lib.check(st, "fwd")
+            if ev:
+                ev[1].record()
+            h = dist.all_reduce(side, async_op=True) if world > 1 else None   # the loss needs the global side sums before backward
+            st = L.ude_rk4_backward(C.byref(desc), _ptr(theta), _ptr(y0), n_steps, _ptr(dt_t), n_out, _ptr(os_t),
+                                    _ptr(ok_t), _ptr(ow_t), _ptr(tape), _ptr(g_out), _ptr(g_side), _ptr(g_y0),
+                                    _ptr(g_theta), _ptr(ws), int(plan.workspace_bytes), stream)
+            _lib.check(st, "bwd")
+            if ev:
+                ev[2].record()
+            if world > 1:
+                dist.all_reduce(g_theta)
+                h.wait()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(evs[i])
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+        bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+        tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(g_theta)
-            dist.all_reduce(side)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        return float(tm.item()) / steps, fwd_ms, bwd_ms, plan, desc, y0_host
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident(False)
-    barrier()
+    warmup = max(args.warmup, 3)
+    B_rank = args.batch if args.batch else B_TOTAL // world
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fwd_ms, bwd_ms = [], []
-    e0.record()
-    for _ in range(args.steps):
-        step_resident(True)
-        # per-kernel durations are read after the loop (events stay valid until re-recorded), so
-        # only the last step's are kept when steps > 1; a short sync-free loop keeps the region tight.
-    e1.record()
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    fwd_ms = ev[0].elapsed_time(ev[1])
-    bwd_ms = ev[1].elapsed_time(ev[2])
+    ms_per_step, fwd_ms, bwd_ms, plan, desc, y0_host = measure(B_rank, args.steps, warmup, 100 + rank)
     clocks = sampler.stop()
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
-    ms_per_step = total_ms / args.steps
-    value = world * B * n_steps / (ms_per_step * 1e-3)
+    value = world * B_rank * n_steps / (ms_per_step * 1e-3)
+    B = B_rank
+    macs = int(L.ude_macs_per_eval(C.byref(desc)))
+    fl = flops_per_traj_step(macs)
+
+    weak = None
+    if world > 1 and not args.batch:
+        w_ms, _, _, _, _, _ = measure(B_TOTAL, min(args.steps, 3), 3, 200 + rank)
+        weak = {"trajectories_per_gpu": B_TOTAL, "ms_per_step": w_ms, "value": world * B_TOTAL * n_steps / (w_ms * 1e-3),
+                "unit": UNIT, "scaling": "weak"}
+    check = dist_check(mod, dev, world, rank) if world > 1 else None
 
     # ---- end-to-end leg: public API, host inputs, H2D + loss + backward + D2H every step
     def step_e2e():
         y0d = y0_host.to(dev, non_blocking=True).requires_grad_(True)
         mod.clear_tracking()
         mod.zero_grad(set_to_none=True)
-        yy = ude_b200.odeint(mod, y0d, t, method="rk4", options=dict(step_size=t[1] - t[0]))
+        opts = dict(step_size=t[1] - t[0])
+        if world > 1:
+            opts["process_group"] = True
+        yy = ude_b200.odeint(mod, y0d, t, method="rk4", options=opts)
         ls = _loss(yy, y_ili, mod)
         ls.backward()
         flat = torch.cat([p.grad.reshape(-1) for p in mod.parameters()])
@@ -327,6 +597,11 @@ def run_ours(args):
             dist.all_reduce(flat)
         out = torch.cat([ls.detach().reshape(1), flat]).to("cpu")
         return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
 
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
@@ -343,9 +618,9 @@ def run_ours(args):
     e2e_value = world * B * n_steps / e2e_sec
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (the adjoint): fp32 FMA pipe, measured peak
         peak = C.c_double(0.0)
         _lib.check(L.ude_measure_ffma_tflops(C.byref(peak), stream), "ffma peak")
+        ffma_peak = float(peak.value)
         ach_bwd = B * n_steps * fl["bwd"] / (bwd_ms * 1e-3) / 1e12
         ach_fwd = B * n_steps * fl["fwd"] / (fwd_ms * 1e-3) / 1e12
         bytes_ts = 3 * 4 * 1 * 8          # fwd state store + bwd state load + bwd cotangent load
@@ -355,20 +630,9 @@ def run_ours(args):
                 peaks = json.load(f)
         except Exception:
             pass
+        t_peak = peaks.get("bf16_tflops") or 1590.0
+        t_peak_src = "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst), of measured" if peaks.get("bf16_tflops") else "fallback 1590 (B200_PROFILING.md), of fallback"
         path = int(L.ude_rk4_path(C.byref(desc)))
-        kname = "rk4_bwd_tc_kernel<1,8> (tcgen05)" if path == 1 else "rk4_bwd_kernel (FFMA)"
-        tensor = None
-        if path == 1:
-            tm = tensor_macs_per_tile_eval(spec)
-            evals = (B + 127) // 128 * n_steps * 4
-            t_peak = peaks.get("bf16_tflops")
-            t_bwd = 2.0 * tm["bwd"] * evals / (bwd_ms * 1e-3) / 1e12
-            t_fwd = 2.0 * tm["fwd"] * evals / (fwd_ms * 1e-3) / 1e12
-            tensor = {"note": "bf16 flops actually issued to the tensor pipe (6 bf16 products emulate one fp32 product; "
-                              "M=128, N<=64 instructions sit on the 50-cycle issue floor measured by tools/umma_probe.cu)",
-                      "bwd_issued_tflops": t_bwd, "fwd_issued_tflops": t_fwd, "peak": t_peak,
-                      "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst), of measured",
-                      "bwd_frac": t_bwd / t_peak if t_peak else None, "fwd_frac": t_fwd / t_peak if t_peak else None}
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -377,42 +641,77 @@ def run_ours(args):
                 traffic = tr.get("bwd_dram_bytes_per_launch")
         except Exception:
             pass
+        if path == 1:
+            # Mixed bound of the tcgen05 adjoint: the time the two pipes it actually uses would need at their
+            # measured peaks -- bf16 flops ISSUED to the tensor pipe / cuBLAS bf16 peak, and the fp32 FMA-pipe remainder (heads,
+            # first-layer products) / measured FFMA peak -- the larger of the two is the bound; frac = bound / measured time.
+            tm_ = tensor_macs_per_tile_eval(spec)
+            fm_ = fma_pipe_macs_per_traj_eval(spec)
+            evals = (B + 127) // 128 * n_steps * 4
+            t_tensor = {k: 2.0 * tm_[k] * evals / (t_peak * 1e12) * 1e3 for k in ("fwd", "bwd")}       # ms
+            t_fma = {k: 2.0 * fm_[k] * B * n_steps * 4 / (ffma_peak * 1e12) * 1e3 for k in ("fwd", "bwd")}
+            bound_ms = max(t_tensor["bwd"], t_fma["bwd"])
+            issued = 2.0 * tm_["bwd"] * evals / (bwd_ms * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor", "kernel": "rk4_bwd_tc_kernel<1,8> (tcgen05, fp32 through 3-way bf16 splits)",
+                "achieved": issued, "peak": t_peak, "unit": "TFLOP/s", "frac": bound_ms / bwd_ms, "peak_source": t_peak_src,
+                "note": "achieved = bf16 flops issued to the tensor pipe by the adjoint (6 bf16 products per fp32 product in the layer and "
+                        "delta chains, 3 in the weight gradients) / its CUDA-event time; frac = mixed bound max(tensor-issued / bf16 peak, "
+                        "FMA-pipe remainder / FFMA peak) / measured time",
+                "mixed_bound_ms": {"tensor": t_tensor["bwd"], "fma": t_fma["bwd"], "measured": bwd_ms},
+                "fwd_kernel": {"ms": fwd_ms, "frac": max(t_tensor["fwd"], t_fma["fwd"]) / fwd_ms,
+                               "issued_tflops": 2.0 * tm_["fwd"] * evals / (fwd_ms * 1e-3) / 1e12},
+            }
+        else:
+            roofline = {"bound": "fp32-fma", "kernel": "rk4_bwd_kernel (FFMA engine)", "achieved": ach_bwd, "peak": ffma_peak,
+                        "unit": "TFLOP/s", "frac": ach_bwd / ffma_peak, "peak_source": "measured live: ude_measure_ffma_tflops",
+                        "fwd_kernel": {"ms": fwd_ms, "frac": ach_fwd / ffma_peak}}
+        roofline.update({
+            "traffic": traffic, "algorithmic_bytes_per_launch": B * n_steps * (48 + 32) + B * 64, "bwd_ms": bwd_ms,
+            # SURVEY 8d's definition (algorithmic fp32 flops against the fp32 FMA pipe), kept as the secondary figure
+            "ffma_algorithmic": {"peak_tflops": ffma_peak, "peak_source": "measured live: ude_measure_ffma_tflops (register-resident FFMA chains)",
+                                 "bwd_achieved_tflops": ach_bwd, "bwd_frac": ach_bwd / ffma_peak, "fwd_achieved_tflops": ach_fwd,
+                                 "fwd_frac": ach_fwd / ffma_peak,
+                                 "whole_step_frac": (B * n_steps * fl["total"] / ((fwd_ms + bwd_ms) * 1e-3) / 1e12) / ffma_peak},
+            "hbm_gbs_algorithmic": B * n_steps * bytes_ts / (ms_per_step * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs")})
         cpu = None
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            sec = cpu_reference_step(CPU_SAMPLE_B, cores, 3)
-            cpu = {"value": CPU_SAMPLE_B * N_STEPS_GRID / sec, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"B={CPU_SAMPLE_B} x {N_STEPS_GRID} steps fwd+autograd backward, median of 3, "
-                             f"oracle port of lib/models.py + torchdiffeq rk4, {cores} torch threads"}
+        secondary = None
+        if world == 1:
+            if not args.no_cpu_baseline:
+                cpu = cpu_baseline_record(os.cpu_count() or 1)
+            if not args.no_secondary:
+                try:
+                    secondary = secondary_configs(dev, ffma_peak, not args.no_cpu_baseline)
+                except Exception as e:        # the headline line must not die with a secondary config
+                    secondary = {"error": f"{type(e).__name__}: {e}"}
+        tdq = "absent"
+        try:
+            import torchdiffeq
+            tdq = torchdiffeq.__version__
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[3]: synthetic ensemble, FaFp R=1 L=8 net [64,64,32] aug [64,64], "
-                                   "RK4(3/8) t=[0..8] h=1 (8 steps), fused forward + discrete-adjoint backward"
-                                   + (", NCCL all-reduce of dtheta" if world > 1 else ""),
-                       "trajectories_per_gpu": B, "grid_steps": n_steps, "parallelism": f"trajectory-shard x{world}",
-                       "l2": "inputs larger than L2 (y0 32 MiB + cotangent 288 MiB + tape 384 MiB per pass)",
-                       "tile_traj": int(plan.tile_traj), "ctas": int(plan.n_ctas)},
-            "roofline": {"bound": "fp32-fma", "kernel": kname, "achieved": ach_bwd, "peak": float(peak.value),
-                         "unit": "TFLOP/s", "frac": ach_bwd / float(peak.value) if peak.value else None,
-                         "peak_source": "measured live: ude_measure_ffma_tflops (register-resident FFMA chains)",
-                         "traffic": traffic,
-                         "algorithmic_bytes_per_launch": B * n_steps * (48 + 32) + B * 64,
-                         "tensor_pipe": tensor,
-                         "fwd_kernel": {"achieved": ach_fwd, "frac": ach_fwd / float(peak.value) if peak.value else None,
-                                        "ms": fwd_ms},
-                         "bwd_ms": bwd_ms,
-                         "whole_step_frac": (B * n_steps * fl["total"] / (ms_per_step * 1e-3) / 1e12) / float(peak.value)
-                         if peak.value else None,
-                         "hbm_gbs_algorithmic": B * n_steps * bytes_ts / (ms_per_step * 1e-3) / 1e9,
-                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if not args.batch else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + (", side sums + dtheta all-reduced over NCCL" if world > 1 else ""),
+                       "trajectories_total": world * B, "trajectories_per_gpu": B, "grid_steps": n_steps,
+                       "parallelism": f"trajectory-shard x{world}",
+                       "l2": f"inputs larger than L2 (per pass and GPU: y0 {B * 32 >> 20} MiB + cotangent {B * 288 >> 20} MiB + tape {B * 384 >> 20} MiB)",
+                       "tile_traj": int(plan.tile_traj), "ctas": int(plan.n_ctas), "torchdiffeq": tdq},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y0_host.numel() * 4),
                     "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_sec * 1e3},
             "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }
+        if weak is not None:
+            line["weak_scaling"] = weak
+        if check is not None:
+            line["dist_check"] = check
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -424,8 +723,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="trajectories per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="trajectories PER GPU (default: 2**20 in total, sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
