@@ -15,10 +15,17 @@ importable alias of this package.
 from ._lib import UdeError, build, lib  # noqa: F401
 from .funcs import Fa, FaFp, Fp, FuncInfo, UnsupportedFunc, describe_func  # noqa: F401
 from . import dist  # noqa: F401
-from .odeint import odeint, odeint_groups, posterior_rows, rk4_grid_tables  # noqa: F401
+from .odeint import flatten_parameters, odeint, odeint_groups, posterior_rows, rk4_grid_tables  # noqa: F401
 
-odeint_adjoint = odeint   # torchdiffeq exports both; the fused backward IS the discrete adjoint
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """torchdiffeq exports both entry points.  The fused backward IS the discrete adjoint of the forward solve, so the
+    ``adjoint_*`` knobs of the continuous-adjoint solver have nothing to configure here: accepted and ignored."""
+    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options, event_fn=event_fn)
+
 
 __all__ = ["odeint", "odeint_groups", "odeint_adjoint", "Fp", "Fa", "FaFp", "describe_func", "build", "lib", "UdeError",
-           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows"]
+           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows", "flatten_parameters"]
 __version__ = "0.1.0"

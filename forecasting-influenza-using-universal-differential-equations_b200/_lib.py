@@ -19,6 +19,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 UDE_MAX_LAYERS = 8
 UDE_OK = 0
 UDE_ERR_CAPACITY = -7
+FLAG_WEIGHTS_PACKED = 16
 KIND = {"Fp": 0, "Fa": 1, "FaFp": 2}
 METHOD = {"rk4": 0, "dopri5": 1}
 
@@ -49,7 +50,7 @@ class UdePlan(C.Structure):
         ("smem_bytes_fwd", C.c_int32),
         ("smem_bytes_bwd", C.c_int32),
         ("weights_in_smem", C.c_int32),
-        ("reserved", C.c_int32),
+        ("path", C.c_int32),
     ]
 
 

@@ -307,6 +307,55 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
                 void* workspace, int64_t workspace_bytes, cudaStream_t s);
 }  // namespace ude
 
+namespace ude {
+// ---------------------------------------------------------------------------------
+// Weight-set groups in ONE launch (Rk4FwdArgs::n_groups): possible when the plans keep the packed weights (and, in the
+// adjoint, the dtheta accumulators) in shared memory -- the small models of the hyper-parameter sweeps
+// (tuning/tune_node.py:169-171).  Anything else falls back to G single-set launch sets (for_each_group).
+// ---------------------------------------------------------------------------------
+// two resident CTAs per SM (the register-capped kernel builds): dynamic + static shared memory of both must fit
+static bool two_ctas_fit(const ModelP& P) { return 2 * (P.smem_floats * 4 + 8 * 1024) <= 227 * 1024; }
+struct GroupedPlan {
+    ModelP Pf, Pb;
+    bool two_f, two_b;
+    long long tiles_f, tiles_b;      // tiles over all groups
+    int ctas_f, ctas_b;
+    float* wpacked;                  // [G][n_packed]
+    double* side_partial;            // [tiles_f][8]
+    float* slabs;                    // [tiles_b][n_packed]
+    long long bytes;
+    long long tape_group_floats;
+};
+static bool grouped_single_launch(const UdeDesc* desc, int n_steps, void* base, GroupedPlan& gp) {
+    const int G = desc->n_groups;
+    if (G <= 1 || (desc->flags & UDE_FLAG_FORCE_TENSOR)) return false;
+    UdeDesc d = *desc;
+    d.n_groups = 1;                  // tile size from the TOTAL batch: all groups share one persistent grid
+    if (choose_plan(&d, gp.Pf, F_NSTATE, 0, false) != UDE_OK || choose_plan(&d, gp.Pb, B_NSTATE, 0, true) != UDE_OK) return false;
+    if (!gp.Pf.w_in_smem || gp.Pf.cold_global || !gp.Pb.w_in_smem || !gp.Pb.g_in_smem || gp.Pb.cold_global) return false;
+    const long long Bg = desc->batch / G;
+    gp.tiles_f = (Bg + gp.Pf.TB - 1) / gp.Pf.TB * G;
+    gp.tiles_b = (Bg + gp.Pb.TB - 1) / gp.Pb.TB * G;
+    const DeviceInfo& di = device_info();
+    const int n_sm = di.ok ? di.n_sm : 148;
+    gp.two_f = two_ctas_fit(gp.Pf);
+    gp.two_b = two_ctas_fit(gp.Pb);
+    const long long cap_f = (long long)n_sm * (gp.two_f ? 2 : 1), cap_b = (long long)n_sm * (gp.two_b ? 2 : 1);
+    gp.ctas_f = (int)(gp.tiles_f < cap_f ? gp.tiles_f : cap_f);
+    gp.ctas_b = (int)(gp.tiles_b < cap_b ? gp.tiles_b : cap_b);
+    long long off = 0;
+    gp.wpacked = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)G * gp.Pf.n_packed * 4, 256);
+    gp.side_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + gp.tiles_f * 8 * 8, 256);
+    gp.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + gp.tiles_b * gp.Pb.n_packed * 4, 256);
+    gp.bytes = off;
+    gp.tape_group_floats = align_up((long long)n_steps * 4 * gp.Pf.Dn * Bg * 4, 256) / 4;
+    return true;
+}
+}  // namespace ude
+
 using namespace ude;
 
 // =====================================================================================
@@ -363,6 +412,16 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
         if ((st = ude_plan(&d1, method, n_steps, plan)) != UDE_OK) return st;
         plan->workspace_bytes = align_up(plan->workspace_bytes, 256) * desc->n_groups;
         plan->tape_bytes = align_up(plan->tape_bytes, 256) * desc->n_groups;
+        GroupedPlan gp;
+        if (grouped_single_launch(desc, n_steps, nullptr, gp)) {      // one launch for all groups (same tape layout)
+            if (gp.bytes > plan->workspace_bytes) plan->workspace_bytes = gp.bytes;
+            plan->tile_traj = gp.Pb.TB;
+            plan->n_ctas = gp.ctas_f > gp.ctas_b ? gp.ctas_f : gp.ctas_b;
+            plan->smem_bytes_fwd = gp.Pf.smem_floats * 4;
+            plan->smem_bytes_bwd = gp.Pb.smem_floats * 4;
+            plan->weights_in_smem = 1;
+            plan->path = 2;           // grouped single launch
+        }
         return UDE_OK;
     }
     ModelP Pf, Pb;      // pure host arithmetic: works without a GPU (148 SMs assumed then)
@@ -395,7 +454,7 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
         plan->smem_bytes_fwd = Mt.smem_bytes_fwd;
         plan->smem_bytes_bwd = Mt.smem_bytes_bwd;
         plan->weights_in_smem = 1;
-        plan->reserved = 1;       // tensor path
+        plan->path = 1;           // tensor path
     }
     return UDE_OK;
 }
@@ -496,9 +555,11 @@ struct GroupFan {
     cudaEvent_t fork, join[kFan];
 };
 static int group_fan(GroupFan** out) {
-    static thread_local GroupFan fan;
+    static thread_local GroupFan fans[kMaxDevices];      // one pool per device and thread, created once, never re-created
     int dev = 0;
     UDE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return UDE_ERR_INVALID;
+    GroupFan& fan = fans[dev];
     if (fan.dev != dev) {
         for (int i = 0; i < kFan; ++i) {
             UDE_CUDA(cudaStreamCreateWithFlags(&fan.s[i], cudaStreamNonBlocking));
@@ -545,6 +606,37 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     if (desc->n_groups != 1) {
+        GroupedPlan gp;
+        if (grouped_single_launch(desc, n_steps, workspace, gp)) {
+            if (gp.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+            cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+            const ModelP& P = gp.Pf;
+            pack_theta_kernel<<<dim3(P.n_rate + P.n_aug + 3, desc->n_groups), 256, 0, s>>>(P, theta, gp.wpacked);
+            UDE_CUDA(cudaGetLastError());
+            Rk4FwdArgs a;
+            a.wpacked = gp.wpacked;
+            a.y0 = y0;
+            a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+            a.y_out = y_out;
+            a.tape = tape;
+            a.side_partial = gp.side_partial;
+            a.cold = nullptr;
+            a.B = desc->batch / desc->n_groups;
+            a.n_groups = desc->n_groups;
+            a.tape_group_floats = gp.tape_group_floats;
+            const int smem = P.smem_floats * 4;
+            if (gp.two_f) {
+                if ((st = set_smem(rk4_fwd_kernel<true, false, 2>, smem)) != UDE_OK) return st;
+                rk4_fwd_kernel<true, false, 2><<<gp.ctas_f, kThreads, smem, s>>>(P, a);
+            } else {
+                if ((st = set_smem(rk4_fwd_kernel<true, false>, smem)) != UDE_OK) return st;
+                rk4_fwd_kernel<true, false><<<gp.ctas_f, kThreads, smem, s>>>(P, a);
+            }
+            UDE_CUDA(cudaGetLastError());
+            reduce_side_kernel<<<desc->n_groups, 32, 0, s>>>(gp.side_partial, (int)(gp.tiles_f / desc->n_groups), side);
+            UDE_CUDA(cudaGetLastError());
+            return UDE_OK;
+        }
         const long long n_theta = ude_theta_size(desc), row = (long long)desc->n_regions * desc->latent_dim;
         return for_each_group(desc, n_steps, reinterpret_cast<cudaStream_t>(stream),
                               [&](const UdeDesc& d1, const UdePlan& p1, int g, long long ws_g, long long tape_g, cudaStream_t sg) {
@@ -580,6 +672,8 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     a.side_partial = w.side_partial;
     a.cold = w.cold;
     a.B = desc->batch;
+    a.n_groups = 1;
+    a.tape_group_floats = 0;
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_FWD(W, C)                                                              \
     do {                                                                                  \
@@ -607,6 +701,42 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     if (desc->n_groups != 1) {
+        GroupedPlan gp;
+        if (grouped_single_launch(desc, n_steps, workspace, gp)) {
+            if (gp.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+            cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+            const ModelP& P = gp.Pb;
+            if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED)) {
+                pack_theta_kernel<<<dim3(P.n_rate + P.n_aug + 3, desc->n_groups), 256, 0, s>>>(P, theta, gp.wpacked);
+                UDE_CUDA(cudaGetLastError());
+            }
+            Rk4BwdArgs a;
+            a.wpacked = gp.wpacked;
+            a.y0 = y0;
+            a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+            a.tape = tape;
+            a.g_out = g_out;
+            a.g_side = g_side;
+            a.g_y0 = g_y0;
+            a.slabs = gp.slabs;
+            a.cold = nullptr;
+            a.B = desc->batch / desc->n_groups;
+            a.n_groups = desc->n_groups;
+            a.tape_group_floats = gp.tape_group_floats;
+            const int smem = P.smem_floats * 4;
+            if (gp.two_b) {
+                if ((st = set_smem(rk4_bwd_kernel<true, true, false, 2>, smem)) != UDE_OK) return st;
+                rk4_bwd_kernel<true, true, false, 2><<<gp.ctas_b, kThreads, smem, s>>>(P, a);
+            } else {
+                if ((st = set_smem(rk4_bwd_kernel<true, true, false>, smem)) != UDE_OK) return st;
+                rk4_bwd_kernel<true, true, false><<<gp.ctas_b, kThreads, smem, s>>>(P, a);
+            }
+            UDE_CUDA(cudaGetLastError());
+            reduce_dtheta_kernel<<<dim3((P.n_theta + 255) / 256, desc->n_groups), 256, 0, s>>>(
+                P, gp.slabs, (int)(gp.tiles_b / desc->n_groups), g_theta);
+            UDE_CUDA(cudaGetLastError());
+            return UDE_OK;
+        }
         const long long n_theta = ude_theta_size(desc), row = (long long)desc->n_regions * desc->latent_dim;
         return for_each_group(desc, n_steps, reinterpret_cast<cudaStream_t>(stream),
                               [&](const UdeDesc& d1, const UdePlan& p1, int g, long long ws_g, long long tape_g, cudaStream_t sg) {
@@ -633,7 +763,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     Workspace w = carve_workspace(workspace, P, n_ctas, P.cold_global ? P.cold_floats : 0);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
+    if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED) && (st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
     Rk4BwdArgs a;
     a.wpacked = w.wpacked;
     a.y0 = y0;
@@ -645,6 +775,8 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     a.slabs = w.slabs;
     a.cold = w.cold;
     a.B = desc->batch;
+    a.n_groups = 1;
+    a.tape_group_floats = 0;
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_BWD(W, G, C)                                                           \
     do {                                                                                  \

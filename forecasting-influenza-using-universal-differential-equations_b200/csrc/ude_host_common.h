@@ -34,20 +34,25 @@ struct DeviceInfo {
     int cc_major = 0;
     int max_smem_optin = 0;
 };
+// Properties of the CURRENT device, cached per device ordinal (a process may drive several GPUs).
+constexpr int kMaxDevices = 64;
 inline DeviceInfo& device_info() {
-    static DeviceInfo info;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return;
+    static DeviceInfo info[kMaxDevices + 1];
+    static std::once_flag once[kMaxDevices + 1];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        (void)cudaGetLastError();
+        return info[kMaxDevices];          // stays !ok: no device visible
+    }
+    std::call_once(once[dev], [dev] {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
-        info.n_sm = prop.multiProcessorCount;
-        info.cc_major = prop.major;
-        info.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-        info.ok = 1;
+        info[dev].n_sm = prop.multiProcessorCount;
+        info[dev].cc_major = prop.major;
+        info[dev].max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+        info[dev].ok = 1;
     });
-    return info;
+    return info[dev];
 }
 
 template <typename K>

@@ -18,7 +18,13 @@ struct Rk4FwdArgs {
     float* tape;            // [n_steps,4,Dn,B] or null
     double* side_partial;   // [gridDim.x, 8]
     float* cold;            // [gridDim.x, cold_floats] when the plan spills the state rows
-    long long B;
+    long long B;            // trajectories of ONE weight set
+    // Weight-set groups (UdeDesc::n_groups = G > 1, BASELINE configs[4]): ONE launch walks the tiles of all G
+    // group-major sub-problems; tile -> group = tile / tiles_per_group; the packed weights are re-staged when a CTA
+    // moves on to another group; side partials are kept per TILE and summed per group in tile order, which is the
+    // summation order of G single-set launches (bit-identical results).
+    int n_groups;
+    long long tape_group_floats;    // distance between the tapes of two groups
 };
 
 struct Rk4BwdArgs {
@@ -29,9 +35,11 @@ struct Rk4BwdArgs {
     const float* g_out;     // [n_out,B,R,L]
     const float* g_side;    // [5] or null
     float* g_y0;            // [B,R,L]
-    float* slabs;           // [gridDim.x, n_packed] per-CTA dtheta accumulators
+    float* slabs;           // [gridDim.x, n_packed] per-CTA dtheta accumulators ([n_tiles, n_packed] per TILE with groups)
     float* cold;
     long long B;
+    int n_groups;           // see Rk4FwdArgs
+    long long tape_group_floats;
 };
 
 // ---- state buffer indices ---------------------------------------------------------
@@ -157,8 +165,11 @@ __device__ __forceinline__ void add_const_cotangent(float* __restrict__ dst, con
 // ===================================================================================
 // forward
 // ===================================================================================
-template <bool SMEM_W, bool COLD>
-__global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_constant__ ModelP Pg, const Rk4FwdArgs a) {
+// MINB = 2: register-capped build (<= 128 per thread) for the SMALL models (hyper-parameter sweeps, Fp with 32-wide nets):
+// their tiles are a chain of short phases separated by CTA barriers, so two resident CTAs per SM hide each other's
+// barrier latency.  Same code, same results.
+template <bool SMEM_W, bool COLD, int MINB = 1>
+__global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_constant__ ModelP Pg, const Rk4FwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
     __shared__ __align__(8) uint64_t wbar;
@@ -188,16 +199,32 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
     side.clear();
     const double n_evals = 4.0 * a.g.n_steps;      // RHS evaluations per trajectory
     const long long B = a.B;
-    const long long n_tiles = (B + TB - 1) / TB;
+    const long long tiles_per_group = (B + TB - 1) / TB;
+    const long long n_tiles = tiles_per_group * a.n_groups;
     const long long tape_stage = (long long)Dn * B;           // floats per (step, stage)
+    const bool grouped = a.n_groups > 1;
+    long long g_cur = 0;
+    const long long out_group = (long long)a.g.n_out * B * P.R * L, y0_group = B * P.R * L;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long b0 = tile * TB;
+        const long long grp = grouped ? tile / tiles_per_group : 0;
+        const long long b0 = (tile - grp * tiles_per_group) * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
-        __syncthreads();                                       // previous tile done with X and the ACT rows
-        load_y0_tile(P, smem, a.y0, b0, nvalid, true, P.hoist != 0);
+        // this group's views of the caller's arrays (group-major layouts, include/ude_b200.h)
+        const float* const a_y0 = a.y0 + grp * y0_group;
+        float* const a_y_out = a.y_out + grp * out_group;
+        float* const a_tape = a.tape ? a.tape + grp * a.tape_group_floats : nullptr;
+        const float* const a_wpacked = a.wpacked + grp * P.n_packed;
+        __syncthreads();                                       // previous tile done with X, the ACT rows and the weights
+        if (SMEM_W && grp != g_cur) {
+            stage_weights_tma(smem + P.off_W, a_wpacked, P.n_packed_hot, &wbar, wphase);
+            g_cur = grp;
+        } else if (!SMEM_W) {
+            Wp = a_wpacked;
+        }
+        load_y0_tile(P, smem, a_y0, b0, nvalid, true, P.hoist != 0);
         __syncthreads();
-        hoist_c0(P, a.wpacked, smem, warp, lane);              // constant part of both first layers, once per tile
+        hoist_c0(P, a_wpacked, smem, warp, lane);              // constant part of both first layers, once per tile
         // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
             SY[(3 * r + 2) * TBP + b] = v[2];
             if (b < nvalid) {
                 const long long row = ((b0 + b) * P.R + r) * (long long)L;
-                store_out_row(P, a.y0 + row, a.y_out + row, v);
+                store_out_row(P, a_y0 + row, a_y_out + row, v);
             }
         }
         // (each thread only re-reads rows it wrote itself below, no sync needed here)
@@ -226,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
                     float f[3];
                     rhs_tail(P, smem, r, b, valid, side, f);
                     float* X = smem + P.off_X + (3 * r) * TBP + b;
-                    float* tp = a.tape ? a.tape + ((long long)(n * 4 + stage) * tape_stage + (long long)(3 * r) * B + b0 + b) : nullptr;
+                    float* tp = a_tape ? a_tape + ((long long)(n * 4 + stage) * tape_stage + (long long)(3 * r) * B + b0 + b) : nullptr;
                     float xn[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -264,8 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
                                         v[c] = kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(xn[c], y)));
                                     }
                                 }
-                                store_out_row(P, a.y0 + ((b0 + b) * P.R + r) * (long long)L,
-                                              a.y_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L, v);
+                                store_out_row(P, a_y0 + ((b0 + b) * P.R + r) * (long long)L,
+                                              a_y_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L, v);
                             }
                             ++jj;
                         }
@@ -288,15 +315,19 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_fwd_kernel(const __grid_const
             }
             j = j_next;
         }
+        if (grouped) {                                         // side sums per TILE (summed per group afterwards)
+            side_block_reduce(side, n_evals, red, a.side_partial + tile * 8);
+            side.clear();
+        }
     }
-    side_block_reduce(side, n_evals, red, a.side_partial + (long long)blockIdx.x * 8);
+    if (!grouped) side_block_reduce(side, n_evals, red, a.side_partial + (long long)blockIdx.x * 8);
 }
 
 // ===================================================================================
 // backward (discrete adjoint)
 // ===================================================================================
-template <bool SMEM_W, bool SMEM_G, bool COLD>
-__global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_constant__ ModelP Pg, const Rk4BwdArgs a) {
+template <bool SMEM_W, bool SMEM_G, bool COLD, int MINB = 1>
+__global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_constant__ ModelP Pg, const Rk4BwdArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
     __shared__ __align__(8) uint64_t wbar;
@@ -326,14 +357,17 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     }
     // dtheta accumulators: the hot part (every evaluation) in shared memory when it fits, else in the CTA's global slab;
     // the constant blocks of the first layers (once per tile) always in the global slab
+    const bool grouped = a.n_groups > 1;      // per-TILE slabs, zeroed and flushed inside the tile loop
     float* Gslab = a.slabs + (long long)blockIdx.x * P.n_packed;
     float* G = SMEM_G ? smem + P.off_G : Gslab;
-    for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) G[i] = 0.f;
-    for (int i = P.n_packed_hot + threadIdx.x; i < P.n_packed; i += kThreads) Gslab[i] = 0.f;
+    if (!grouped) {
+        for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) G[i] = 0.f;
+        for (int i = P.n_packed_hot + threadIdx.x; i < P.n_packed; i += kThreads) Gslab[i] = 0.f;
+    }
     for (int i = threadIdx.x; i < (P.Dn_p - P.Dn) * TBP; i += kThreads) smem[P.off_X + P.Dn * TBP + i] = 0.f;
 
     float gs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if (a.g_side) {
+    if (a.g_side && !grouped) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
@@ -346,15 +380,40 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
     float* DL = smem + P.off_DL;
 
     const long long B = a.B;
-    const long long n_tiles = (B + TB - 1) / TB;
+    const long long tiles_per_group = (B + TB - 1) / TB;
+    const long long n_tiles = tiles_per_group * a.n_groups;
     const long long tape_stage = (long long)Dn * B;
     const int n_steps = a.g.n_steps;
+    long long g_cur = 0;
+    const long long out_group = (long long)a.g.n_out * B * P.R * L, y0_group = B * P.R * L;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long b0 = tile * TB;
+        const long long grp = grouped ? tile / tiles_per_group : 0;
+        const long long b0 = (tile - grp * tiles_per_group) * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
+        const float* const a_y0 = a.y0 + grp * y0_group;
+        float* const a_g_y0 = a.g_y0 + grp * y0_group;
+        const float* const a_g_out = a.g_out + grp * out_group;
+        const float* const a_tape = a.tape + grp * a.tape_group_floats;
+        const float* const a_wpacked = a.wpacked + grp * P.n_packed;
         __syncthreads();
-        load_y0_tile(P, smem, a.y0, b0, nvalid, false, P.hoist != 0);     // constants only; the dynamic rows come from the tape
+        if (SMEM_W && grp != g_cur) {
+            stage_weights_tma(smem + P.off_W, a_wpacked, P.n_packed_hot, &wbar, wphase);
+            g_cur = grp;
+        } else if (!SMEM_W) {
+            Wp = a_wpacked;
+        }
+        if (grouped) {
+            Gslab = a.slabs + tile * P.n_packed;
+            if (!SMEM_G) G = Gslab;
+            for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) G[i] = 0.f;
+            for (int i = P.n_packed_hot + threadIdx.x; i < P.n_packed; i += kThreads) Gslab[i] = 0.f;
+            if (a.g_side) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + grp * 5 + i);
+            }
+        }
+        load_y0_tile(P, smem, a_y0, b0, nvalid, false, P.hoist != 0);     // constants only; the dynamic rows come from the tape
         for (int i = threadIdx.x; i < SS; i += kThreads) LAM[i] = 0.f;
         for (int i = threadIdx.x; i < P.Dn_p * TBP; i += kThreads) GX[i] = 0.f;
         for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
@@ -364,11 +423,11 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
                 const long long row = ((b0 + b) * P.R + r) * (long long)L;
-                for (int l = 0; l < L; ++l) a.g_y0[row + l] = __ldg(a.g_out + row + l);
+                for (int l = 0; l < L; ++l) a_g_y0[row + l] = __ldg(a_g_out + row + l);
             }
         }
         __syncthreads();
-        hoist_c0(P, a.wpacked, smem, warp, lane);
+        hoist_c0(P, a_wpacked, smem, warp, lane);
 
         int j = a.g.n_out - 1;
         for (int n = n_steps - 1; n >= 0; --n) {
@@ -390,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                     for (int jj = j; jj > j_next; --jj) {
                         const int kind = __ldg(a.g.out_kind + jj);
                         const float w = __ldg(a.g.out_w + jj);
-                        const float* gp = a.g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
+                        const float* gp = a_g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
 #pragma unroll
                         for (int l = 0; l < 3; ++l) {
                             const float g = __ldg(gp + l);
@@ -398,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                             else if (kind == 0) pend[l] += g;
                             else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
                         }
-                        add_const_cotangent(a.g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L);
+                        add_const_cotangent(a_g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L);
                     }
                 }
                 const float c8 = dt * 0.125f;
@@ -413,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                     LAM[row] = lam[c] + pend[c];    // becomes lambda_n once the four stage VJPs are added
                     // stage input of stage 4
                     float* X = smem + P.off_X + (3 * r + c) * TBP + b;
-                    *X = valid ? __ldg(a.tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                    *X = valid ? __ldg(a_tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
                 }
             }
             j = j_next;
@@ -458,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
                         LAM[row] += xb;
                         // next stage input (stage-1), from the tape
                         if (stage > 0)
-                            smem[P.off_X + xrow] = valid ? __ldg(a.tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                            smem[P.off_X + xrow] = valid ? __ldg(a_tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
                     }
                 }
                 UDE_PROF_WORK_DONE();
@@ -470,16 +529,19 @@ __global__ void __launch_bounds__(kThreads, 1) rk4_bwd_kernel(const __grid_const
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
-                float* dst = a.g_y0 + ((b0 + b) * P.R + r) * (long long)L;
+                float* dst = a_g_y0 + ((b0 + b) * P.R + r) * (long long)L;
 #pragma unroll
                 for (int l = 0; l < 3; ++l) dst[l] = LAM[(3 * r + l) * TBP + b] + dst[l];
             }
         }
         __syncthreads();
-        hoist_backward_epilogue(P, a.wpacked, smem, Gslab, a.y0, a.g_y0, b0, nvalid, warp, lane);
+        hoist_backward_epilogue(P, a_wpacked, smem, Gslab, a_y0, a_g_y0, b0, nvalid, warp, lane);
+        if (grouped && SMEM_G) {
+            for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
+        }
     }
     __syncthreads();
-    if (SMEM_G)
+    if (SMEM_G && !grouped)
         for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
     if (tm_acc) {
         dw_tm_flush(P, smem + P.off_GB, Gslab, tmem, warp, lane);
@@ -502,7 +564,9 @@ __device__ __forceinline__ int first_layer_src_col(const ModelP& P, int col, boo
 
 // theta (PyTorch layout) -> packed blob (padded rows, zero fill).  One block per layer, then one per constant
 // block of the first layers (ModelP: "Hoisting"), then the tail padding.
-__global__ void pack_theta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ theta, float* __restrict__ packed) {
+__global__ void pack_theta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ theta_all, float* __restrict__ packed_all) {
+    const float* __restrict__ theta = theta_all + (long long)blockIdx.y * P.n_theta;          // weight set blockIdx.y
+    float* __restrict__ packed = packed_all + (long long)blockIdx.y * P.n_packed;
     const int li = blockIdx.x, nl = P.n_rate + P.n_aug;
     if (li == nl + 2) {       // tail padding
         for (int i = threadIdx.x; i < kPadTail; i += blockDim.x) packed[P.n_packed - kPadTail + i] = 0.f;
@@ -526,8 +590,11 @@ __global__ void pack_theta_kernel(const __grid_constant__ ModelP P, const float*
 }
 
 // g_theta[e] = sum over CTA slabs (fixed order => deterministic) of the packed accumulators.
-__global__ void reduce_dtheta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ slabs, int n_slabs,
-                                     float* __restrict__ g_theta) {
+__global__ void reduce_dtheta_kernel(const __grid_constant__ ModelP P, const float* __restrict__ slabs_all, int n_slabs,
+                                     float* __restrict__ g_theta_all) {
+    // weight set blockIdx.y owns slabs [y * n_slabs, (y + 1) * n_slabs)
+    const float* __restrict__ slabs = slabs_all + (long long)blockIdx.y * n_slabs * P.n_packed;
+    float* __restrict__ g_theta = g_theta_all + (long long)blockIdx.y * P.n_theta;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P.n_theta) return;
     int pidx = -1;
@@ -559,7 +626,9 @@ __global__ void reduce_dtheta_kernel(const __grid_constant__ ModelP P, const flo
 }
 
 // side[0..7] = sum over CTA partials (fixed order).
-__global__ void reduce_side_kernel(const double* __restrict__ partial, int n_parts, double* __restrict__ side) {
+__global__ void reduce_side_kernel(const double* __restrict__ partial_all, int n_parts, double* __restrict__ side_all) {
+    const double* __restrict__ partial = partial_all + (long long)blockIdx.x * n_parts * 8;    // weight set blockIdx.x
+    double* __restrict__ side = side_all + (long long)blockIdx.x * 8;
     const int i = threadIdx.x;
     if (i >= 8) return;
     double s = 0.0;

@@ -12,7 +12,10 @@ static inline int round16(int x) { return (x + 15) & ~15; }
 // Trajectories from which the layer products count as "real dense contractions" (BASELINE north_star):
 // below this the 128-trajectory tiles cannot fill the 148 SMs and the FFMA engine (32/64-trajectory
 // tiles) is the better fit.
-static const long long kTcMinBatch = 148LL * kTcTile;
+static long long tc_min_batch() {
+    const DeviceInfo& di = device_info();
+    return (long long)(di.ok ? di.n_sm : 148) * kTcTile;
+}
 static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit minus the static part (~1.2 KB) and alignment slack
 
 static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes, int head_elu, int& th) {
@@ -138,7 +141,7 @@ int tc_choose(const UdeDesc* d, TcModel& M) {
     const bool ok = tc_build_model(d, M);
     if (d->flags & UDE_FLAG_FORCE_TENSOR) return ok ? 1 : UDE_ERR_UNSUPPORTED;
     if (d->flags & UDE_FLAG_FORCE_FFMA) return 0;
-    return (ok && d->batch >= kTcMinBatch) ? 1 : 0;
+    return (ok && d->batch >= tc_min_batch()) ? 1 : 0;
 }
 
 // MMA instruction lists of every layer (shared-memory addresses relative to the dynamic smem base;
@@ -228,8 +231,10 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     const int n_ctas = tc_grid(desc->batch);
     TcWorkspace w = tc_carve(workspace, M, n_ctas);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
-    tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
-    UDE_CUDA(cudaGetLastError());
+    if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED)) {
+        tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
+        UDE_CUDA(cudaGetLastError());
+    }
     UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)n_ctas * M.slab_floats * 4, s));
     static thread_local TcTable tab_storage;
     TcTable* tab = &tab_storage;

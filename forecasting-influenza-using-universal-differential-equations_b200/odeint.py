@@ -95,11 +95,47 @@ def _grid_on_device(t: torch.Tensor, step_size, device):
 # ---------------------------------------------------------------------------------------
 # autograd bridge
 # ---------------------------------------------------------------------------------------
+def flat_theta(params) -> torch.Tensor:
+    """The C ABI's flat weight vector from the module's (W, b) tensors in theta order.  Zero-copy when they already are
+    consecutive views of ONE buffer (``ude_b200.flatten_parameters``), else one ``torch.cat``."""
+    p0 = params[0]
+    ptr, esz = p0.data_ptr(), p0.element_size()
+    for p in params:
+        if p.data_ptr() != ptr or not p.is_contiguous():
+            return torch.cat([q.detach().reshape(-1) for q in params])
+        ptr += p.numel() * esz
+    n = (ptr - p0.data_ptr()) // esz
+    base = p0.detach()
+    return base.as_strided((n,), (1,))      # stays inside the shared buffer by construction
+
+
+def split_like(flat: torch.Tensor, params):
+    """Views of `flat` shaped like `params` (gradients come back as views of ONE buffer: no per-parameter kernels)."""
+    out, off = [], 0
+    for p in params:
+        n = p.numel()
+        out.append(flat[off:off + n].view(p.shape))
+        off += n
+    return out
+
+
+def flatten_parameters(func) -> torch.Tensor:
+    """Re-home the ODE func's Linear weights and biases as consecutive views of one flat buffer (theta order), so that a
+    solve hands the buffer to the kernels without gathering it and the optimizer can treat it as one tensor.
+    Returns the buffer; the module's parameters keep their names, shapes and values (state_dict unchanged)."""
+    info = describe_func(func)
+    ps = [p for l in info.linears() for p in (l.weight, l.bias)]
+    flat = torch.cat([p.detach().reshape(-1) for p in ps])
+    for p, v in zip(ps, split_like(flat, ps)):
+        p.data = v
+    return flat
+
+
 class _Rk4Solve(torch.autograd.Function):
-    """(theta, y0) -> (y_out [T,B,R,L], side [8] fp64).  One fused launch each way."""
+    """(y0, *params) -> (y_out [T,B,R,L], side [8] fp64).  One fused launch each way."""
 
     @staticmethod
-    def forward(ctx, theta, y0, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool):
+    def forward(ctx, y0, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool, *params):
         L = _lib.lib()
         dev = y0.device
         B, R, Ld = y0.shape
@@ -107,7 +143,7 @@ class _Rk4Solve(torch.autograd.Function):
         plan = _lib.UdePlan()
         with torch.cuda.device(dev):
             _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
-            theta_c = theta.detach().contiguous()
+            theta_c = flat_theta(params)
             y0_c = y0.detach().contiguous()
             y_out = torch.empty((n_out, B, R, Ld), dtype=torch.float32, device=dev)
             side = torch.empty(8, dtype=torch.float64, device=dev)
@@ -120,8 +156,12 @@ class _Rk4Solve(torch.autograd.Function):
             _lib.check(st, "ude_rk4_forward")
         ctx.info, ctx.tables, ctx.n_steps, ctx.n_out = info, tables, n_steps, n_out
         ctx.plan_ws = int(plan.workspace_bytes)
-        ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev))
+        # the workspace travels to the backward: it still holds THIS theta's packed weight images, which the adjoint then
+        # does not build again (UDE_FLAG_WEIGHTS_PACKED); theta itself is a snapshot when it was gathered with cat
+        ctx.save_for_backward(theta_c, y0_c, tape if tape is not None else torch.empty(0, device=dev),
+                              ws if tape is not None else torch.empty(0, device=dev))
         ctx.has_tape = tape is not None
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
         return y_out, side
 
     @staticmethod
@@ -129,11 +169,12 @@ class _Rk4Solve(torch.autograd.Function):
         if not ctx.has_tape:
             raise RuntimeError("fused odeint was run without a tape (no input required grad)")
         L = _lib.lib()
-        theta_c, y0_c, tape = ctx.saved_tensors
+        theta_c, y0_c, tape, ws = ctx.saved_tensors
         info: FuncInfo = ctx.info
         dev = y0_c.device
         B = y0_c.shape[0]
         desc = info.desc(B)
+        desc.flags |= _lib.FLAG_WEIGHTS_PACKED
         with torch.cuda.device(dev):
             if g_out is None:
                 g_out = torch.zeros((ctx.n_out, *y0_c.shape), dtype=torch.float32, device=dev)
@@ -142,14 +183,17 @@ class _Rk4Solve(torch.autograd.Function):
             if g_side is not None:
                 gs = g_side[:5].to(torch.float32).contiguous()
             g_y0 = torch.empty_like(y0_c)
-            g_theta = torch.empty_like(theta_c)
-            ws = torch.empty(ctx.plan_ws, dtype=torch.uint8, device=dev)
+            g_theta = torch.empty(theta_c.numel(), dtype=torch.float32, device=dev)
             dt, out_step, out_kind, out_w = ctx.tables
             st = L.ude_rk4_backward(C.byref(desc), _ptr(theta_c), _ptr(y0_c), ctx.n_steps, _ptr(dt), ctx.n_out,
                                     _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(tape), _ptr(g_out), _ptr(gs),
                                     _ptr(g_y0), _ptr(g_theta), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
             _lib.check(st, "ude_rk4_backward")
-        return g_theta, g_y0, None, None, None, None, None
+        grads, off = [], 0
+        for shape, n in ctx.param_meta:
+            grads.append(g_theta[off:off + n].view(shape))
+            off += n
+        return (g_y0, None, None, None, None, None, *grads)
 
 
 class _Rk4SolveGroups(torch.autograd.Function):
@@ -285,9 +329,9 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
             options.get("grid_constructor", None) is not None:
         raise NotImplementedError("only step_size grids with linear interpolation are fused")
     (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
-    theta = info.theta()
-    need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
-    y_out, side = _Rk4Solve.apply(theta, y0, info, tables, n_steps, int(t.numel()), need_tape)
+    params = [p for l in info.linears() for p in (l.weight, l.bias)]
+    need_tape = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
+    y_out, side = _Rk4Solve.apply(y0, info, tables, n_steps, int(t.numel()), need_tape, *params)
     if group is not None:
         from .dist import all_reduce_side
         side = all_reduce_side(side, None if group is True else group)

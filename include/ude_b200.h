@@ -100,6 +100,10 @@ typedef struct UdeDesc {
  * FORCE_TENSOR on an uncovered configuration returns UDE_ERR_UNSUPPORTED. */
 #define UDE_FLAG_FORCE_FFMA 4
 #define UDE_FLAG_FORCE_TENSOR 8
+/* ude_rk4_backward only: `workspace` is the buffer the matching ude_rk4_forward call (same desc, same theta) used and
+ * nothing has written to it since, so it still holds the packed weight images -- the adjoint does not build them again.
+ * (One launch less per training step; what loss.backward() right after odeint() looks like, lib/VAE.py:201-203.) */
+#define UDE_FLAG_WEIGHTS_PACKED 16
 
 typedef enum UdeMethod { UDE_METHOD_RK4 = 0, UDE_METHOD_DOPRI5 = 1 } UdeMethod;
 
@@ -113,7 +117,10 @@ typedef struct UdePlan {
     int32_t smem_bytes_fwd;     /* dynamic shared memory per CTA                  */
     int32_t smem_bytes_bwd;
     int32_t weights_in_smem;    /* 1: staged once per CTA with a TMA bulk copy    */
-    int32_t reserved;
+    int32_t path;               /* kernel family the call will run: 0 FFMA engine, 1 tcgen05 engine (ude_rk4_path),
+                                 * 2 FFMA engine, all weight-set groups in one launch.  The two engines round
+                                 * differently (both inside the 1e-5 bar): pin UDE_FLAG_FORCE_* for bit-reproducibility
+                                 * across batch sizes / shard counts.                                            */
 } UdePlan;
 
 int         ude_abi_version(void);

@@ -116,8 +116,9 @@ def test_descriptor_validation_and_plan(built_lib):
 
 
 def test_group_plan_is_g_single_group_plans(built_lib):
-    """n_groups = G (BASELINE configs[4]): workspace and tape are G per-group blocks of the single-set plan
-    (group-major layouts, include/ude_b200.h), theta size stays per group; batch must divide by G."""
+    """n_groups = G (BASELINE configs[4]): the tape is G per-group blocks of the single-set plan (group-major layouts,
+    include/ude_b200.h), the workspace at least that, theta size stays per group; batch must divide by G.  Small models
+    run all groups in ONE launch (plan.path == 2) with tiles sized for the total batch."""
     from ude_b200 import _lib
     one = _desc("Fp", 1, 8, [32, 32, 2], [], B=2048)
     p1 = _lib.UdePlan()
@@ -127,10 +128,10 @@ def test_group_plan_is_g_single_group_plans(built_lib):
     pg = _lib.UdePlan()
     assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) == 0
     up = lambda v: (v + 255) // 256 * 256
-    assert pg.workspace_bytes == 512 * up(p1.workspace_bytes)
+    assert pg.workspace_bytes >= 512 * up(p1.workspace_bytes)
     assert pg.tape_bytes == 512 * up(p1.tape_bytes)
     assert pg.n_theta == p1.n_theta == built_lib.ude_theta_size(C.byref(grp))
-    assert pg.tile_traj == p1.tile_traj
+    assert pg.path == 2 and pg.tile_traj == 64 and pg.n_ctas == 2 * 148
     grp.batch = 512 * 2048 + 1
     assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) != 0
     grp.batch = 512 * 2048

@@ -56,4 +56,6 @@ def test_package_exposes_the_torchdiffeq_surface():
     assert list(sig.parameters) == ["func", "y0", "t", "rtol", "atol", "method", "options", "event_fn"]
     assert sig.parameters["rtol"].default == 1e-7 and sig.parameters["atol"].default == 1e-9
     assert sig.parameters["method"].default is None          # None -> dopri5, as torchdiffeq
-    assert ude_b200.odeint_adjoint is ude_b200.odeint
+    adj = inspect.signature(ude_b200.odeint_adjoint)       # torchdiffeq's second entry point incl. its adjoint_* knobs
+    assert list(adj.parameters)[:8] == list(sig.parameters)
+    assert {"adjoint_rtol", "adjoint_atol", "adjoint_method", "adjoint_options", "adjoint_params"} <= set(adj.parameters)

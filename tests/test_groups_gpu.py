@@ -47,9 +47,11 @@ def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg):
         y0s = y0[g].cuda().requires_grad_(True)
         ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=h))
         (ys * Gc[g].cuda()).sum().backward()
+        # per-trajectory results do not depend on the tiling: same bits; dtheta is a sum over tiles whose size follows the
+        # TOTAL batch in the grouped launch (64 instead of 32 trajectories): same value to fp32 summation round-off
         assert torch.equal(ys, grouped[g][0])
         assert torch.equal(y0s.grad, grouped[g][1])
-        assert torch.equal(flat_grad(mod), grouped[g][2])
+        assert rel_err(grouped[g][2], flat_grad(mod)) <= 2e-6
         # and the oracle
         f = OracleFunc(spec, thetas[g])
         y0r = y0[g].clone().requires_grad_(True)
@@ -79,18 +81,24 @@ def test_group_side_channels_are_per_model():
         with torch.no_grad():
             ude_b200.odeint(mod, y0[g], t, method="rk4", options=dict(step_size=1.0))
         p = mod.posterior()
-        assert torch.equal(p.mean, posts[g].mean) and torch.equal(p.stddev, posts[g].stddev)
+        assert rel_err(posts[g].mean, p.mean) <= 1e-6 and rel_err(posts[g].stddev, p.stddev) <= 1e-5
     assert not torch.equal(posts[0].mean, posts[1].mean)
 
 
 def test_many_groups_fan_out():
-    """64 groups x 2048 trajectories (the per-GPU share of configs[4]) through the stream fan-out: finite, and group 17
-    equals its own single-set solve."""
+    """64 groups x 2048 trajectories (the per-GPU share of configs[4]) in ONE forward and ONE backward launch (plan path
+    2): finite, and group 17 equals its own single-set solve."""
+    import ctypes as C
+
     import ude_b200
+    from ude_b200 import _lib
     from oracle.ude_rhs import UdeSpec, synth_y0
     spec = UdeSpec("Fp", 1, 8, (32, 32), ())
     G, Bg = 64, 2048
     thetas, mods = _models(spec, G, seed=100)
+    plan = _lib.UdePlan()
+    desc = ude_b200.describe_func(mods[0]).desc(G * Bg, n_groups=G)
+    assert ude_b200.lib().ude_plan(C.byref(desc), 0, 8, C.byref(plan)) == 0 and plan.path == 2, "not the single-launch grouped path"
     t = torch.linspace(1, 56, 56) / 7
     y0 = synth_y0(G * Bg, 1, 8, seed=3).reshape(G, Bg, 1, 8).cuda().requires_grad_(True)
     y = ude_b200.odeint_groups(mods, y0, t, method="rk4", options=dict(step_size=1.0))
@@ -102,7 +110,7 @@ def test_many_groups_fan_out():
     (ys[..., :3] ** 2).sum().backward()
     assert torch.equal(ys, y[17])
     assert torch.equal(y0s.grad, y0.grad[17])
-    assert torch.equal(flat_grad(mod), flat_grad(mods[17]))
+    assert rel_err(flat_grad(mods[17]), flat_grad(mod)) <= 2e-6
 
 
 def test_group_architecture_mismatch_is_an_error():
