@@ -530,7 +530,8 @@ def run_ours(args):
             _lib.check(st, "fwd")
             if ev:
                 ev[1].record()
-            h = dist.all_reduce(side, async_op=True) if world > 1 else None   # the loss needs the global side sums before backward
+            if world > 1:       # the loss needs the GLOBAL side sums before backward; in-stream: an NCCL kernel that overlaps the
+                dist.all_reduce(side)   # persistent adjoint kernel takes an SM away from its one-CTA-per-SM grid
             st = L.ude_rk4_backward(C.byref(desc), _ptr(theta), _ptr(y0), n_steps, _ptr(dt_t), n_out, _ptr(os_t),
                                     _ptr(ok_t), _ptr(ow_t), _ptr(tape), _ptr(g_out), _ptr(g_side), _ptr(g_y0),
                                     _ptr(g_theta), _ptr(ws), int(plan.workspace_bytes), stream)
@@ -539,7 +540,6 @@ def run_ours(args):
                 ev[2].record()
             if world > 1:
                 dist.all_reduce(g_theta)
-                h.wait()
 
         def barrier():
             if world > 1:

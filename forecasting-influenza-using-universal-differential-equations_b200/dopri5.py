@@ -12,6 +12,7 @@ Extra (fused-path only) options: ``max_accepted_steps`` (tape capacity, default 
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import torch
 
@@ -23,15 +24,27 @@ STATUS_TEXT = {1: "max_accepted_steps exceeded (raise options['max_accepted_step
                2: "max_num_steps exceeded", 3: "underflow in dt / non-finite state"}
 
 
-def _opts(rtol, atol, options) -> "_lib.UdeDopri5Opts":
+class PerTrajectoryStepControl(UserWarning):
+    """The fused Dopri5 was called on a batch without ``options['per_trajectory']`` being stated."""
+
+
+def _opts(rtol, atol, options, batch: int = 1) -> "_lib.UdeDopri5Opts":
     known = {"first_step", "safety", "ifactor", "dfactor", "max_num_steps", "max_accepted_steps", "return_stats",
              "per_trajectory", "dtype", "process_group"}
     unknown = set(options) - known
     if unknown:
         raise ValueError(f"unexpected dopri5 options {sorted(unknown)}")
-    if options.get("per_trajectory", True) is False:
+    if options.get("per_trajectory", None) is False:
         raise NotImplementedError("the fused Dopri5 runs one controller per trajectory (see DESIGN.md); "
-                                  "shared-step batch control is not fused")
+                                  "torchdiffeq's shared-step batch control (one RMS norm and one dt for the whole "
+                                  "tensor) is not fused")
+    if batch > 1 and "per_trajectory" not in options:
+        # the default call must not silently differ from torchdiffeq's batch semantics (ADVICE r1): say so, once per site
+        warnings.warn(
+            "ude_b200.odeint(method='dopri5') controls the step size PER TRAJECTORY (= torchdiffeq applied to every row "
+            "alone); torchdiffeq itself uses one error norm and one step size for the whole batch, and its side-channel "
+            "lists also hold rejected and probe evaluations.  Results agree to the controller's tolerance, not step for "
+            "step.  Pass options={'per_trajectory': True} to acknowledge.", PerTrajectoryStepControl, stacklevel=4)
     o = _lib.UdeDopri5Opts()
     o.rtol = float(rtol)
     o.atol = float(atol)
@@ -117,7 +130,7 @@ class Dopri5Stats:
 
 
 def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
-    opts = _opts(rtol, atol, options)
+    opts = _opts(rtol, atol, options, int(y0.shape[0]))
     t_dev = t_cpu.to(torch.float64).to(y0.device)
     theta = info.theta()
     need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)

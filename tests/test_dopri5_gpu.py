@@ -112,3 +112,26 @@ def test_failure_status_is_reported():
     g = load_golden("dopri5_fafp_r1")
     with pytest.raises(ude_b200.UdeError, match="max_num_steps"):
         _solve(g, max_num_steps=2)
+
+
+def test_batch_semantics_must_be_acknowledged():
+    """torchdiffeq steps the whole batch with ONE step size; the fused path controls every trajectory on its own.  The
+    default call on a batch says so; B == 1 (where the two coincide) and an explicit
+    options['per_trajectory'] = True are silent; the shared-step mode is an explicit error, not a silent substitute."""
+    import warnings
+
+    import ude_b200
+    from ude_b200.dopri5 import PerTrajectoryStepControl
+    g = load_golden("dopri5_fafp_r1")
+    mod = module_from_spec(g["spec"], torch.from_numpy(g["theta"]), g["fa_w"], "cuda")
+    y0 = torch.from_numpy(g["y0"]).cuda()
+    t = torch.from_numpy(g["t"])
+    with torch.no_grad():
+        with pytest.warns(PerTrajectoryStepControl):
+            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error", PerTrajectoryStepControl)
+            ude_b200.odeint(mod, y0[:1], t, rtol=1e-5, atol=1e-9)
+            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(per_trajectory=True))
+        with pytest.raises(NotImplementedError):
+            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(per_trajectory=False))
