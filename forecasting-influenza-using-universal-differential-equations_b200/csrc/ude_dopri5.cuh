@@ -107,12 +107,16 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     __shared__ double s_t0[kMaxTB], s_t1[kMaxTB], s_dt[kMaxTB];
     __shared__ float s_dtold[kMaxTB], s_h0[kMaxTB];
     __shared__ int s_j[kMaxTB], s_nacc[kMaxTB], s_nrej[kMaxTB], s_natt[kMaxTB], s_status[kMaxTB], s_acc[kMaxTB];
+    __shared__ __align__(8) uint64_t rbar[2];
 
     copy_model_to_smem(&P, Pg);
     if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn, R = P.R;
+    const bool ring = COLD && P.w_ring;          // see rk4_fwd_kernel
+    WRing wr;
+    if (ring) ring_setup(wr, P, smem, rbar, a.wpacked);
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
@@ -140,7 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
 
     // one RHS evaluation at X; `record`: 0 none, 1 straight into the thread's accumulators, 2 into SA (attempt)
     auto eval_into = [&](float* Kdst, int record, int nvalid) {
-        rhs_forward_layers(P, Wp, smem, warp, lane);
+        if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, 0u);
+        else rhs_forward_layers(P, Wp, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const bool valid = b < nvalid;
@@ -178,7 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             s_acc[b] = 0;
         }
         __syncthreads();
-        hoist_c0(P, a.wpacked, smem, warp, lane);
+        if (ring) hoist_c0_ring(P, a.wpacked, smem, warp, lane, 0u);
+        else hoist_c0(P, a.wpacked, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const float* X = smem + P.off_X + (3 * r) * TBP + b;
@@ -428,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
         }
     }
     side_block_reduce(side, 0.0, red, a.side_partial + (long long)blockIdx.x * 8);
+    if (ring) wr_drain(wr);
 }
 
 // ===================================================================================
@@ -442,13 +449,17 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
     __shared__ float s_dt[kMaxTB];
     __shared__ int s_j[kMaxTB], s_nacc[kMaxTB], s_act[kMaxTB], s_max;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t rbar[2];
 
     copy_model_to_smem(&P, Pg);
     if (threadIdx.x == 0 && SMEM_W) mbar_init(&wbar, 1);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn, R = P.R;
-    const bool tm_acc = COLD && P.tm_acc;          // see rk4_bwd_kernel
+    const bool ring = COLD && P.w_ring;            // see rk4_bwd_kernel
+    WRing wr;
+    if (ring) ring_setup(wr, P, smem, rbar, a.wpacked);
+    const bool tm_acc = COLD && P.tm_acc;
     uint32_t tmem = 0u;
     if (tm_acc) {
         if (warp == 0) tm_alloc512(&tmem_slot);
@@ -487,7 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
 
     // VJP of one RHS evaluation at X with cotangent KB[ki]; afterwards GX holds dL/dx (all rows)
     auto vjp_at_x = [&](int ki, int nvalid) {
-        rhs_forward_layers(P, Wp, smem, warp, lane);
+        if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, tmem);
+        else rhs_forward_layers(P, Wp, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             const int row = (3 * r) * TBP + b;
@@ -498,7 +510,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             gx[0] = xb[0]; gx[TBP] = xb[1]; gx[2 * TBP] = xb[2];
         }
         __syncthreads();
-        if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
+        if (ring) rhs_backward_layers_ring(P, wr, smem, smem + P.off_GB, warp, lane, tmem);
+        else if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
         else rhs_backward_layers<false>(P, Wp, smem, G, warp, lane);
     };
 
@@ -506,10 +519,14 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         const long long b0 = tile * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         __syncthreads();
-        load_y0_tile(P, smem, a.y0, b0, nvalid, false, P.hoist != 0);
+        // live rows too: trajectories that are not active in a step (fewer accepted steps than the tile's maximum) and the
+        // invalid columns of a ragged tile still run through the MLPs and must see FINITE inputs (0 * NaN = NaN)
+        load_y0_tile(P, smem, a.y0, b0, nvalid, true, P.hoist != 0);
         for (int i = threadIdx.x; i < DB_NSTATE * SS; i += kThreads) SB[P.off_S + i] = 0.f;
         for (int i = threadIdx.x; i < P.Dn_p * TBP; i += kThreads) GX[i] = 0.f;
-        for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
+        if (ring && P.c0_tm) dl_tm_clear(P, tmem, warp);
+        else
+            for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {      // dL/dy0 starts from the cotangent of output 0
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
@@ -519,7 +536,8 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         }
         if (threadIdx.x == 0) s_max = 0;
         __syncthreads();
-        hoist_c0(P, a.wpacked, smem, warp, lane);
+        if (ring) hoist_c0_ring(P, a.wpacked, smem, warp, lane, tmem);
+        else hoist_c0(P, a.wpacked, smem, warp, lane);
         if (threadIdx.x < TB) {
             const int b = threadIdx.x;
             s_nacc[b] = b < nvalid ? a.counts[(b0 + b) * 4 + 0] : 0;
@@ -552,11 +570,12 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
                         const float x = (float)((a.t_out[jj] - t0) / (t1 - t0));
                         const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
                         const float* gp = a.g_out + (((long long)jj * B + b0 + b) * R + r) * (long long)L;
+                        float gl[3];
+                        add_const_cotangent(a.g_y0 + ((b0 + b) * R + r) * (long long)L, gp, L, gl);
                         for (int l = 0; l < 3; ++l) {
-                            const float g = __ldg(gp + l);
+                            const float g = gl[l];
                             ce[l] += g; cd[l] += x * g; cc[l] += x2 * g; cbv[l] += x3 * g; ca[l] += x4 * g;
                         }
-                        add_const_cotangent(a.g_y0 + ((b0 + b) * R + r) * (long long)L, gp, L);
                     }
                 }
                 for (int c = 0; c < 3; ++c) {
@@ -640,6 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
             }
         }
         __syncthreads();
+        if (ring && P.c0_tm) dl_tm_dump(P, smem, P.off_DL, tmem, warp, lane);
         hoist_backward_epilogue(P, a.wpacked, smem, Gslab, a.y0, a.g_y0, b0, nvalid, warp, lane);
     }
     __syncthreads();
@@ -651,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_bwd_kernel(const __grid_co
         __syncthreads();
         if (warp == 0) tm_free512(tmem);
     }
+    if (ring) wr_drain(wr);
 }
 
 }  // namespace ude

@@ -500,10 +500,15 @@ __device__ __forceinline__ void dw_flush_run(const LayerP& Lp, float* Gslab, int
     else if (Lp.tm_dw == 4 && Lp.tn_dw == 1) dw_flush_unit<4, 1>(Lp, Gslab, mt, nt, lane, tm);
     else dw_flush_unit<1, 1>(Lp, Gslab, mt, nt, lane, tm);
 }
-// TMEM address of the accumulators of the `it`-th unit this warp runs in the weight-gradient phase of depth s:
-// warps w and w + 4 share a lane quarter, so their slots interleave
-__device__ __forceinline__ uint32_t dw_tm_addr(const ModelP& P, uint32_t tmem, int s, int it, int warp) {
-    return tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(P.tm_dw_base[s] + (it * (kWarps / 4) + (warp >> 2)) * kTmSlot);
+// TMEM accumulators: the weight-gradient units of a launch are numbered through all phases (depth s, heads first):
+// unit u of depth s is g = tm_dw_prefix[s] + u, it runs on warp g % kWarps and owns slot g / kWarps of that warp
+// (warps w and w + 4 share a lane quarter, so their slots interleave).  Dense: ceil(units / kWarps) slots per warp.
+__device__ __forceinline__ int dw_first_unit(const ModelP& P, int s, int warp) {
+    return (warp - P.tm_dw_prefix[s]) & (kWarps - 1);
+}
+__device__ __forceinline__ uint32_t dw_tm_addr(const ModelP& P, uint32_t tmem, int s, int u, int warp) {
+    const int slot = (P.tm_dw_prefix[s] + u) / kWarps;
+    return tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((slot * (kWarps / 4) + (warp >> 2)) * kTmSlot);
 }
 __device__ __forceinline__ int bwd_units(const LayerP& Lp, int mt_shift) { return Lp.bwd_nt << mt_shift; }
 __device__ __forceinline__ void bwd_run(const LayerP& Lp, const LayerP* prev, const float* Wp, float* smem, int TBP,
@@ -542,9 +547,8 @@ __device__ __forceinline__ void rhs_backward_layers(const ModelP& P, const float
             }
             const int w0 = Lr ? dw_units(*Lr) : 0;
             const int w1 = La ? dw_units(*La) : 0;
-            int it = 0;
-            for (int u = warp; u < w0 + w1; u += kWarps, ++it) {
-                const uint32_t tm = TM_ACC ? dw_tm_addr(P, tmem, s, it, warp) : 0u;
+            for (int u = TM_ACC ? dw_first_unit(P, s, warp) : warp; u < w0 + w1; u += kWarps) {
+                const uint32_t tm = TM_ACC ? dw_tm_addr(P, tmem, s, u, warp) : 0u;
                 if (u < w0) dw_run<TM_ACC>(*Lr, smem, G, P.TB, P.TBP, u, lane, tm);
                 else dw_run<TM_ACC>(*La, smem, G, P.TB, P.TBP, u - w0, lane, tm);
             }
@@ -591,9 +595,8 @@ __device__ __forceinline__ void dw_tm_flush(const ModelP& P, const float* gb, fl
         const LayerP* Lr = lr >= 0 ? &P.rate[lr] : nullptr;
         const LayerP* La = la >= 0 ? &P.aug[la] : nullptr;
         const int w0 = Lr ? dw_units(*Lr) : 0, w1 = La ? dw_units(*La) : 0;
-        int it = 0;
-        for (int u = warp; u < w0 + w1; u += kWarps, ++it) {
-            const uint32_t tm = dw_tm_addr(P, tmem, s, it, warp);
+        for (int u = dw_first_unit(P, s, warp); u < w0 + w1; u += kWarps) {
+            const uint32_t tm = dw_tm_addr(P, tmem, s, u, warp);
             if (u < w0) dw_flush_run(*Lr, Gslab, u, lane, tm);
             else dw_flush_run(*La, Gslab, u - w0, lane, tm);
         }

@@ -2,6 +2,8 @@
 //
 // Everything here is plain C++/CUDA runtime: no torch, no allocation of persistent
 // memory, no exceptions across the boundary.
+#include <stdlib.h>
+
 #include "ude_host_common.h"
 #include "ude_dopri5.cuh"
 #include "ude_rk4.cuh"
@@ -122,7 +124,25 @@ static void tile_shapes(LayerP& Lp, int m_tiles, int want) {
 }
 
 // Shared-memory plan for a given tile size; returns the arena size in floats.
-static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int n_state, int n_rbuf, bool bwd) {
+// ring-mode tile shapes: one net per phase, so a phase wants >= kWarps units of its own (ude_ring.cuh)
+static void tile_shapes_ring(LayerP& Lp, int m_tiles, bool c0_slot, bool dl_slot) {
+    const int groups = (Lp.n_out_p + 3) / 4;
+    int tn = (groups * m_tiles + kWarps - 1) / kWarps;
+    tn = tn < 1 ? 1 : (tn > 6 ? 8 : tn);
+    if (c0_slot && tn > 4) tn = 4;                      // c0 slots hold 16 values per thread
+    Lp.tn_fwd = tn;
+    Lp.fwd_nt = (Lp.n_out_p + 4 * tn - 1) / (4 * tn);
+    int best = 2, best_cost = 1 << 30;
+    for (int t = 2; t <= (dl_slot ? 4 : 8); t *= 2) {   // D slots hold 16 values per thread
+        const int units = (Lp.n_in_p + 4 * t - 1) / (4 * t) * m_tiles;
+        const int cost = (units + kWarps - 1) / kWarps * t;
+        if (cost <= best_cost) { best = t; best_cost = cost; }
+    }
+    Lp.tn_bwd = best;
+    Lp.bwd_nt = (Lp.n_in_p + 4 * best - 1) / (4 * best);
+}
+
+static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int n_state, int n_rbuf, bool bwd, bool ring = false) {
     P.TB = TB;
     P.TBP = TB + 4;
     P.tb_shift = TB == 64 ? 6 : 5;
@@ -150,21 +170,60 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
     // constants of the tile: alias the ACT rows (only alive in the tile prologue / epilogue)
     P.off_XC = act0;
     if (off - act0 < P.Dc_p * P.TBP) off = act0 + P.Dc_p * P.TBP;
-    // hoisted first-layer parts: c0 rows (both directions), D rows (adjoint)
+    // hoisted first-layer parts: c0 rows (both directions), D rows (adjoint); in the ring-mode adjoint both live in
+    // tensor memory and D is dumped behind the constants' rows for the tile epilogue
+    P.w_ring = ring;
+    P.c0_tm = ring && bwd && P.hoist;
     P.dl_rows = 0;
     if (P.hoist) {
         for (int net = 0; net < 2; ++net) {
             LayerP* Ls = net == 0 ? P.rate : P.aug;
             LayerP& Lc = net == 0 ? P.rate_c : P.aug_c;
             if ((net == 0 ? P.n_rate : P.n_aug) == 0) continue;
-            Ls[0].c0_off = off;
+            P.dl_rows += Ls[0].n_out_p;
             Lc.in_off = P.off_XC;
+            if (P.c0_tm) { Ls[0].c0_off = -1; Lc.act_off = 0; continue; }
+            Ls[0].c0_off = off;
             Lc.act_off = off;
             off += Ls[0].n_out_p * P.TBP;
-            P.dl_rows += Ls[0].n_out_p;
         }
-        P.off_DL = off;
-        if (bwd) off += P.dl_rows * P.TBP;
+        if (P.c0_tm) {
+            P.off_DL = P.off_XC + P.Dc_p * P.TBP;
+            if (off < P.off_DL + P.dl_rows * P.TBP) off = P.off_DL + P.dl_rows * P.TBP;
+        } else {
+            P.off_DL = off;
+            if (bwd) off += P.dl_rows * P.TBP;
+        }
+    }
+    // weight ring: two slots, each as large as the largest [W | b] layer block
+    P.off_ring = off;
+    P.ring_slot_floats = 0;
+    if (ring) {
+        int id = 0;
+        for (int net = 0; net < 2; ++net) {
+            LayerP* Ls = net == 0 ? P.rate : P.aug;
+            const int n = net == 0 ? P.n_rate : P.n_aug;
+            for (int i = 0; i < n; ++i, ++id) {
+                P.wblk_off[id] = Ls[i].w_off;
+                P.wblk_n[id] = Ls[i].n_out_p * Ls[i].ldw + Ls[i].n_out_p;
+                if (P.wblk_n[id] > P.ring_slot_floats) P.ring_slot_floats = P.wblk_n[id];
+            }
+        }
+        off += 2 * P.ring_slot_floats;
+        // acquisition order of one RHS evaluation: forward layer by layer (rate, aug), then -- adjoint kernels -- the
+        // delta phases from the heads down (rhs_forward_layers_ring / rhs_backward_layers_ring)
+        const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
+        int q = 0;
+        for (int li = 0; li < nl; ++li) {
+            if (li < P.n_rate) P.wseq[q++] = (short)li;
+            if (li < P.n_aug) P.wseq[q++] = (short)(P.n_rate + li);
+        }
+        if (bwd)
+            for (int sdepth = 0; sdepth < nl; ++sdepth) {
+                if (P.n_rate - 1 - sdepth >= 0) P.wseq[q++] = (short)(P.n_rate - 1 - sdepth);
+                if (P.n_aug - 1 - sdepth >= 0) P.wseq[q++] = (short)(P.n_rate + P.n_aug - 1 - sdepth);
+            }
+        P.n_wseq = q;
     }
     // solver-state rows: in shared memory, or (large R) in a per-CTA global scratch ("cold")
     int coff = 0;
@@ -192,8 +251,20 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
         if (P.n_rate > 0) tile_shapes(P.rate_c, m_tiles, want);
         if (P.n_aug > 0) tile_shapes(P.aug_c, m_tiles, want);
     }
-    // weight-gradient accumulators in tensor memory: only on the plan of last resort (nothing else fits on chip),
-    // one 16-column slot per unit and warp, phases of depth s (heads first) side by side
+    if (ring) {
+        for (int net = 0; net < 2; ++net) {
+            LayerP* Ls = net == 0 ? P.rate : P.aug;
+            const int n = net == 0 ? P.n_rate : P.n_aug;
+            for (int i = 0; i < n; ++i) tile_shapes_ring(Ls[i], m_tiles, i == 0 && P.c0_tm, i == 1 && P.c0_tm);
+            if (n > 0 && P.hoist) {          // the constant block runs with the live block's unit shape (same c0 slots)
+                LayerP& Lc = net == 0 ? P.rate_c : P.aug_c;
+                Lc.tn_fwd = Ls[0].tn_fwd;
+                Lc.fwd_nt = Ls[0].fwd_nt;
+            }
+        }
+    }
+    // weight-gradient accumulators in tensor memory: only on the plans of last resort (nothing else fits on chip),
+    // one 16-column slot per unit and warp, the units of all phases (heads first) numbered through
     P.tm_acc = 0;
     P.tm_cols = 0;
     P.n_bias_c = 0;
@@ -206,25 +277,41 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
             for (int i = 0; i < n; ++i) { Ls[i].bc_off = bc; bc += Ls[i].n_out_p; }
         }
         const int nl = P.n_rate > P.n_aug ? P.n_rate : P.n_aug;
-        int cols = 0;
-        bool ok = true;
+        int total = 0;
         for (int s = 0; s < nl; ++s) {
             const int lr = P.n_rate - 1 - s, la = P.n_aug - 1 - s;
-            int units = 0;
+            P.tm_dw_prefix[s] = total;
             for (int net = 0; net < 2; ++net) {
                 const int l = net == 0 ? lr : la;
                 if (l < 0) continue;
                 const LayerP& Lp = net == 0 ? P.rate[l] : P.aug[l];
-                units += Lp.dw_mt * Lp.dw_nt;
+                total += Lp.dw_mt * Lp.dw_nt;
             }
-            P.tm_dw_base[s] = cols;
-            cols += (units + kWarps - 1) / kWarps * (kWarps / 4) * 16;
         }
-        if (ok && cols <= 512) {
+        int cols = (total + kWarps - 1) / kWarps * (kWarps / 4) * 16;
+        const int dw_cols = cols;
+        if (P.c0_tm) {       // c0 and D slots of the first-layer / layer-1-delta phases, per net
+            for (int net = 0; net < 2; ++net) {
+                P.tm_c0_base[net] = cols;
+                if ((net == 0 ? P.n_rate : P.n_aug) == 0) continue;
+                const LayerP& L0 = net == 0 ? P.rate[0] : P.aug[0];
+                cols += ((L0.fwd_nt << P.mt_shift) + kWarps - 1) / kWarps * (kWarps / 4) * 16;
+            }
+            for (int net = 0; net < 2; ++net) {
+                P.tm_dl_base[net] = cols;
+                if ((net == 0 ? P.n_rate : P.n_aug) == 0) continue;
+                const LayerP& L1 = net == 0 ? P.rate[1] : P.aug[1];
+                cols += ((L1.bwd_nt << P.mt_shift) + kWarps - 1) / kWarps * (kWarps / 4) * 16;
+            }
+            P.tm_dl_end = cols;
+        }
+        if (cols <= 512) {
             P.tm_acc = 1;
-            P.tm_cols = cols;
+            P.tm_cols = dw_cols;
             P.n_bias_c = bc;
             off += bc;
+        } else if (ring) {
+            off = 1 << 30;          // the ring plan needs its tensor-memory slots: does not fit
         }
     }
     P.smem_floats = off;
@@ -242,14 +329,18 @@ static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, int n_rbuf, boo
     const int n_sm = di.ok ? di.n_sm : 148;
     // small batches: smaller tiles spread over more SMs
     const int tb_order[2] = {tiles64 >= n_sm ? 64 : 32, tiles64 >= n_sm ? 32 : 64};
-    struct Cand { int w, g, cold; };
-    const Cand cands_bwd[4] = {{1, 1, 0}, {1, 0, 0}, {0, 0, 0}, {0, 0, 1}};
-    const Cand cands_fwd[3] = {{1, 0, 0}, {0, 0, 0}, {0, 0, 1}};
+    struct Cand { int w, g, cold, ring; };
+    // weights (+ accumulators) resident; else the ring plan for wide models (ude_ring.cuh: weights streamed through
+    // shared memory, accumulators in tensor memory, state rows in the CTA's global scratch); else everything from L2
+    const Cand cands_bwd[5] = {{1, 1, 0, 0}, {1, 0, 0, 0}, {0, 0, 1, 1}, {0, 0, 0, 0}, {0, 0, 1, 0}};
+    const Cand cands_fwd[4] = {{1, 0, 0, 0}, {0, 0, 1, 1}, {0, 0, 0, 0}, {0, 0, 1, 0}};
     const Cand* cands = bwd ? cands_bwd : cands_fwd;
-    const int nc = bwd ? 4 : 3;
+    const int nc = bwd ? 5 : 4;
+    const bool no_ring = getenv("UDE_B200_NO_RING") != nullptr;         // A/B switch for profiling
     for (int c = 0; c < nc; ++c)
         for (int t = 0; t < 2; ++t) {
-            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, cands[c].cold, n_state, n_rbuf, bwd) <= budget)
+            if (cands[c].ring && no_ring) continue;
+            if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, cands[c].cold, n_state, n_rbuf, bwd, cands[c].ring) <= budget)
                 return UDE_OK;
         }
     return UDE_ERR_UNSUPPORTED;

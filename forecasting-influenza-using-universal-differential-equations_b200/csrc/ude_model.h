@@ -78,8 +78,17 @@ struct ModelP {
     int n_state;
     int off_RB, n_rbuf;     // per-region scratch: n_rbuf buffers of [R_p][TBP] (dopri5)
     int tm_acc;             // (bwd) weight-gradient accumulators in tensor memory (ude_engine.cuh: TmIo), bias sums at off_GB
-    int tm_dw_base[kMaxLayers];   // first TMEM column of the weight-gradient phase of depth s (counted from the heads)
-    int tm_cols;            // columns in use
+    int tm_dw_prefix[kMaxLayers]; // weight-gradient units of all phases before depth s (counted from the heads): unit u of
+                                  // depth s is unit g = prefix + u of the launch, runs on warp g % kWarps and owns slot g / kWarps
+    int tm_cols;            // accumulator columns in use
+    // ---- ring mode (ude_ring.cuh): weights through a 2-slot TMA ring, c0 / D in tensor memory
+    int w_ring;
+    int off_ring, ring_slot_floats;
+    int c0_tm;              // c0 (and, in the adjoint, D) live in tensor memory
+    int tm_c0_base[2], tm_dl_base[2], tm_dl_end;      // first column per net
+    int wblk_off[2 * kMaxLayers], wblk_n[2 * kMaxLayers];   // [W | b] block of layer id (rate 0.., then aug 0..): floats
+    short wseq[4 * kMaxLayers];   // layer ids in acquisition order of ONE RHS evaluation of this kernel
+    int n_wseq;
     int n_bias_c, off_GB;   // compact bias array [n_bias_c] in shared memory
     int cold_global;        // solver-state rows (off_S, off_RB, off_CB) live in a per-CTA global scratch
     int cold_floats;        // size of that scratch per CTA

@@ -7,6 +7,7 @@
 // and the autograd replay behind /root/reference/lib/VAE.py:203.
 #pragma once
 #include "ude_engine.cuh"
+#include "ude_ring.cuh"
 
 namespace ude {
 
@@ -41,6 +42,24 @@ struct Rk4BwdArgs {
     int n_groups;           // see Rk4FwdArgs
     long long tape_group_floats;
 };
+
+// Ring-mode prologue shared by the four FFMA-engine kernels (COLD variants): barriers, descriptor, first two fetches.
+__device__ __forceinline__ void ring_setup(WRing& wr, const ModelP& P, float* smem, uint64_t* rbar, const float* wpacked) {
+    if (threadIdx.x == 0) {
+        mbar_init(&rbar[0], 1);
+        mbar_init(&rbar[1], 1);
+    }
+    __syncthreads();
+    wr.slots = smem + P.off_ring;
+    wr.bar = rbar;
+    wr.src = wpacked;
+    wr.seq = P.wseq;
+    wr.blk_off = P.wblk_off;
+    wr.blk_n = P.wblk_n;
+    wr.slot_floats = P.ring_slot_floats;
+    wr.nseq = P.n_wseq;
+    wr_start(wr);
+}
 
 // ---- state buffer indices ---------------------------------------------------------
 enum { F_Y = 0, F_K1 = 1, F_K2 = 2, F_K3 = 3, F_NSTATE = 4 };
@@ -156,10 +175,26 @@ __device__ __forceinline__ void hoist_backward_epilogue(const ModelP& P, const f
     __syncthreads();
 }
 
-// cotangent of the constant components of one output row: straight into the caller's g_y0 row (each row is owned by one
-// thread; the lines stay in L2) -- the running sum needs no shared-memory rows
-__device__ __forceinline__ void add_const_cotangent(float* __restrict__ dst, const float* __restrict__ gp, int L) {
-    for (int l = 3; l < L; ++l) dst[l] += __ldg(gp + l);
+// One output row's cotangent: the live components come back in gl[], the constant ones are added straight into the
+// caller's g_y0 row (each row is owned by one thread; the lines stay in L2) -- no shared-memory rows for that running
+// sum.  128-bit accesses when the row allows it (the live lanes of the first quad are rewritten with their own values).
+__device__ __forceinline__ void add_const_cotangent(float* __restrict__ dst, const float* __restrict__ gp, int L, float (&gl)[3]) {
+    if ((L & 3) == 0) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+        float4 d0 = ld4(dst);
+        gl[0] = g0.x; gl[1] = g0.y; gl[2] = g0.z;
+        d0.w += g0.w;
+        st4(dst, d0);
+        for (int l = 4; l < L; l += 4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gp + l));
+            float4 d = ld4(dst + l);
+            d.x += g.x; d.y += g.y; d.z += g.z; d.w += g.w;
+            st4(dst + l, d);
+        }
+    } else {
+        gl[0] = __ldg(gp); gl[1] = __ldg(gp + 1); gl[2] = __ldg(gp + 2);
+        for (int l = 3; l < L; ++l) dst[l] += __ldg(gp + l);
+    }
 }
 
 // ===================================================================================
@@ -173,6 +208,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
     __shared__ __align__(8) uint64_t wbar;
+    __shared__ __align__(8) uint64_t rbar[2];
     __shared__ double red[kWarps * 8];
 
     copy_model_to_smem(&P, Pg);
@@ -180,6 +216,9 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn;
+    const bool ring = COLD && P.w_ring;          // wide models: weights through the TMA ring (ude_ring.cuh)
+    WRing wr;
+    if (ring) ring_setup(wr, P, smem, rbar, a.wpacked);
     uint32_t wphase = 0;
     const float* Wp = a.wpacked;
     if (SMEM_W) {
@@ -224,7 +263,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
         }
         load_y0_tile(P, smem, a_y0, b0, nvalid, true, P.hoist != 0);
         __syncthreads();
-        hoist_c0(P, a_wpacked, smem, warp, lane);              // constant part of both first layers, once per tile
+        if (ring) hoist_c0_ring(P, a_wpacked, smem, warp, lane, 0u);
+        else hoist_c0(P, a_wpacked, smem, warp, lane);          // constant part of both first layers, once per tile
         // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
@@ -245,7 +285,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
             int j_next = j;
 #pragma unroll 1
             for (int stage = 0; stage < 4; ++stage) {
-                rhs_forward_layers(P, Wp, smem, warp, lane);
+                if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, 0u);
+                else rhs_forward_layers(P, Wp, smem, warp, lane);
                 UDE_PROF_DECL;
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
                     const int r = idx >> P.tb_shift, b = idx & (TB - 1);
@@ -254,23 +295,33 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
                     rhs_tail(P, smem, r, b, valid, side, f);
                     float* X = smem + P.off_X + (3 * r) * TBP + b;
                     float* tp = a_tape ? a_tape + ((long long)(n * 4 + stage) * tape_stage + (long long)(3 * r) * B + b0 + b) : nullptr;
-                    float xn[3];
+                    // All state loads of the task first, then the stores: with the state rows in the CTA's global scratch
+                    // (wide models) a store followed by a load the compiler cannot prove disjoint costs one L2 round trip each.
+                    float xn[3], yv[3], k1v[3], k2v[3], k3v[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        const float y = SY[row];
+                        yv[c] = SY[row];
+                        k1v[c] = stage >= 1 ? SK1[row] : 0.f;
+                        k2v[c] = stage >= 2 ? SK2[row] : 0.f;
+                        k3v[c] = stage >= 3 ? SK3[row] : 0.f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int row = (3 * r + c) * TBP + b;
+                        const float y = yv[c];
                         if (tp && valid) tp[(long long)c * B] = X[c * TBP];     // stage input x_{stage+1}
                         if (stage == 0) {
                             SK1[row] = f[c];
                             xn[c] = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f[c]), 1.0f / 3.0f));
                         } else if (stage == 1) {
                             SK2[row] = f[c];
-                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f[c], __fmul_rn(SK1[row], 1.0f / 3.0f))));
+                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f[c], __fmul_rn(k1v[c], 1.0f / 3.0f))));
                         } else if (stage == 2) {
                             SK3[row] = f[c];
-                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(SK1[row], SK2[row]), f[c])));
+                            xn[c] = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(k1v[c], k2v[c]), f[c])));
                         } else {
-                            const float s = __fadd_rn(__fadd_rn(SK1[row], __fmul_rn(3.0f, __fadd_rn(SK2[row], SK3[row]))), f[c]);
+                            const float s = __fadd_rn(__fadd_rn(k1v[c], __fmul_rn(3.0f, __fadd_rn(k2v[c], k3v[c]))), f[c]);
                             xn[c] = __fadd_rn(y, __fmul_rn(__fmul_rn(s, dt), 0.125f));
                         }
                     }
@@ -287,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
                                     const float w = __ldg(a.g.out_w + jj);
 #pragma unroll
                                     for (int c = 0; c < 3; ++c) {
-                                        const float y = SY[(3 * r + c) * TBP + b];
+                                        const float y = yv[c];
                                         v[c] = kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(xn[c], y)));
                                     }
                                 }
@@ -321,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
         }
     }
     if (!grouped) side_block_reduce(side, n_evals, red, a.side_partial + (long long)blockIdx.x * 8);
+    if (ring) wr_drain(wr);
 }
 
 // ===================================================================================
@@ -331,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
     extern __shared__ __align__(128) float smem[];
     __shared__ ModelP P;
     __shared__ __align__(8) uint64_t wbar;
+    __shared__ __align__(8) uint64_t rbar[2];
     __shared__ uint32_t tmem_slot;
 
     copy_model_to_smem(&P, Pg);
@@ -338,7 +391,10 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int TB = P.TB, TBP = P.TBP, L = P.L, Dn = P.Dn;
-    // plan of last resort (wide models): the weight-gradient accumulators live in tensor memory for the whole launch
+    const bool ring = COLD && P.w_ring;          // wide models: weights through the TMA ring, c0 / D in tensor memory
+    WRing wr;
+    if (ring) ring_setup(wr, P, smem, rbar, a.wpacked);
+    // plans of last resort (wide models): the weight-gradient accumulators live in tensor memory for the whole launch
     const bool tm_acc = COLD && P.tm_acc;
     uint32_t tmem = 0u;
     if (tm_acc) {
@@ -416,7 +472,9 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
         load_y0_tile(P, smem, a_y0, b0, nvalid, false, P.hoist != 0);     // constants only; the dynamic rows come from the tape
         for (int i = threadIdx.x; i < SS; i += kThreads) LAM[i] = 0.f;
         for (int i = threadIdx.x; i < P.Dn_p * TBP; i += kThreads) GX[i] = 0.f;
-        for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
+        if (ring && P.c0_tm) dl_tm_clear(P, tmem, warp);
+        else
+            for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) DL[i] = 0.f;
         // dL/dy0 starts from the cotangent of output 0 (= y0 itself); the constant components then collect the other
         // outputs' cotangents as they are visited, the live ones are overwritten at the end
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
@@ -427,7 +485,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             }
         }
         __syncthreads();
-        hoist_c0(P, a_wpacked, smem, warp, lane);
+        if (ring) hoist_c0_ring(P, a_wpacked, smem, warp, lane, tmem);
+        else hoist_c0(P, a_wpacked, smem, warp, lane);
 
         int j = a.g.n_out - 1;
         for (int n = n_steps - 1; n >= 0; --n) {
@@ -450,17 +509,22 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                         const int kind = __ldg(a.g.out_kind + jj);
                         const float w = __ldg(a.g.out_w + jj);
                         const float* gp = a_g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
+                        float gl[3];
+                        add_const_cotangent(a_g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L, gl);
 #pragma unroll
                         for (int l = 0; l < 3; ++l) {
-                            const float g = __ldg(gp + l);
+                            const float g = gl[l];
                             if (kind == 1) lam[l] += g;
                             else if (kind == 0) pend[l] += g;
                             else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
                         }
-                        add_const_cotangent(a_g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L);
                     }
                 }
                 const float c8 = dt * 0.125f;
+                float x4[3];          // stage input of stage 4 (loads before the state stores, see the forward kernel)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    x4[c] = valid ? __ldg(a_tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int row = (3 * r + c) * TBP + b;
@@ -470,16 +534,15 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                     KB[2 * SS + row] = 3.f * base;
                     KB[3 * SS + row] = base;
                     LAM[row] = lam[c] + pend[c];    // becomes lambda_n once the four stage VJPs are added
-                    // stage input of stage 4
-                    float* X = smem + P.off_X + (3 * r + c) * TBP + b;
-                    *X = valid ? __ldg(a_tape + (long long)(n * 4 + 3) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                    smem[P.off_X + row] = x4[c];
                 }
             }
             j = j_next;
             __syncthreads();
 #pragma unroll 1
             for (int stage = 3; stage >= 0; --stage) {
-                rhs_forward_layers(P, Wp, smem, warp, lane);
+                if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, tmem);
+                else rhs_forward_layers(P, Wp, smem, warp, lane);
                 UDE_PROF_DECL;
                 // ---- tail VJP: cotangent KB[stage] -> head cotangents (in place) + direct dx
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
@@ -494,30 +557,41 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                 UDE_PROF_WORK_DONE();
                 __syncthreads();
                 UDE_PROF_PHASE_END(20);
-                if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
+                if (ring) rhs_backward_layers_ring(P, wr, smem, smem + P.off_GB, warp, lane, tmem);
+                else if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
                 else rhs_backward_layers<false>(P, Wp, smem, G, warp, lane);
                 UDE_PROF_RESTART();
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
                     const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                     const bool valid = b < nvalid;
+                    // loads first (state rows may live in the CTA's global scratch), then the arithmetic, then the stores
+                    float xbv[3], k0[3], k1[3], k2[3], lm[3], xnext[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const int row = (3 * r + c) * TBP + b;
-                        const int xrow = row;
-                        const float xb = GX[xrow];
+                        xbv[c] = GX[row];
+                        k0[c] = stage >= 1 ? KB[0 * SS + row] : 0.f;
+                        k1[c] = stage >= 2 ? KB[1 * SS + row] : 0.f;
+                        k2[c] = stage >= 3 ? KB[2 * SS + row] : 0.f;
+                        lm[c] = LAM[row];
+                        xnext[c] = (stage > 0 && valid)
+                                       ? __ldg(a_tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const int row = (3 * r + c) * TBP + b;
+                        const float xb = xbv[c];
                         const float u = xb * dt;
                         if (stage == 3) {            // x4 = y + dt*((k1 - k2) + k3)
-                            KB[2 * SS + row] += u; KB[0 * SS + row] += u; KB[1 * SS + row] -= u;
+                            KB[2 * SS + row] = k2[c] + u; KB[0 * SS + row] = k0[c] + u; KB[1 * SS + row] = k1[c] - u;
                         } else if (stage == 2) {     // x3 = y + dt*(k2 - k1/3)
-                            KB[1 * SS + row] += u; KB[0 * SS + row] -= u * (1.0f / 3.0f);
+                            KB[1 * SS + row] = k1[c] + u; KB[0 * SS + row] = k0[c] - u * (1.0f / 3.0f);
                         } else if (stage == 1) {     // x2 = y + (dt*k1)/3
-                            KB[0 * SS + row] += (xb * (1.0f / 3.0f)) * dt;
+                            KB[0 * SS + row] = k0[c] + (xb * (1.0f / 3.0f)) * dt;
                         }
-                        LAM[row] += xb;
-                        // next stage input (stage-1), from the tape
-                        if (stage > 0)
-                            smem[P.off_X + xrow] = valid ? __ldg(a_tape + (long long)(n * 4 + stage - 1) * tape_stage + (long long)(3 * r + c) * B + b0 + b) : 0.f;
+                        LAM[row] = lm[c] + xb;
+                        if (stage > 0) smem[P.off_X + row] = xnext[c];     // next stage input (stage-1), from the tape
                     }
                 }
                 UDE_PROF_WORK_DONE();
@@ -535,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             }
         }
         __syncthreads();
+        if (ring && P.c0_tm) dl_tm_dump(P, smem, P.off_DL, tmem, warp, lane);      // D: tensor memory -> rows behind the constants
         hoist_backward_epilogue(P, a_wpacked, smem, Gslab, a_y0, a_g_y0, b0, nvalid, warp, lane);
         if (grouped && SMEM_G) {
             for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
@@ -549,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
         __syncthreads();
         if (warp == 0) tm_free512(tmem);
     }
+    if (ring) wr_drain(wr);
 }
 
 // ===================================================================================
