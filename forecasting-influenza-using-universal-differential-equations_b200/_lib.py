@@ -54,6 +54,16 @@ class UdePlan(C.Structure):
     ]
 
 
+class UdeReparam(C.Structure):
+    _fields_ = [
+        ("eps", C.c_void_p),
+        ("mean", C.c_void_p),
+        ("std", C.c_void_p),
+        ("n_samples", C.c_int32),
+        ("batch", C.c_int32),
+    ]
+
+
 class UdeDopri5Opts(C.Structure):
     _fields_ = [
         ("rtol", C.c_double),
@@ -128,7 +138,7 @@ _lock = threading.Lock()
 EXPORTS = [
     "ude_abi_version", "ude_strerror", "ude_last_cuda_error", "ude_theta_size", "ude_macs_per_eval", "ude_plan",
     "ude_rk4_grid", "ude_rk4_forward", "ude_rk4_backward", "ude_dopri5_forward", "ude_dopri5_backward",
-    "ude_measure_ffma_tflops", "ude_rk4_path",
+    "ude_measure_ffma_tflops", "ude_rk4_path", "ude_rk4_forward_reparam", "ude_rk4_backward_reparam",
 ]
 
 
@@ -163,6 +173,12 @@ def lib() -> C.CDLL:
         L.ude_rk4_backward.restype = C.c_int
         L.ude_rk4_backward.argtypes = [C.POINTER(UdeDesc), vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                        i64, vp]
+        L.ude_rk4_forward_reparam.restype = C.c_int
+        L.ude_rk4_forward_reparam.argtypes = [C.POINTER(UdeDesc), vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp, vp, vp, vp,
+                                              vp, i64, vp]
+        L.ude_rk4_backward_reparam.restype = C.c_int
+        L.ude_rk4_backward_reparam.argtypes = [C.POINTER(UdeDesc), vp, C.POINTER(UdeReparam), vp, i32, vp, i32, vp, vp, vp, vp, vp,
+                                               vp, vp, vp, vp, vp, i64, vp]
         L.ude_dopri5_forward.restype = C.c_int
         L.ude_dopri5_forward.argtypes = [C.POINTER(UdeDesc), C.POINTER(UdeDopri5Opts), vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, i64, vp]

@@ -32,6 +32,38 @@ struct GridTables {
     const float* out_w;     // [n_out]
 };
 
+// Fused producer of y0: z = eps * std + mean; y0 = [|z0|, |z1|, 1 - (|z0| + |z1|), z2, ...] + 1e-5
+// (lib/models.py:16-24 reparam, the "+ 1e-5" of lib/VAE.py:130; same operations in the same order, so the rows are
+// the bits torch produces).  eps [n_samples, batch, R, L-1] is indexed by the flat trajectory index s * batch + b
+// directly; mean / std [batch, R, L-1] by b = index % batch.  std == nullptr: z = mean (uncertainty=False).
+struct ReparamArgs {
+    const float* eps;
+    const float* mean;
+    const float* std;
+    float* g_z;             // adjoint only: dL/dz [B, R, L-1]
+    int batch;
+};
+// host side: the *_reparam entry points park their arguments here for the launch they forward to (ude_host.cu)
+ReparamArgs& pending_reparam();
+__device__ __forceinline__ float reparam_z(const ReparamArgs& rp, long long traj, int r, int R, int Lm1, int k) {
+    const long long b = traj % rp.batch;
+    const float m = rp.mean[(b * R + r) * Lm1 + k];
+    if (!rp.std) return m;
+    return __fadd_rn(__fmul_rn(rp.eps[(traj * R + r) * Lm1 + k], rp.std[(b * R + r) * Lm1 + k]), m);
+}
+// component l of the y0 row from z (z0, z1 given): l = 0, 1, 2 or 3 + (k - 2)
+__device__ __forceinline__ float reparam_y(float z0, float z1, float zk, int l) {
+    const float a0 = fabsf(z0), a1 = fabsf(z1);
+    const float v = l == 0 ? a0 : (l == 1 ? a1 : (l == 2 ? __fsub_rn(1.0f, __fadd_rn(a0, a1)) : zk));
+    return __fadd_rn(v, 1e-5f);
+}
+// dL/dz row from dL/dy0 row g[0..L): z0, z1 feed |.| and the third component; z_k (k >= 2) is y0[k + 1]
+__device__ __forceinline__ float reparam_gz(float z0, float z1, const float g0, const float g1, const float g2, float gk, int k) {
+    if (k == 0) return (z0 > 0.f ? 1.f : (z0 < 0.f ? -1.f : 0.f)) * (g0 - g2);
+    if (k == 1) return (z1 > 0.f ? 1.f : (z1 < 0.f ? -1.f : 0.f)) * (g1 - g2);
+    return gk;
+}
+
 // ----------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------

@@ -388,6 +388,10 @@ static int n_rbuf_for(int method, bool bwd) { return (method == UDE_METHOD_DOPRI
 }  // namespace ude
 
 namespace ude {
+ReparamArgs& pending_reparam() {
+    static thread_local ReparamArgs rp = {};
+    return rp;
+}
 // tensor-core path, defined in ude_tc_host.cu
 int tc_choose(const UdeDesc* d, TcModel& M);
 void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas);
@@ -704,7 +708,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
             const ModelP& P = gp.Pf;
             pack_theta_kernel<<<dim3(P.n_rate + P.n_aug + 3, desc->n_groups), 256, 0, s>>>(P, theta, gp.wpacked);
             UDE_CUDA(cudaGetLastError());
-            Rk4FwdArgs a;
+            Rk4FwdArgs a{};
             a.wpacked = gp.wpacked;
             a.y0 = y0;
             a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
@@ -754,7 +758,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if ((st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
-    Rk4FwdArgs a;
+    Rk4FwdArgs a{};
     a.wpacked = w.wpacked;
     a.y0 = y0;
     a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
@@ -765,6 +769,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     a.B = desc->batch;
     a.n_groups = 1;
     a.tape_group_floats = 0;
+    a.rp = pending_reparam();
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_FWD(W, C)                                                              \
     do {                                                                                  \
@@ -801,7 +806,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
                 pack_theta_kernel<<<dim3(P.n_rate + P.n_aug + 3, desc->n_groups), 256, 0, s>>>(P, theta, gp.wpacked);
                 UDE_CUDA(cudaGetLastError());
             }
-            Rk4BwdArgs a;
+            Rk4BwdArgs a{};
             a.wpacked = gp.wpacked;
             a.y0 = y0;
             a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
@@ -855,7 +860,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED) && (st = launch_pack(P, theta, w.wpacked, s)) != UDE_OK) return st;
-    Rk4BwdArgs a;
+    Rk4BwdArgs a{};
     a.wpacked = w.wpacked;
     a.y0 = y0;
     a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
@@ -868,6 +873,7 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     a.B = desc->batch;
     a.n_groups = 1;
     a.tape_group_floats = 0;
+    a.rp = pending_reparam();
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_BWD(W, G, C)                                                           \
     do {                                                                                  \
@@ -895,6 +901,39 @@ int ude_debug_read_prof(unsigned long long* out /*[kWarps*32*2]*/) {
     return UDE_OK;
 }
 #endif
+
+static int check_reparam(const UdeDesc* desc, const UdeReparam* rp) {
+    if (!desc || !rp || !rp->mean || (!rp->eps && rp->std) || (rp->eps && !rp->std)) return UDE_ERR_INVALID;
+    if (rp->n_samples < 1 || rp->batch < 1 || (int64_t)rp->n_samples * rp->batch != desc->batch) return UDE_ERR_INVALID;
+    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    return UDE_OK;
+}
+
+int ude_rk4_forward_reparam(const UdeDesc* desc, const float* theta, const UdeReparam* rp, int32_t n_steps, const float* dt,
+                            int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w, float* y_out,
+                            float* tape, double* side, void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_reparam(desc, rp);
+    if (st != UDE_OK) return st;
+    pending_reparam() = ReparamArgs{rp->eps, rp->mean, rp->std, nullptr, rp->batch};
+    st = ude_rk4_forward(desc, theta, /*y0 = output 0, produced by the kernel*/ y_out, n_steps, dt, n_out, out_step, out_kind, out_w,
+                         y_out, tape, side, workspace, workspace_bytes, stream);
+    pending_reparam() = ReparamArgs{};
+    return st;
+}
+
+int ude_rk4_backward_reparam(const UdeDesc* desc, const float* theta, const UdeReparam* rp, const float* y0, int32_t n_steps,
+                             const float* dt, int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                             const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_z, float* g_theta,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_reparam(desc, rp);
+    if (st != UDE_OK) return st;
+    if (!g_z) return UDE_ERR_INVALID;
+    pending_reparam() = ReparamArgs{rp->eps, rp->mean, rp->std, g_z, rp->batch};
+    st = ude_rk4_backward(desc, theta, y0, n_steps, dt, n_out, out_step, out_kind, out_w, tape, g_out, g_side, g_y0, g_theta,
+                          workspace, workspace_bytes, stream);
+    pending_reparam() = ReparamArgs{};
+    return st;
+}
 
 int ude_measure_ffma_tflops(double* tflops, void* stream) {
     if (!tflops) return UDE_ERR_INVALID;

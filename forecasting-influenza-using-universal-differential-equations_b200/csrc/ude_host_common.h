@@ -55,9 +55,19 @@ inline DeviceInfo& device_info() {
     return info[dev];
 }
 
+// Opt in to `bytes` of dynamic shared memory for `kernel`, once per (device, size): repeated launches -- and launches
+// under CUDA-graph capture -- must not touch the function attributes again.
 template <typename K>
 inline int set_smem(K kernel, int bytes) {
+    static int have[kMaxDevices] = {};          // one instance per kernel instantiation
+    static std::mutex mu;
+    int dev = 0;
+    UDE_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return UDE_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(mu);
+    if (bytes <= have[dev]) return UDE_OK;
     UDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    have[dev] = bytes;
     return UDE_OK;
 }
 

@@ -26,6 +26,7 @@ struct Rk4FwdArgs {
     // summation order of G single-set launches (bit-identical results).
     int n_groups;
     long long tape_group_floats;    // distance between the tapes of two groups
+    ReparamArgs rp;                 // rp.mean != nullptr: y0 is PRODUCED here (ude_engine.cuh) and lives in y_out[0]
 };
 
 struct Rk4BwdArgs {
@@ -41,6 +42,7 @@ struct Rk4BwdArgs {
     long long B;
     int n_groups;           // see Rk4FwdArgs
     long long tape_group_floats;
+    ReparamArgs rp;         // rp.mean != nullptr: also write dL/dz (rp.g_z) from the finished dL/dy0 rows
 };
 
 // Ring-mode prologue shared by the four FFMA-engine kernels (COLD variants): barriers, descriptor, first two fetches.
@@ -107,17 +109,48 @@ __device__ __forceinline__ void load_y0_tile(const ModelP& P, float* smem, const
         for (int i = threadIdx.x; i < (P.Dc_p - P.Dc) * TBP; i += kThreads) smem[P.off_XC + P.Dc * TBP + i] = 0.f;
 }
 
+// y0 tile PRODUCED from (eps, mean, std): the rows go to y_out[0] (their home from now on), the live components to X,
+// the constant ones to XC -- same destinations as load_y0_tile.
+__device__ __forceinline__ void reparam_y0_tile(const ModelP& P, float* smem, const ReparamArgs& rp, float* __restrict__ y_out0,
+                                                long long b0, int nvalid, bool consts) {
+    const int TB = P.TB, TBP = P.TBP, L = P.L, Lc = P.L - 3;
+    for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+        const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+        float* X = smem + P.off_X + (3 * r) * TBP + b;
+        float* XC = smem + P.off_XC + (r * Lc) * TBP + b;
+        if (b < nvalid) {
+            const long long traj = b0 + b;
+            const float z0 = reparam_z(rp, traj, r, P.R, L - 1, 0), z1 = reparam_z(rp, traj, r, P.R, L - 1, 1);
+            float* row = y_out0 + (traj * P.R + r) * (long long)L;
+            for (int l = 0; l < L; ++l) {
+                const float y = reparam_y(z0, z1, l >= 3 ? reparam_z(rp, traj, r, P.R, L - 1, l - 1) : 0.f, l);
+                row[l] = y;
+                if (l < 3) X[l * TBP] = y;
+                else if (consts) XC[(l - 3) * TBP] = y;
+            }
+        } else {
+            X[0] = 0.f; X[TBP] = 0.f; X[2 * TBP] = 0.f;
+            if (consts)
+                for (int l = 0; l < Lc; ++l) XC[l * TBP] = 0.f;
+        }
+    }
+    if (consts)
+        for (int i = threadIdx.x; i < (P.Dc_p - P.Dc) * TBP; i += kThreads) smem[P.off_XC + P.Dc * TBP + i] = 0.f;
+}
+
 // Store one output row (r, b): dynamic comps from v[], constants straight from the caller's y0 row (L2-resident).
-__device__ __forceinline__ void store_out_row(const ModelP& P, const float* __restrict__ y0row, float* __restrict__ dst,
-                                              const float (&v)[3]) {
+__device__ __forceinline__ void store_out_row(const ModelP& P, const float* y0row, float* dst, const float (&v)[3]) {
+    // L2 (coherent) loads: with the fused reparam the y0 rows were written by THIS kernel (same thread, earlier)
     const int L = P.L;
     if ((L & 3) == 0) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(y0row));
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(y0row));
         st4(dst, make_float4(v[0], v[1], v[2], a.w));
-        for (int l = 4; l < L; l += 4) st4(dst + l, __ldg(reinterpret_cast<const float4*>(y0row + l)));
+        for (int l = 4; l < L; l += 4) {
+            st4(dst + l, __ldcg(reinterpret_cast<const float4*>(y0row + l)));
+        }
     } else {
         dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
-        for (int l = 3; l < L; ++l) dst[l] = __ldg(y0row + l);
+        for (int l = 3; l < L; ++l) dst[l] = __ldcg(y0row + l);
     }
 }
 
@@ -250,8 +283,9 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
         const long long b0 = (tile - grp * tiles_per_group) * TB;
         const int nvalid = (int)((B - b0) < TB ? (B - b0) : TB);
         // this group's views of the caller's arrays (group-major layouts, include/ude_b200.h)
-        const float* const a_y0 = a.y0 + grp * y0_group;
         float* const a_y_out = a.y_out + grp * out_group;
+        const bool reparam = a.rp.mean != nullptr;             // y0 = y_out[0], produced below
+        const float* const a_y0 = reparam ? a_y_out : a.y0 + grp * y0_group;
         float* const a_tape = a.tape ? a.tape + grp * a.tape_group_floats : nullptr;
         const float* const a_wpacked = a.wpacked + grp * P.n_packed;
         __syncthreads();                                       // previous tile done with X, the ACT rows and the weights
@@ -261,7 +295,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
         } else if (!SMEM_W) {
             Wp = a_wpacked;
         }
-        load_y0_tile(P, smem, a_y0, b0, nvalid, true, P.hoist != 0);
+        if (reparam) reparam_y0_tile(P, smem, a.rp, a_y_out, b0, nvalid, P.hoist != 0);
+        else load_y0_tile(P, smem, a_y0, b0, nvalid, true, P.hoist != 0);
         __syncthreads();
         if (ring) hoist_c0_ring(P, a_wpacked, smem, warp, lane, 0u);
         else hoist_c0(P, a_wpacked, smem, warp, lane);          // constant part of both first layers, once per tile
@@ -611,6 +646,20 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
         __syncthreads();
         if (ring && P.c0_tm) dl_tm_dump(P, smem, P.off_DL, tmem, warp, lane);      // D: tensor memory -> rows behind the constants
         hoist_backward_epilogue(P, a_wpacked, smem, Gslab, a_y0, a_g_y0, b0, nvalid, warp, lane);
+        if (a.rp.mean) {        // fused reparam: dL/dz rows from the finished dL/dy0 rows (same thread wrote them)
+            const int Lm1 = L - 1;
+            for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+                if (b < nvalid) {
+                    const long long traj = b0 + b;
+                    const float* g = a_g_y0 + (traj * P.R + r) * (long long)L;
+                    float* gz = a.rp.g_z + (traj * P.R + r) * (long long)Lm1;
+                    const float z0 = reparam_z(a.rp, traj, r, P.R, Lm1, 0), z1 = reparam_z(a.rp, traj, r, P.R, Lm1, 1);
+                    const float g0 = g[0], g1 = g[1], g2 = g[2];
+                    for (int k = 0; k < Lm1; ++k) gz[k] = reparam_gz(z0, z1, g0, g1, g2, k >= 2 ? g[k + 1] : 0.f, k);
+                }
+            }
+        }
         if (grouped && SMEM_G) {
             for (int i = threadIdx.x; i < P.n_packed_hot; i += kThreads) Gslab[i] = G[i];
         }

@@ -37,6 +37,7 @@ struct TcFwdArgs {
     float* tape;            // [n_steps,4,3R,B] or null (same format as the FFMA path)
     double* side_partial;   // [gridDim.x, 8]
     long long B;
+    ReparamArgs rp;         // rp.mean != nullptr: y0 is produced in the prologue (ude_engine.cuh) and written as output 0
 };
 
 struct TcBwdArgs {
@@ -49,6 +50,7 @@ struct TcBwdArgs {
     float* g_y0;            // [B,R,L]
     float* slabs;           // [gridDim.x, slab_floats], zeroed by the host wrapper
     long long B;
+    ReparamArgs rp;         // rp.mean != nullptr: also dL/dz (rp.g_z) in the epilogue
 };
 
 // ----------------------------------------------------------------------------------
@@ -977,7 +979,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
         float x[D0], y[DN], k1[DN], k2[DN], k3[DN];
 #pragma unroll
         for (int i = 0; i < D0; ++i) x[i] = 0.f;
-        if (valid) {
+        if (valid && a.rp.mean) {                    // fused reparam: this thread's row from (eps, mean, std)
+            static_assert(R == 1, "tensor path: R = 1");
+            const long long traj = b0 + c.t;
+            float* dst = a.y_out + traj * (long long)D0;
+            const float z0 = reparam_z(a.rp, traj, 0, 1, L - 1, 0), z1 = reparam_z(a.rp, traj, 0, 1, L - 1, 1);
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                x[l] = reparam_y(z0, z1, l >= 3 ? reparam_z(a.rp, traj, 0, 1, L - 1, l - 1) : 0.f, l);
+                dst[l] = x[l];
+            }
+        } else if (valid) {
             const float* src = a.y0 + (b0 + c.t) * (long long)D0;
             float* dst = a.y_out + (b0 + c.t) * (long long)D0;          // output 0 = y0 (torchdiffeq: solution[0] = y0)
             if ((D0 & 3) == 0) {
@@ -1600,13 +1612,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         if (valid) {
             const float* gp = a.g_out + (b0 + c.t) * (long long)D0;
             float* dst = a.g_y0 + (b0 + c.t) * (long long)D0;
+            float gy[D0];
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
                     const float g = __ldg(gp + r * L + l);
-                    dst[r * L + l] = (l < 3 ? lam[3 * r + l] : cb[r * L + l]) + g;
+                    gy[r * L + l] = (l < 3 ? lam[3 * r + l] : cb[r * L + l]) + g;
+                    dst[r * L + l] = gy[r * L + l];
                 }
+            if (a.rp.mean) {    // fused reparam: dL/dz row
+                const long long traj = b0 + c.t;
+                float* gz = a.rp.g_z + traj * (long long)(L - 1);
+                const float z0 = reparam_z(a.rp, traj, 0, 1, L - 1, 0), z1 = reparam_z(a.rp, traj, 0, 1, L - 1, 1);
+#pragma unroll
+                for (int k = 0; k < L - 1; ++k) gz[k] = reparam_gz(z0, z1, gy[0], gy[1], gy[2], k >= 2 ? gy[k + 1] : 0.f, k);
+            }
         }
     }
     }

@@ -201,7 +201,7 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     static thread_local TcTable tab_storage;
     TcTable* tab = &tab_storage;
     tc_build_table(M, *tab, false);
-    TcFwdArgs a;
+    TcFwdArgs a{};
     a.blob = w.blob;
     a.y0 = y0;
     a.g = g;
@@ -209,6 +209,7 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     a.tape = tape;
     a.side_partial = w.side_partial;
     a.B = desc->batch;
+    a.rp = pending_reparam();
     int st;
 #define UDE_TC_FWD(RR, LL)                                                                     \
     do {                                                                                       \
@@ -239,7 +240,7 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     static thread_local TcTable tab_storage;
     TcTable* tab = &tab_storage;
     tc_build_table(M, *tab, true);
-    TcBwdArgs a;
+    TcBwdArgs a{};
     a.blob = w.blob;
     a.y0 = y0;
     a.g = g;
@@ -249,6 +250,7 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     a.g_y0 = g_y0;
     a.slabs = w.slabs;
     a.B = desc->batch;
+    a.rp = pending_reparam();
     int st;
 #define UDE_TC_BWD(RR, LL)                                                                     \
     do {                                                                                       \

@@ -196,6 +196,77 @@ class _Rk4Solve(torch.autograd.Function):
         return (g_y0, None, None, None, None, None, *grads)
 
 
+class _Rk4SolveReparam(torch.autograd.Function):
+    """(eps, std, mean, *params) -> (y_out [T, S*b, R, L], side): the y0 rows are produced in the solve's prologue and the
+    adjoint's epilogue hands back dL/dz (include/ude_b200.h UdeReparam)."""
+
+    @staticmethod
+    def forward(ctx, eps, std, mean, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool, *params):
+        L = _lib.lib()
+        dev = eps.device
+        S, b, R, Lm1 = eps.shape
+        B, Ld = S * b, Lm1 + 1
+        desc = info.desc(B)
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
+            theta_c = flat_theta(params)
+            eps_c, std_c, mean_c = eps.detach().contiguous(), std.detach().contiguous(), mean.detach().contiguous()
+            rp = _lib.UdeReparam(eps_c.data_ptr(), mean_c.data_ptr(), std_c.data_ptr(), S, b)
+            y_out = torch.empty((n_out, B, R, Ld), dtype=torch.float32, device=dev)
+            side = torch.empty(8, dtype=torch.float64, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            dt, out_step, out_kind, out_w = tables
+            st = L.ude_rk4_forward_reparam(C.byref(desc), _ptr(theta_c), C.byref(rp), n_steps, _ptr(dt), n_out, _ptr(out_step),
+                                           _ptr(out_kind), _ptr(out_w), _ptr(y_out), _ptr(tape), _ptr(side), _ptr(ws),
+                                           int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward_reparam")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out = info, tables, n_steps, n_out
+        ctx.plan_ws = int(plan.workspace_bytes)
+        empty = torch.empty(0, device=dev)
+        # y0 for the adjoint is output 0 itself (a view: nothing is copied)
+        ctx.save_for_backward(theta_c, eps_c, std_c, mean_c, y_out[0] if need_tape else empty, tape if need_tape else empty,
+                              ws if need_tape else empty)
+        ctx.has_tape = need_tape
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        return y_out, side
+
+    @staticmethod
+    def backward(ctx, g_out, g_side):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_c, eps_c, std_c, mean_c, y0_c, tape, ws = ctx.saved_tensors
+        S, b, R, Lm1 = eps_c.shape
+        dev = eps_c.device
+        desc = ctx.info.desc(S * b)
+        desc.flags |= _lib.FLAG_WEIGHTS_PACKED
+        with torch.cuda.device(dev):
+            if g_out is None:
+                g_out = torch.zeros((ctx.n_out, S * b, R, Lm1 + 1), dtype=torch.float32, device=dev)
+            g_out = g_out.contiguous().float()
+            gs = g_side[:5].to(torch.float32).contiguous() if g_side is not None else None
+            g_y0 = torch.empty((S * b, R, Lm1 + 1), dtype=torch.float32, device=dev)
+            g_z = torch.empty((S, b, R, Lm1), dtype=torch.float32, device=dev)
+            g_theta = torch.empty(theta_c.numel(), dtype=torch.float32, device=dev)
+            rp = _lib.UdeReparam(eps_c.data_ptr(), mean_c.data_ptr(), std_c.data_ptr(), S, b)
+            dt, out_step, out_kind, out_w = ctx.tables
+            st = L.ude_rk4_backward_reparam(C.byref(desc), _ptr(theta_c), C.byref(rp), _ptr(y0_c), ctx.n_steps, _ptr(dt), ctx.n_out,
+                                            _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(tape), _ptr(g_out), _ptr(gs),
+                                            _ptr(g_y0), _ptr(g_z), _ptr(g_theta), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward_reparam")
+        # the sample-axis sums (tiny next to the solve): z = eps * std + mean
+        g_eps = g_z * std_c if ctx.needs_input_grad[0] else None
+        g_std = (g_z * eps_c).sum(0) if ctx.needs_input_grad[1] else None
+        g_mean = g_z.sum(0) if ctx.needs_input_grad[2] else None
+        grads, off = [], 0
+        for shape, n in ctx.param_meta:
+            grads.append(g_theta[off:off + n].view(shape))
+            off += n
+        return (g_eps, g_std, g_mean, None, None, None, None, None, *grads)
+
+
 class _Rk4SolveGroups(torch.autograd.Function):
     """G independent weight sets in one call (C ABI ``n_groups = G``, group-major layouts):
     (theta [G, n_theta], y0 [G, B_g, R, L]) -> (y_out [G, T, B_g, R, L], side [G, 8] fp64)."""
@@ -332,6 +403,45 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     params = [p for l in info.linears() for p in (l.weight, l.bias)]
     need_tape = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
     y_out, side = _Rk4Solve.apply(y0, info, tables, n_steps, int(t.numel()), need_tape, *params)
+    if group is not None:
+        from .dist import all_reduce_side
+        side = all_reduce_side(side, None if group is True else group)
+    install_side_channels(func, info, side)
+    return y_out
+
+
+def odeint_reparam(func, eps, std, mean, t, *, method="rk4", options=None):
+    """``odeint(func, reparam(eps, std, mean, n_samples, batch) + 1e-5, t, method='rk4', options=...)`` with the producer of
+    y0 fused into the solve (lib/models.py:16-24, lib/VAE.py:120,130,137 -- SURVEY 8(f1)): the ``[n_samples * batch, R, L]``
+    initial state is never materialised by torch (it is output 0 of the solve), and ``loss.backward()`` returns the
+    gradients of ``mean`` / ``std`` (/ ``eps``) straight from the adjoint kernel's dL/dz rows.
+
+    eps ``[n_samples, batch, R, L-1]``, std / mean ``[batch, R, L-1]`` (the encoder's outputs).  Returns ``[len(t),
+    n_samples * batch, R, L]`` with flat index ``s * batch + b`` like reparam's reshape."""
+    if method != "rk4":
+        raise NotImplementedError("the fused reparam prologue implements the reference's method, rk4")
+    if eps.dim() != 4 or mean.shape != eps.shape[1:] or std.shape != eps.shape[1:]:
+        raise ValueError("eps must be [n_samples, batch, R, L-1] and std / mean [batch, R, L-1]")
+    info = describe_func(func)
+    if eps.shape[2] != info.n_regions or eps.shape[3] + 1 != info.latent_dim:
+        raise ValueError(f"eps must be [n_samples, batch, {info.n_regions}, {info.latent_dim - 1}]")
+    for x in (eps, std, mean):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("the fused UDE solver runs on fp32 CUDA tensors only; there is no CPU fallback")
+    options = {} if options is None else dict(options)
+    group = options.pop("process_group", None)
+    info.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)
+    unknown = set(options) - {"step_size"}
+    if unknown:
+        raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
+    t_cpu = t.detach().to("cpu")
+    if t.dim() != 1 or t.numel() < 2 or not bool((t_cpu[1:] > t_cpu[:-1]).all()):
+        raise ValueError("t must be a one dimensional, strictly increasing tensor")
+    (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), eps.device)
+    params = [p for l in info.linears() for p in (l.weight, l.bias)]
+    need_tape = torch.is_grad_enabled() and (eps.requires_grad or std.requires_grad or mean.requires_grad or
+                                             any(p.requires_grad for p in params))
+    y_out, side = _Rk4SolveReparam.apply(eps, std, mean, info, tables, n_steps, int(t.numel()), need_tape, *params)
     if group is not None:
         from .dist import all_reduce_side
         side = all_reduce_side(side, None if group is True else group)

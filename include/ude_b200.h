@@ -183,6 +183,36 @@ int ude_rk4_backward(const UdeDesc* desc,
                      float* g_y0 /*dev [B,R,L]*/, float* g_theta /*dev [G,n_theta]*/,
                      void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
 
+/*
+ * Fused producer of y0: the caller of the path builds the initial state element-wise from the
+ * encoder's (mean, std) and a normal draw,
+ *     z  = eps * std + mean;  y0 = [|z0|, |z1|, 1 - (|z0| + |z1|), z2, ...] + 1e-5
+ * (/root/reference/lib/models.py:16-24 reparam, /root/reference/lib/VAE.py:120,130).  The *_reparam entry points do that
+ * in the solve's prologue (the rows land in y_out[0], which IS y0) and, in the adjoint's epilogue, turn dL/dy0 into
+ * dL/dz -- the sample-axis sums dL/dmean = sum_s dL/dz, dL/dstd = sum_s dL/dz * eps stay with the caller.
+ * Trajectory index = s * batch + b, as reparam's reshape produces it (lib/models.py:23).  rk4, one weight set.
+ */
+typedef struct UdeReparam {
+    const float* eps;           /* dev [n_samples, batch, R, L-1]; NULL together with std: z = mean (uncertainty=False) */
+    const float* mean;          /* dev [batch, R, L-1]                                                                  */
+    const float* std;           /* dev [batch, R, L-1]                                                                  */
+    int32_t n_samples, batch;   /* n_samples * batch == desc->batch                                                     */
+} UdeReparam;
+
+int ude_rk4_forward_reparam(const UdeDesc* desc, const float* theta /*dev*/, const UdeReparam* rp,
+                            int32_t n_steps, const float* dt /*dev*/, int32_t n_out, const int32_t* out_step /*dev*/,
+                            const int32_t* out_kind /*dev*/, const float* out_w /*dev*/,
+                            float* y_out /*dev [n_out,B,R,L]; y_out[0] = y0*/, float* tape /*dev | NULL*/, double* side /*dev*/,
+                            void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+/* y0 = the forward call's y_out[0]; g_y0 [B,R,L] is written as well (dL/dy0); g_z dev [B,R,L-1] */
+int ude_rk4_backward_reparam(const UdeDesc* desc, const float* theta /*dev*/, const UdeReparam* rp, const float* y0 /*dev*/,
+                             int32_t n_steps, const float* dt /*dev*/, int32_t n_out, const int32_t* out_step /*dev*/,
+                             const int32_t* out_kind /*dev*/, const float* out_w /*dev*/, const float* tape /*dev*/,
+                             const float* g_out /*dev*/, const float* g_side /*dev | NULL*/, float* g_y0 /*dev*/,
+                             float* g_z /*dev*/, float* g_theta /*dev*/,
+                             void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
 /* Controller options of torchdiffeq's RKAdaptiveStepsizeODESolver. */
 typedef struct UdeDopri5Opts {
     double  rtol, atol;
