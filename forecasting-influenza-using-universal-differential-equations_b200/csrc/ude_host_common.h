@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 
 #include "../../include/ude_b200.h"
@@ -55,19 +56,22 @@ inline DeviceInfo& device_info() {
     return info[dev];
 }
 
-// Opt in to `bytes` of dynamic shared memory for `kernel`, once per (device, size): repeated launches -- and launches
-// under CUDA-graph capture -- must not touch the function attributes again.
+// Opt in to `bytes` of dynamic shared memory for `kernel`, once per (kernel, device, size): repeated launches -- and
+// launches under CUDA-graph capture -- must not touch the function attributes again.  Keyed by the kernel's ADDRESS:
+// instantiations with the same signature share one template instance of this function.
 template <typename K>
 inline int set_smem(K kernel, int bytes) {
-    static int have[kMaxDevices] = {};          // one instance per kernel instantiation
+    struct Have { int bytes[kMaxDevices] = {}; };
+    static std::map<const void*, Have> have;
     static std::mutex mu;
     int dev = 0;
     UDE_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return UDE_ERR_INVALID;
     std::lock_guard<std::mutex> lock(mu);
-    if (bytes <= have[dev]) return UDE_OK;
+    int& cur = have[(const void*)kernel].bytes[dev];
+    if (bytes <= cur) return UDE_OK;
     UDE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    have[dev] = bytes;
+    cur = bytes;
     return UDE_OK;
 }
 

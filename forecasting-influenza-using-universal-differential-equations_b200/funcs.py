@@ -65,7 +65,10 @@ class _UdeFunc(nn.Module):
     def posterior(self) -> Normal:
         rows = torch.stack(self.params).reshape(-1, 2)
         self.params = []
-        return Normal(rows.mean(0), rows.std(0))
+        # Argument validation reads a device flag back to the host (a sync, and illegal under CUDA-graph capture);
+        # off while a stream is capturing -- same distribution either way.
+        capturing = rows.is_cuda and torch.cuda.is_current_stream_capturing()
+        return Normal(rows.mean(0), rows.std(0), validate_args=False if capturing else None)
 
     # -- shared math ------------------------------------------------------------------
     def _rates(self, net: nn.ModuleList, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
