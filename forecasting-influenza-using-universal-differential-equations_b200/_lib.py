@@ -64,6 +64,14 @@ class UdeReparam(C.Structure):
     ]
 
 
+class UdeDecoder(C.Structure):
+    _fields_ = [
+        ("weight", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("n_out", C.c_int32),
+    ]
+
+
 class UdeDopri5Opts(C.Structure):
     _fields_ = [
         ("rtol", C.c_double),
@@ -139,6 +147,7 @@ EXPORTS = [
     "ude_abi_version", "ude_strerror", "ude_last_cuda_error", "ude_theta_size", "ude_macs_per_eval", "ude_plan",
     "ude_rk4_grid", "ude_rk4_forward", "ude_rk4_backward", "ude_dopri5_forward", "ude_dopri5_backward",
     "ude_measure_ffma_tflops", "ude_rk4_path", "ude_rk4_forward_reparam", "ude_rk4_backward_reparam",
+    "ude_rk4_forward_decoded", "ude_rk4_backward_decoded",
 ]
 
 
@@ -179,6 +188,12 @@ def lib() -> C.CDLL:
         L.ude_rk4_backward_reparam.restype = C.c_int
         L.ude_rk4_backward_reparam.argtypes = [C.POINTER(UdeDesc), vp, C.POINTER(UdeReparam), vp, i32, vp, i32, vp, vp, vp, vp, vp,
                                                vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_forward_decoded.restype = C.c_int
+        L.ude_rk4_forward_decoded.argtypes = [C.POINTER(UdeDesc), vp, vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp,
+                                              C.POINTER(UdeDecoder), vp, vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_backward_decoded.restype = C.c_int
+        L.ude_rk4_backward_decoded.argtypes = [C.POINTER(UdeDesc), vp, vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp,
+                                               C.POINTER(UdeDecoder), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         L.ude_dopri5_forward.restype = C.c_int
         L.ude_dopri5_forward.argtypes = [C.POINTER(UdeDesc), C.POINTER(UdeDopri5Opts), vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, i64, vp]

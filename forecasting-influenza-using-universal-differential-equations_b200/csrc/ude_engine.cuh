@@ -45,6 +45,33 @@ struct ReparamArgs {
 };
 // host side: the *_reparam entry points park their arguments here for the launch they forward to (ude_host.cu)
 ReparamArgs& pending_reparam();
+
+// Fused consumer of the outputs: instead of the [n_out,B,R,L] trajectories the solve emits what the
+// caller's next ops reduce them to (lib/VAE.py:138,186):
+//     y_pred[j] = Decoder.decoder(latent[j][..., :3]) = Wd . vec(v_j) + bd          lib/models.py:38-51
+//     reg      += latent_init_loss(latent[..., :3]) = sum |v| [v < 0] + |1 - v| [v > 1]   lib/train_functions.py:116-126
+// and a 6-bit mask per (output, trajectory, region) -- bit 2c: v_c < 0, bit 2c+1: v_c > 1 -- from which the adjoint
+// rebuilds d reg / d v.  The adjoint takes dL/dy_pred and dL/dreg, and returns dL/dWd, dL/dbd next to the usual gradients;
+// the output states it needs (for dWd) are stage inputs already on the tape, plus ONE extra record (the final state).
+struct DecArgs {
+    const float* W;         // [n_dec][3R]  (vec(v) index 3r + c: the reference flattens latent[..., :3] row-major)
+    const float* b;         // [n_dec]
+    int n_dec;              // 0: mode off
+    float* y_pred;          // forward: [n_out][B][n_dec]
+    unsigned char* mask;    // [n_out][B][R]
+    const float* g_pred;    // adjoint: [n_out][B][n_dec]
+    float* partial;         // adjoint: per-CTA partial sums [gridDim.x][n_dec * (3R + 1)]  (dW row-major, then db)
+};
+DecArgs& pending_decoded();
+int& decoded_ctas();          // host: CTAs of the last decoded adjoint launch (= partial blocks written)
+__device__ __forceinline__ unsigned reg_mask_bits(float v0, float v1, float v2) {
+    return (v0 < 0.f ? 1u : 0u) | (v0 > 1.f ? 2u : 0u) | (v1 < 0.f ? 4u : 0u) | (v1 > 1.f ? 8u : 0u) | (v2 < 0.f ? 16u : 0u) |
+           (v2 > 1.f ? 32u : 0u);
+}
+// latent_init_loss term of one value (lib/train_functions.py:118-124)
+__device__ __forceinline__ float reg_term(float v) { return (v < 0.f ? fabsf(v) : 0.f) + (v > 1.f ? fabsf(__fsub_rn(1.0f, v)) : 0.f); }
+// d reg / d v from the mask bits of component c
+__device__ __forceinline__ float reg_sign(unsigned m, int c) { return ((m >> (2 * c + 1)) & 1u) ? 1.f : (((m >> (2 * c)) & 1u) ? -1.f : 0.f); }
 __device__ __forceinline__ float reparam_z(const ReparamArgs& rp, long long traj, int r, int R, int Lm1, int k) {
     const long long b = traj % rp.batch;
     const float m = rp.mean[(b * R + r) * Lm1 + k];
@@ -647,8 +674,9 @@ __device__ __forceinline__ void dw_tm_flush(const ModelP& P, const float* gb, fl
 // ----------------------------------------------------------------------------------
 struct SideAcc {
     double sb, sg, sb2, sg2, sf2;
+    double reg;             // decoded mode: sum of latent_init_loss terms over the outputs (side[7])
     long long rows;
-    __device__ __forceinline__ void clear() { sb = sg = sb2 = sg2 = sf2 = 0.0; rows = 0; }
+    __device__ __forceinline__ void clear() { sb = sg = sb2 = sg2 = sf2 = reg = 0.0; rows = 0; }
 };
 
 __device__ __forceinline__ void rhs_tail(const ModelP& P, const float* __restrict__ smem, const int r, const int b,
@@ -728,25 +756,24 @@ __device__ __forceinline__ void rhs_tail_vjp(const ModelP& P, float* __restrict_
 // Block-wide reduction of the side-channel accumulators into out[0..7] (fp64).
 __device__ __forceinline__ void side_block_reduce(const SideAcc& s, double n_evals, double* scratch /*smem [kWarps*8]*/,
                                                   double* out) {
-    double v[6] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows};
+    double v[7] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows, s.reg};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
     }
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = v[i];
+        for (int i = 0; i < 7; ++i) scratch[warp * 8 + i] = v[i];
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 7) {
         double t = 0.0;
         for (int w = 0; w < kWarps; ++w) t += scratch[w * 8 + threadIdx.x];
-        out[threadIdx.x] = t;
+        out[threadIdx.x == 6 ? 7 : threadIdx.x] = t;
     }
-    if (threadIdx.x == 6) out[6] = n_evals;
-    if (threadIdx.x == 7) out[7] = 0.0;
+    if (threadIdx.x == 7) out[6] = n_evals;
     __syncthreads();
 }
 

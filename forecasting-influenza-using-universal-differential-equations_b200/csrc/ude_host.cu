@@ -392,6 +392,16 @@ ReparamArgs& pending_reparam() {
     static thread_local ReparamArgs rp = {};
     return rp;
 }
+// the *_decoded entry points park their arguments here for the launch they forward to; the adjoint launch records how many
+// per-CTA partial blocks it wrote
+DecArgs& pending_decoded() {
+    static thread_local DecArgs d = {};
+    return d;
+}
+int& decoded_ctas() {
+    static thread_local int n = 0;
+    return n;
+}
 // tensor-core path, defined in ude_tc_host.cu
 int tc_choose(const UdeDesc* d, TcModel& M);
 void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas);
@@ -532,7 +542,8 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     TcModel Mt;
     const int path = method == UDE_METHOD_RK4 ? tc_choose(desc, Mt) : 0;
     if (path < 0) return path;
-    if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up((long long)n_steps * 4 * Pf.Dn * desc->batch * 4, 256);
+    // rk4: [n_steps][4 stages][Dn][B] stage inputs + ONE record for the final state (read by the decoded adjoint only)
+    if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up(((long long)n_steps * 4 + 1) * Pf.Dn * desc->batch * 4, 256);
     else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
     plan->tile_traj = Pb.TB;
     plan->n_ctas = n_ctas;
@@ -770,6 +781,7 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     a.n_groups = 1;
     a.tape_group_floats = 0;
     a.rp = pending_reparam();
+    a.dec = pending_decoded();
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_FWD(W, C)                                                              \
     do {                                                                                  \
@@ -874,6 +886,8 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     a.n_groups = 1;
     a.tape_group_floats = 0;
     a.rp = pending_reparam();
+    a.dec = pending_decoded();
+    decoded_ctas() = n_ctas;
     const int smem = P.smem_floats * 4;
 #define UDE_LAUNCH_BWD(W, G, C)                                                           \
     do {                                                                                  \
@@ -933,6 +947,67 @@ int ude_rk4_backward_reparam(const UdeDesc* desc, const float* theta, const UdeR
                           workspace, workspace_bytes, stream);
     pending_reparam() = ReparamArgs{};
     return st;
+}
+
+static int check_decoder(const UdeDesc* desc, const UdeDecoder* dec) {
+    if (!desc || !dec || !dec->weight || !dec->bias || dec->n_out < 1) return UDE_ERR_INVALID;
+    if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+    return UDE_OK;
+}
+// the tensor-core kernels cover the reference's decoder shape at R = 1 (one output per region); anything wider runs the FFMA engine
+static int decoded_desc(const UdeDesc* desc, const UdeDecoder* dec, UdeDesc* d) {
+    *d = *desc;
+    if (dec->n_out != 1) {
+        if (d->flags & UDE_FLAG_FORCE_TENSOR) return UDE_ERR_UNSUPPORTED;
+        d->flags |= UDE_FLAG_FORCE_FFMA;
+    }
+    return UDE_OK;
+}
+
+int ude_rk4_forward_decoded(const UdeDesc* desc, const float* theta, const float* y0, const UdeReparam* rp, int32_t n_steps,
+                            const float* dt, int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                            const UdeDecoder* dec, float* y_pred, uint8_t* out_mask, float* y0_out, float* tape, double* side,
+                            void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_decoder(desc, dec);
+    if (st != UDE_OK) return st;
+    if (!y_pred || !out_mask || (rp ? !y0_out : !y0)) return UDE_ERR_INVALID;
+    UdeDesc d;
+    if ((st = decoded_desc(desc, dec, &d)) != UDE_OK) return st;
+    pending_decoded() = DecArgs{dec->weight, dec->bias, dec->n_out, y_pred, out_mask, nullptr, nullptr};
+    if (rp)
+        st = ude_rk4_forward_reparam(&d, theta, rp, n_steps, dt, n_out, out_step, out_kind, out_w, y0_out, tape, side, workspace,
+                                     workspace_bytes, stream);
+    else    // y_out is not written in decoded mode without the reparam prologue: any non-null pointer passes the checks
+        st = ude_rk4_forward(&d, theta, y0, n_steps, dt, n_out, out_step, out_kind, out_w, const_cast<float*>(y0), tape, side,
+                             workspace, workspace_bytes, stream);
+    pending_decoded() = DecArgs{};
+    return st;
+}
+
+int ude_rk4_backward_decoded(const UdeDesc* desc, const float* theta, const float* y0, const UdeReparam* rp, int32_t n_steps,
+                             const float* dt, int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                             const UdeDecoder* dec, const float* tape, const uint8_t* out_mask, const float* g_pred,
+                             const float* g_side, float* g_y0, float* g_z, float* g_theta, float* g_dec, float* dec_partial,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_decoder(desc, dec);
+    if (st != UDE_OK) return st;
+    if (!out_mask || !g_pred || !g_dec || !dec_partial || !y0) return UDE_ERR_INVALID;
+    UdeDesc d;
+    if ((st = decoded_desc(desc, dec, &d)) != UDE_OK) return st;
+    pending_decoded() = DecArgs{dec->weight, dec->bias, dec->n_out, nullptr, const_cast<uint8_t*>(out_mask), g_pred, dec_partial};
+    decoded_ctas() = 0;
+    if (rp)
+        st = ude_rk4_backward_reparam(&d, theta, rp, y0, n_steps, dt, n_out, out_step, out_kind, out_w, tape, /*g_out unused*/ g_pred,
+                                      g_side, g_y0, g_z, g_theta, workspace, workspace_bytes, stream);
+    else
+        st = ude_rk4_backward(&d, theta, y0, n_steps, dt, n_out, out_step, out_kind, out_w, tape, /*g_out unused*/ g_pred, g_side,
+                              g_y0, g_theta, workspace, workspace_bytes, stream);
+    pending_decoded() = DecArgs{};
+    if (st != UDE_OK) return st;
+    const int n = dec->n_out * (3 * desc->n_regions + 1);
+    reduce_dec_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dec_partial, decoded_ctas(), n, g_dec);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
 }
 
 int ude_measure_ffma_tflops(double* tflops, void* stream) {

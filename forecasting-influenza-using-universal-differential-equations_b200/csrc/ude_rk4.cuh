@@ -27,6 +27,8 @@ struct Rk4FwdArgs {
     int n_groups;
     long long tape_group_floats;    // distance between the tapes of two groups
     ReparamArgs rp;                 // rp.mean != nullptr: y0 is PRODUCED here (ude_engine.cuh) and lives in y_out[0]
+    DecArgs dec;                    // dec.n_dec > 0: decoded outputs (ude_engine.cuh DecArgs); y_out then holds row 0 only,
+                                    // and the tape gets one extra record (index 4 * n_steps): the final state
 };
 
 struct Rk4BwdArgs {
@@ -43,6 +45,7 @@ struct Rk4BwdArgs {
     int n_groups;           // see Rk4FwdArgs
     long long tape_group_floats;
     ReparamArgs rp;         // rp.mean != nullptr: also write dL/dz (rp.g_z) from the finished dL/dy0 rows
+    DecArgs dec;            // dec.n_dec > 0: cotangents arrive as dL/dy_pred [n_out,B,n_dec] + g_side[5] = dL/dreg (g_out unused)
 };
 
 // Ring-mode prologue shared by the four FFMA-engine kernels (COLD variants): barriers, descriptor, first two fetches.
@@ -151,6 +154,80 @@ __device__ __forceinline__ void store_out_row(const ModelP& P, const float* y0ro
     } else {
         dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
         for (int l = 3; l < L; ++l) dst[l] = __ldcg(y0row + l);
+    }
+}
+
+// ---- decoded outputs (ude_engine.cuh DecArgs) ----------------------------------------------------------------------
+// Live value (row k, trajectory b) of output jj: the grid state after the step (kind 1, rows X), before it (kind 0,
+// rows SY) or torchdiffeq's linear interpolation between the two (kind 2) -- the arithmetic of the plain output store.
+__device__ __forceinline__ float out_value(const float* __restrict__ XN, const float* __restrict__ SY, int at, int kind, float w) {
+    if (kind == 1) return XN[at];
+    const float y = SY[at];
+    return kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(XN[at], y)));
+}
+// y_pred[jj] = Wd . v + bd for the tile, the reg sum and the sign mask.  Pre: XN (and SY) rows synced.  No sync inside.
+__device__ __forceinline__ void decode_output(const ModelP& P, const DecArgs& d, const float* __restrict__ XN, const float* __restrict__ SY,
+                                              int jj, int kind, float w, long long B, long long b0, int nvalid, SideAcc& side) {
+    const int TB = P.TB, TBP = P.TBP, K = P.Dn;
+    for (int idx = threadIdx.x; idx < d.n_dec * TB; idx += kThreads) {
+        const int o = idx >> P.tb_shift, b = idx & (TB - 1);
+        if (b >= nvalid) continue;
+        const float* __restrict__ wrow = d.W + (long long)o * K;
+        float acc = __ldg(d.b + o);
+        for (int k = 0; k < K; ++k) acc = fmaf(__ldg(wrow + k), out_value(XN, SY, k * TBP + b, kind, w), acc);
+        d.y_pred[((long long)jj * B + b0 + b) * d.n_dec + o] = acc;
+    }
+    for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+        const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+        if (b >= nvalid) continue;
+        const float v0 = out_value(XN, SY, (3 * r) * TBP + b, kind, w), v1 = out_value(XN, SY, (3 * r + 1) * TBP + b, kind, w),
+                    v2 = out_value(XN, SY, (3 * r + 2) * TBP + b, kind, w);
+        d.mask[((long long)jj * B + b0 + b) * P.R + r] = (unsigned char)reg_mask_bits(v0, v1, v2);
+        side.reg += (double)reg_term(v0) + (double)reg_term(v1) + (double)reg_term(v2);
+    }
+}
+
+// Adjoint of decode_output, cotangent side: dL/dv_c (c < 3) of region r of one trajectory for output jj.
+__device__ __forceinline__ void dec_cotangent(const ModelP& P, const DecArgs& d, float g_reg, int jj, long long B, long long traj, int r,
+                                              float (&gl)[3]) {
+    const float* __restrict__ gp = d.g_pred + ((long long)jj * B + traj) * d.n_dec;
+    const unsigned m = d.mask[((long long)jj * B + traj) * P.R + r];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    for (int o = 0; o < d.n_dec; ++o) {
+        const float g = __ldg(gp + o);
+        const float* __restrict__ wv = d.W + (long long)o * P.Dn + 3 * r;
+        g0 = fmaf(__ldg(wv), g, g0);
+        g1 = fmaf(__ldg(wv + 1), g, g1);
+        g2 = fmaf(__ldg(wv + 2), g, g2);
+    }
+    gl[0] = fmaf(g_reg, reg_sign(m, 0), g0);
+    gl[1] = fmaf(g_reg, reg_sign(m, 1), g1);
+    gl[2] = fmaf(g_reg, reg_sign(m, 2), g2);
+}
+// Adjoint of decode_output, parameter side: partial[o * 3R + k] += sum_b g_pred[jj][b][o] * v_k(b), partial[n_dec * 3R + o] +=
+// sum_b g_pred[jj][b][o].  Every entry has ONE owning thread per CTA (fixed order: bit-reproducible).  v: rows XN hold the
+// state after the step; the state before it (kinds 0 / 2) is the step's first stage input on the tape (yn, global).
+__device__ __forceinline__ void dec_param_grad(const ModelP& P, const DecArgs& d, float* __restrict__ partial, const float* __restrict__ XN,
+                                               const float* __restrict__ yn, int jj, int kind, float w, long long B, long long b0, int nvalid) {
+    const int K = P.Dn, TBP = P.TBP, nw = d.n_dec * K;
+    const float* __restrict__ gp = d.g_pred + ((long long)jj * B + b0) * d.n_dec;
+    for (int idx = threadIdx.x; idx < nw + d.n_dec; idx += kThreads) {
+        float acc = 0.f;
+        if (idx < nw) {
+            const int o = idx / K, k = idx - o * K;
+            for (int b = 0; b < nvalid; ++b) {
+                float v = XN[k * TBP + b];
+                if (kind != 1) {
+                    const float y = __ldg(yn + (long long)k * B + b0 + b);
+                    v = kind == 0 ? y : __fadd_rn(y, __fmul_rn(w, __fsub_rn(v, y)));
+                }
+                acc = fmaf(__ldg(gp + (long long)b * d.n_dec + o), v, acc);
+            }
+        } else {
+            const int o = idx - nw;
+            for (int b = 0; b < nvalid; ++b) acc += __ldg(gp + (long long)b * d.n_dec + o);
+        }
+        partial[idx] += acc;
     }
 }
 
@@ -277,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
     const bool grouped = a.n_groups > 1;
     long long g_cur = 0;
     const long long out_group = (long long)a.g.n_out * B * P.R * L, y0_group = B * P.R * L;
+    const bool decoded = a.dec.n_dec > 0;      // outputs leave as y_pred / reg / mask (single weight set)
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long grp = grouped ? tile / tiles_per_group : 0;
@@ -308,11 +386,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
             SY[(3 * r + 0) * TBP + b] = v[0];
             SY[(3 * r + 1) * TBP + b] = v[1];
             SY[(3 * r + 2) * TBP + b] = v[2];
-            if (b < nvalid) {
+            if (b < nvalid && !decoded) {
                 const long long row = ((b0 + b) * P.R + r) * (long long)L;
                 store_out_row(P, a_y0 + row, a_y_out + row, v);
             }
         }
+        if (decoded) decode_output(P, a.dec, smem + P.off_X, SY, 0, 1, 0.f, B, b0, nvalid, side);     // output 0 = y0 (X rows, synced above)
         // (each thread only re-reads rows it wrote itself below, no sync needed here)
         int j = 1;
         for (int n = 0; n < a.g.n_steps; ++n) {
@@ -364,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
                         // outputs that fall into (t_n, t_{n+1}]  (FixedGridODESolver.integrate)
                         int jj = j;
                         while (jj < a.g.n_out && __ldg(a.g.out_step + jj) == n) {
-                            if (valid) {
+                            if (valid && !decoded) {
                                 const int kind = __ldg(a.g.out_kind + jj);
                                 float v[3];
                                 if (kind == 1) {
@@ -383,8 +462,10 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
                             ++jj;
                         }
                         j_next = jj;
+                        if (!decoded) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = xn[c];
+                            for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = xn[c];
+                        }
                     }
 #pragma unroll
                     for (int c = 0; c < 3; ++c) X[c * TBP] = xn[c];
@@ -398,6 +479,23 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
                 UDE_PROF_WORK_DONE();
                 __syncthreads();
                 UDE_PROF_PHASE_END(6);
+                if (stage == 3 && decoded) {
+                    // X = y_{n+1}, SY still = y_n: decode the outputs of (t_n, t_{n+1}], then advance SY
+                    for (int jj = j; jj < j_next; ++jj)
+                        decode_output(P, a.dec, smem + P.off_X, SY, jj, __ldg(a.g.out_kind + jj), __ldg(a.g.out_w + jj), B, b0, nvalid, side);
+                    if (a_tape && n == a.g.n_steps - 1) {      // the extra tape record: the final state
+                        for (int idx = threadIdx.x; idx < Dn * TB; idx += kThreads) {
+                            const int k = idx >> P.tb_shift, b = idx & (TB - 1);
+                            if (b < nvalid) a_tape[(long long)(4 * a.g.n_steps) * tape_stage + (long long)k * B + b0 + b] = smem[P.off_X + k * TBP + b];
+                        }
+                    }
+                    __syncthreads();
+                    for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                        const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) SY[(3 * r + c) * TBP + b] = smem[P.off_X + (3 * r + c) * TBP + b];
+                    }
+                }
             }
             j = j_next;
         }
@@ -462,6 +560,11 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
+    const bool decoded = a.dec.n_dec > 0;      // cotangents arrive as dL/dy_pred + dL/dreg (ude_engine.cuh DecArgs)
+    const float g_reg = (decoded && a.g_side) ? __ldg(a.g_side + 5) : 0.f;
+    float* const dpart = decoded ? a.dec.partial + (long long)blockIdx.x * (a.dec.n_dec * (P.Dn + 1)) : nullptr;
+    if (decoded)
+        for (int i = threadIdx.x; i < a.dec.n_dec * (P.Dn + 1); i += kThreads) dpart[i] = 0.f;      // own entries only, see dec_param_grad
 
     const int SS = P.Dn_p * TBP;
     float* SB = COLD ? a.cold + (long long)blockIdx.x * P.cold_floats : smem;
@@ -516,7 +619,13 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
                 const long long row = ((b0 + b) * P.R + r) * (long long)L;
-                for (int l = 0; l < L; ++l) a_g_y0[row + l] = __ldg(a_g_out + row + l);
+                for (int l = 0; l < L; ++l) a_g_y0[row + l] = decoded ? 0.f : __ldg(a_g_out + row + l);
+            }
+        }
+        if (decoded) {      // X := the final state (the tape's extra record): the outputs of the last step need it
+            for (int idx = threadIdx.x; idx < Dn * TB; idx += kThreads) {
+                const int k = idx >> P.tb_shift, b = idx & (TB - 1);
+                smem[P.off_X + k * TBP + b] = b < nvalid ? __ldg(a_tape + (long long)(4 * n_steps) * tape_stage + (long long)k * B + b0 + b) : 0.f;
             }
         }
         __syncthreads();
@@ -533,6 +642,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                 while (jj >= 1 && __ldg(a.g.out_step + jj) == n) --jj;
                 j_next = jj;
             }
+            if (decoded) {      // X still holds y_{n+1} (stage-1 input of step n+1, or the final record): decoder gradients first
+                for (int jj = j; jj > j_next; --jj)
+                    dec_param_grad(P, a.dec, dpart, smem + P.off_X, a_tape + (long long)(n * 4) * tape_stage, jj, __ldg(a.g.out_kind + jj),
+                                   __ldg(a.g.out_w + jj), B, b0, nvalid);
+                __syncthreads();
+            }
             for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
                 const int r = idx >> P.tb_shift, b = idx & (TB - 1);
                 const bool valid = b < nvalid;
@@ -543,9 +658,13 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                     for (int jj = j; jj > j_next; --jj) {
                         const int kind = __ldg(a.g.out_kind + jj);
                         const float w = __ldg(a.g.out_w + jj);
-                        const float* gp = a_g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
                         float gl[3];
-                        add_const_cotangent(a_g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L, gl);
+                        if (decoded) {
+                            dec_cotangent(P, a.dec, g_reg, jj, B, b0 + b, r, gl);
+                        } else {
+                            const float* gp = a_g_out + (((long long)jj * B + b0 + b) * P.R + r) * (long long)L;
+                            add_const_cotangent(a_g_y0 + ((b0 + b) * P.R + r) * (long long)L, gp, L, gl);
+                        }
 #pragma unroll
                         for (int l = 0; l < 3; ++l) {
                             const float g = gl[l];
@@ -635,12 +754,20 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             }
         }
         // ---- output 0 (= y0 itself, already in g_y0) + lambda_0; then the hoisted constants' share
+        if (decoded) dec_param_grad(P, a.dec, dpart, smem + P.off_X, nullptr, 0, 1, 0.f, B, b0, nvalid);      // X = stage-1 input of step 0 = y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
             if (b < nvalid) {
                 float* dst = a_g_y0 + ((b0 + b) * P.R + r) * (long long)L;
+                if (decoded) {
+                    float gl[3];
+                    dec_cotangent(P, a.dec, g_reg, 0, B, b0 + b, r, gl);
 #pragma unroll
-                for (int l = 0; l < 3; ++l) dst[l] = LAM[(3 * r + l) * TBP + b] + dst[l];
+                    for (int l = 0; l < 3; ++l) dst[l] = LAM[(3 * r + l) * TBP + b] + gl[l];
+                } else {
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) dst[l] = LAM[(3 * r + l) * TBP + b] + dst[l];
+                }
             }
         }
         __syncthreads();
@@ -760,6 +887,15 @@ __global__ void reduce_side_kernel(const double* __restrict__ partial_all, int n
     for (int c = 0; c < n_parts; ++c) s += partial[c * 8 + i];
     if (i == 6) s = partial[6];   // RHS evaluations per trajectory: identical in every CTA
     side[i] = s;
+}
+
+// decoder gradients: g_dec[e] = sum over the CTAs' partial blocks (fixed order)
+__global__ void reduce_dec_kernel(const float* __restrict__ partial, int n_parts, int n, float* __restrict__ g_dec) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s = 0.f;
+    for (int c = 0; c < n_parts; ++c) s += partial[(long long)c * n + e];
+    g_dec[e] = s;
 }
 
 // Register-resident FFMA chains: the measured fp32 roofline denominator.

@@ -38,6 +38,7 @@ struct TcFwdArgs {
     double* side_partial;   // [gridDim.x, 8]
     long long B;
     ReparamArgs rp;         // rp.mean != nullptr: y0 is produced in the prologue (ude_engine.cuh) and written as output 0
+    DecArgs dec;            // dec.n_dec == 1: decoded outputs (ude_engine.cuh DecArgs; the tensor path is R = 1, one decoder output)
 };
 
 struct TcBwdArgs {
@@ -51,6 +52,7 @@ struct TcBwdArgs {
     float* slabs;           // [gridDim.x, slab_floats], zeroed by the host wrapper
     long long B;
     ReparamArgs rp;         // rp.mean != nullptr: also dL/dz (rp.g_z) in the epilogue
+    DecArgs dec;            // dec.n_dec == 1: cotangents arrive as dL/dy_pred + g_side[5] = dL/dreg (g_out unused)
 };
 
 // ----------------------------------------------------------------------------------
@@ -847,25 +849,24 @@ __device__ __forceinline__ void tc_tmem_free(uint32_t base) {
 
 // block reduction of the side sums over the 128 trajectory threads (warps 0-3)
 __device__ __forceinline__ void tc_side_reduce(const SideAcc& s, double n_evals, double* scratch /*[8*8]*/, double* out) {
-    double v[6] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows};
+    double v[7] = {s.sb, s.sg, s.sb2, s.sg2, s.sf2, (double)s.rows, s.reg};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
     }
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) scratch[warp * 8 + i] = v[i];
+        for (int i = 0; i < 7; ++i) scratch[warp * 8 + i] = v[i];
     }
     __syncthreads();
-    if (threadIdx.x < 6) {
+    if (threadIdx.x < 7) {
         double t = 0.0;
         for (int w = 0; w < kTcThreads / 32; ++w) t += scratch[w * 8 + threadIdx.x];
-        out[threadIdx.x] = t;
+        out[threadIdx.x == 6 ? 7 : threadIdx.x] = t;
     }
-    if (threadIdx.x == 6) out[6] = n_evals;
-    if (threadIdx.x == 7) out[7] = 0.0;
+    if (threadIdx.x == 7) out[6] = n_evals;
 }
 
 // ----------------------------------------------------------------------------------
@@ -900,6 +901,39 @@ __device__ __forceinline__ void tc_issuer_loop_bwd(const TcModel& M, const TcTab
 // ===================================================================================
 // forward kernel
 // ===================================================================================
+// ---- decoded outputs (ude_engine.cuh DecArgs), tensor path: R = 1, ONE decoder output, thread = trajectory ------------
+__device__ __forceinline__ void tc_decode_store(const DecArgs& d, int jj, long long B, long long traj, float v0, float v1, float v2,
+                                                SideAcc& side) {
+    float acc = __ldg(d.b);
+    acc = fmaf(__ldg(d.W), v0, acc);
+    acc = fmaf(__ldg(d.W + 1), v1, acc);
+    acc = fmaf(__ldg(d.W + 2), v2, acc);
+    d.y_pred[(long long)jj * B + traj] = acc;
+    d.mask[(long long)jj * B + traj] = (unsigned char)reg_mask_bits(v0, v1, v2);
+    side.reg += (double)reg_term(v0) + (double)reg_term(v1) + (double)reg_term(v2);
+}
+// adjoint: cotangent of the three live components of output jj, and the decoder-gradient terms of this trajectory summed over
+// the warp into acc4[warp][0..3] = (dWd0, dWd1, dWd2, dbd)  (fixed shuffle tree: bit-reproducible)
+__device__ __forceinline__ void tc_decode_vjp(const DecArgs& d, float g_reg, int jj, long long B, long long traj, bool valid, float v0, float v1,
+                                              float v2, float (&gl)[3], float* acc4, int lane) {
+    float gp = 0.f;
+    unsigned m = 0u;
+    if (valid) {
+        gp = __ldg(d.g_pred + (long long)jj * B + traj);
+        m = d.mask[(long long)jj * B + traj];
+    }
+    gl[0] = fmaf(g_reg, reg_sign(m, 0), __ldg(d.W) * gp);
+    gl[1] = fmaf(g_reg, reg_sign(m, 1), __ldg(d.W + 1) * gp);
+    gl[2] = fmaf(g_reg, reg_sign(m, 2), __ldg(d.W + 2) * gp);
+    float p[4] = {gp * v0, gp * v1, gp * v2, gp};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p[i] += __shfl_xor_sync(0xffffffffu, p[i], o);
+    }
+    if (lane < 4) acc4[lane] += (lane == 0 ? p[0] : (lane == 1 ? p[1] : (lane == 2 ? p[2] : p[3])));
+}
+
 template <int R, int L>
 __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcFwdArgs a) {
     constexpr int D0 = R * L, DN = 3 * R;
@@ -979,6 +1013,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
         float x[D0], y[DN], k1[DN], k2[DN], k3[DN];
 #pragma unroll
         for (int i = 0; i < D0; ++i) x[i] = 0.f;
+        const bool decoded = a.dec.n_dec > 0;
         if (valid && a.rp.mean) {                    // fused reparam: this thread's row from (eps, mean, std)
             static_assert(R == 1, "tensor path: R = 1");
             const long long traj = b0 + c.t;
@@ -997,13 +1032,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                 for (int i = 0; i < D0; i += 4) {
                     const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
                     x[i] = v.x; x[i + 1] = v.y; x[i + 2] = v.z; x[i + 3] = v.w;
-                    st4(dst + i, v);
+                    if (!decoded) st4(dst + i, v);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < D0; ++i) { x[i] = __ldg(src + i); dst[i] = x[i]; }
+                for (int i = 0; i < D0; ++i) { x[i] = __ldg(src + i); if (!decoded) dst[i] = x[i]; }
             }
         }
+        if (valid && decoded) tc_decode_store(a.dec, 0, B, b0 + c.t, x[0], x[1], x[2], side);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             y[3 * r] = x[r * L]; y[3 * r + 1] = x[r * L + 1]; y[3 * r + 2] = x[r * L + 2];
@@ -1064,7 +1100,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                                         row[r * L + cc] = kind == 1 ? xx : (kind == 0 ? yy : __fadd_rn(yy, __fmul_rn(w, __fsub_rn(xx, yy))));
                                     }
                                 float* dst = a.y_out + ((long long)jj * B + b0 + c.t) * (long long)D0;
-                                if ((D0 & 3) == 0) {
+                                if (decoded) {
+                                    tc_decode_store(a.dec, jj, B, b0 + c.t, row[0], row[1], row[2], side);
+                                } else if ((D0 & 3) == 0) {
 #pragma unroll
                                     for (int i = 0; i < D0; i += 4) st4(dst + i, make_float4(row[i], row[i + 1], row[i + 2], row[i + 3]));
                                 } else {
@@ -1075,6 +1113,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                             ++jj;
                         }
                         j = jj;
+                        if (decoded && valid && a.tape && n == a.g.n_steps - 1) {      // the extra tape record: the final state
+#pragma unroll
+                            for (int i = 0; i < DN; ++i) a.tape[(long long)(4 * a.g.n_steps) * tape_stage + (long long)i * B + b0 + c.t] = xn[i];
+                        }
 #pragma unroll
                         for (int i = 0; i < DN; ++i) y[i] = xn[i];
                     }
@@ -1407,6 +1449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     __shared__ __align__(8) uint64_t mbar2;
     __shared__ __align__(16) TcHeadScratch head_scratch;
     __shared__ uint32_t tmem_slot;
+    __shared__ float dec_acc[4][4];         // decoded mode: per trajectory warp (dWd0, dWd1, dWd2, dbd)
 
     if (threadIdx.x == 0) {
         mbar_init(&wbar, 1);
@@ -1415,6 +1458,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         mbar_init(&mbar2, 1);
         for (int i = 0; i < 8; ++i) mbar_init(&head_scratch.bar[i >> 2][i & 3], kTcSlots > 1 ? kTcSlots - 1 : 1);
     }
+    if (threadIdx.x < 16) dec_acc[threadIdx.x >> 2][threadIdx.x & 3] = 0.f;
     if (threadIdx.x < 32) tc_tmem_alloc<512>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -1464,6 +1508,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
     float* slab = a.slabs + (long long)blockIdx.x * M.slab_floats;
+    const bool decoded = a.dec.n_dec > 0;
+    const float g_reg = (decoded && a.g_side) ? __ldg(a.g_side + 5) : 0.f;
 
     const long long B = a.B;
     const long long n_tiles = (B + kTcTile - 1) / kTcTile;
@@ -1490,6 +1536,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
             const float* src = a.y0 + (b0 + c.t) * (long long)D0;      // constants of x; dynamic comps come from the tape
 #pragma unroll
             for (int i = 0; i < D0; ++i) x[i] = __ldg(src + i);
+            if (decoded) {      // live part := the final state (the tape's extra record): the outputs of the last step need it
+#pragma unroll
+                for (int i = 0; i < DN; ++i) x[i] = __ldg(a.tape + (long long)(4 * n_steps) * tape_stage + (long long)i * B + b0 + c.t);
+            }
         }
         float xt[DN];       // tape prefetch: stage input of the NEXT evaluation to be reversed
 #pragma unroll
@@ -1505,7 +1555,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                 for (int i = 0; i < DN; ++i) pend[i] = 0.f;
                 int jj = j;
                 while (jj >= 1 && __ldg(a.g.out_step + jj) == n) {
-                    if (valid) {
+                    if (decoded) {
+                        if (is_traj) {      // whole warps (shuffle sums inside); x = state after the step, y_n from the tape
+                            const int kind = __ldg(a.g.out_kind + jj);
+                            const float w = __ldg(a.g.out_w + jj);
+                            float v[3] = {x[0], x[1], x[2]}, gl[3];
+                            if (kind != 1 && valid) {
+#pragma unroll
+                                for (int i = 0; i < 3; ++i) {
+                                    const float yy = __ldg(a.tape + (long long)(n * 4) * tape_stage + (long long)i * B + b0 + c.t);
+                                    v[i] = kind == 0 ? yy : __fadd_rn(yy, __fmul_rn(w, __fsub_rn(v[i], yy)));
+                                }
+                            }
+                            tc_decode_vjp(a.dec, g_reg, jj, B, b0 + c.t, valid, v[0], v[1], v[2], gl, dec_acc[warp], c.lane);
+#pragma unroll
+                            for (int l = 0; l < 3; ++l) {
+                                const float g = gl[l];
+                                if (kind == 1) lam[l] += g;
+                                else if (kind == 0) pend[l] += g;
+                                else { const float sg = w * g; lam[l] += sg; pend[l] += g - sg; }
+                            }
+                        }
+                    } else if (valid) {
                         const int kind = __ldg(a.g.out_kind + jj);
                         const float w = __ldg(a.g.out_w + jj);
                         const float* gp = a.g_out + ((long long)jj * B + b0 + c.t) * (long long)D0;
@@ -1609,6 +1680,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
             }
         }
         // ---- output 0 (= y0 itself) and the final store of dL/dy0
+        float g0dec[3] = {0.f, 0.f, 0.f};
+        if (decoded && is_traj) tc_decode_vjp(a.dec, g_reg, 0, B, b0 + c.t, valid, x[0], x[1], x[2], g0dec, dec_acc[warp], c.lane);   // x = y0
         if (valid) {
             const float* gp = a.g_out + (b0 + c.t) * (long long)D0;
             float* dst = a.g_y0 + (b0 + c.t) * (long long)D0;
@@ -1617,7 +1690,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int l = 0; l < L; ++l) {
-                    const float g = __ldg(gp + r * L + l);
+                    const float g = decoded ? (l < 3 ? g0dec[l] : 0.f) : __ldg(gp + r * L + l);
                     gy[r * L + l] = (l < 3 ? lam[3 * r + l] : cb[r * L + l]) + g;
                     dst[r * L + l] = gy[r * L + l];
                 }
@@ -1635,6 +1708,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     tc_prof_dump(c);
     tc_fence_before();
     __syncthreads();
+    if (decoded && threadIdx.x < 4)
+        a.dec.partial[(long long)blockIdx.x * 4 + threadIdx.x] =
+            ((dec_acc[0][threadIdx.x] + dec_acc[1][threadIdx.x]) + dec_acc[2][threadIdx.x]) + dec_acc[3][threadIdx.x];
     if (threadIdx.x < 32) tc_tmem_free<512>(c.tmem);
 }
 

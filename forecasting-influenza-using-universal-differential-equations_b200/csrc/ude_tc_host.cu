@@ -210,6 +210,7 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     a.side_partial = w.side_partial;
     a.B = desc->batch;
     a.rp = pending_reparam();
+    a.dec = pending_decoded();
     int st;
 #define UDE_TC_FWD(RR, LL)                                                                     \
     do {                                                                                       \
@@ -251,6 +252,8 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     a.slabs = w.slabs;
     a.B = desc->batch;
     a.rp = pending_reparam();
+    a.dec = pending_decoded();
+    decoded_ctas() = n_ctas;
     int st;
 #define UDE_TC_BWD(RR, LL)                                                                     \
     do {                                                                                       \

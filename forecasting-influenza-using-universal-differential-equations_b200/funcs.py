@@ -45,6 +45,29 @@ def _run(mods: nn.ModuleList, x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+class Decoder(nn.Module):
+    """The consumer of the solve's outputs, mirror of /root/reference/lib/models.py:26-51: ``Sequential(Flatten,
+    Linear(R * latent_dim, R * input_dim))`` over ``data[..., :latent_dim]`` with ``latent_dim = 3`` when ``Fp=True`` (the
+    reference's setting), N(0, 0.1) weights and zero bias (lib/utils.py:69-73).  Same ``state_dict`` keys (``decoder.1.*``).
+    ``ude_b200.odeint_decoded`` applies it inside the solve's output store."""
+
+    def __init__(self, n_regions, latent_dim, input_dim, Fp=True, device=torch.device("cpu"), dtype=torch.float32, **kwargs):
+        super().__init__()
+        self.Fp = Fp
+        self.n_regions = n_regions
+        self.input_dim = input_dim
+        self.latent_dim = 3 if Fp else latent_dim
+        self.decoder = nn.Sequential(nn.Flatten(), nn.Linear(n_regions * self.latent_dim, n_regions * input_dim)).to(device=device, dtype=dtype)
+        nn.init.normal_(self.decoder[1].weight, mean=0, std=0.1)
+        nn.init.constant_(self.decoder[1].bias, val=0)
+
+    def forward(self, data):
+        data = data[..., :self.latent_dim]
+        shape = data.shape
+        out = self.decoder(data.reshape((-1,) + tuple(shape[2:])))
+        return out.reshape(tuple(shape[:2]) + (-1,))
+
+
 class _UdeFunc(nn.Module):
     """Shared behaviour of the three ODE funcs."""
     ode_type = "?"

@@ -267,6 +267,107 @@ class _Rk4SolveReparam(torch.autograd.Function):
         return (g_eps, g_std, g_mean, None, None, None, None, None, *grads)
 
 
+class _Rk4SolveDecoded(torch.autograd.Function):
+    """(y0 | eps, std, mean; dec_w, dec_b; *params) -> (y_pred [T, B, n_dec], side [8] fp64 with side[7] = the
+    latent_init_loss sum): the decoder and the reg loss are applied where the outputs are produced, the trajectories are
+    never written (include/ude_b200.h UdeDecoder)."""
+
+    @staticmethod
+    def forward(ctx, y0, eps, std, mean, dec_w, dec_b, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool, *params):
+        L = _lib.lib()
+        reparam = y0 is None
+        dev = dec_w.device
+        if reparam:
+            S, b, R, Lm1 = eps.shape
+            B, Ld = S * b, Lm1 + 1
+        else:
+            B, R, Ld = y0.shape
+        n_dec = dec_w.shape[0]
+        desc = info.desc(B)
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
+            theta_c = flat_theta(params)
+            w_c, b_c = dec_w.detach().contiguous(), dec_b.detach().contiguous()
+            dec = _lib.UdeDecoder(w_c.data_ptr(), b_c.data_ptr(), n_dec)
+            rp = None
+            if reparam:
+                eps_c, std_c, mean_c = eps.detach().contiguous(), std.detach().contiguous(), mean.detach().contiguous()
+                rp = _lib.UdeReparam(eps_c.data_ptr(), mean_c.data_ptr(), std_c.data_ptr(), S, b)
+                y0_c = torch.empty((B, R, Ld), dtype=torch.float32, device=dev)      # produced by the prologue
+            else:
+                y0_c = y0.detach().contiguous()
+                eps_c = std_c = mean_c = torch.empty(0, device=dev)
+            y_pred = torch.empty((n_out, B, n_dec), dtype=torch.float32, device=dev)
+            mask = torch.empty((n_out, B, R), dtype=torch.uint8, device=dev)
+            side = torch.empty(8, dtype=torch.float64, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            dt, out_step, out_kind, out_w = tables
+            st = L.ude_rk4_forward_decoded(C.byref(desc), _ptr(theta_c), _ptr(None if reparam else y0_c),
+                                           C.byref(rp) if reparam else None, n_steps, _ptr(dt), n_out, _ptr(out_step),
+                                           _ptr(out_kind), _ptr(out_w), C.byref(dec), _ptr(y_pred), _ptr(mask),
+                                           _ptr(y0_c if reparam else None), _ptr(tape), _ptr(side), _ptr(ws),
+                                           int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward_decoded")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out, ctx.reparam = info, tables, n_steps, n_out, reparam
+        ctx.plan_ws, ctx.n_ctas = int(plan.workspace_bytes), int(plan.n_ctas)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(theta_c, y0_c, eps_c, std_c, mean_c, w_c, b_c, mask if need_tape else empty,
+                              tape if need_tape else empty, ws if need_tape else empty)
+        ctx.has_tape = need_tape
+        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        return y_pred, side
+
+    @staticmethod
+    def backward(ctx, g_pred, g_side):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_c, y0_c, eps_c, std_c, mean_c, w_c, b_c, mask, tape, ws = ctx.saved_tensors
+        dev = w_c.device
+        B, R, Ld = y0_c.shape
+        n_dec = w_c.shape[0]
+        desc = ctx.info.desc(B)
+        desc.flags |= _lib.FLAG_WEIGHTS_PACKED
+        with torch.cuda.device(dev):
+            if g_pred is None:
+                g_pred = torch.zeros((ctx.n_out, B, n_dec), dtype=torch.float32, device=dev)
+            g_pred = g_pred.contiguous().float()
+            gs = None
+            if g_side is not None:      # [0..4]: the usual side sums, [5]: dL/d(reg sum) = dL/dside[7]
+                gs = torch.cat([g_side[:5], g_side[7:8]]).to(torch.float32).contiguous()
+            g_y0 = torch.empty_like(y0_c)
+            g_theta = torch.empty(theta_c.numel(), dtype=torch.float32, device=dev)
+            n_d = n_dec * (3 * R + 1)
+            g_dec = torch.empty(n_d, dtype=torch.float32, device=dev)
+            partial = torch.empty(ctx.n_ctas * n_d, dtype=torch.float32, device=dev)
+            dec = _lib.UdeDecoder(w_c.data_ptr(), b_c.data_ptr(), n_dec)
+            rp, g_z = None, None
+            if ctx.reparam:
+                S, b = eps_c.shape[0], eps_c.shape[1]
+                rp = _lib.UdeReparam(eps_c.data_ptr(), mean_c.data_ptr(), std_c.data_ptr(), S, b)
+                g_z = torch.empty((S, b, R, Ld - 1), dtype=torch.float32, device=dev)
+            dt, out_step, out_kind, out_w = ctx.tables
+            st = L.ude_rk4_backward_decoded(C.byref(desc), _ptr(theta_c), _ptr(y0_c), C.byref(rp) if rp is not None else None,
+                                            ctx.n_steps, _ptr(dt), ctx.n_out, _ptr(out_step), _ptr(out_kind), _ptr(out_w),
+                                            C.byref(dec), _ptr(tape), _ptr(mask), _ptr(g_pred), _ptr(gs), _ptr(g_y0), _ptr(g_z),
+                                            _ptr(g_theta), _ptr(g_dec), _ptr(partial), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward_decoded")
+        g_in = [None, None, None, None]
+        if ctx.reparam:
+            g_in[1] = g_z * std_c if ctx.needs_input_grad[1] else None
+            g_in[2] = (g_z * eps_c).sum(0) if ctx.needs_input_grad[2] else None
+            g_in[3] = g_z.sum(0) if ctx.needs_input_grad[3] else None
+        else:
+            g_in[0] = g_y0
+        grads, off = [], 0
+        for shape, n in ctx.param_meta:
+            grads.append(g_theta[off:off + n].view(shape))
+            off += n
+        return (*g_in, g_dec[:n_dec * 3 * R].view(n_dec, 3 * R), g_dec[n_dec * 3 * R:], None, None, None, None, None, *grads)
+
+
 class _Rk4SolveGroups(torch.autograd.Function):
     """G independent weight sets in one call (C ABI ``n_groups = G``, group-major layouts):
     (theta [G, n_theta], y0 [G, B_g, R, L]) -> (y_out [G, T, B_g, R, L], side [G, 8] fp64)."""
@@ -447,6 +548,76 @@ def odeint_reparam(func, eps, std, mean, t, *, method="rk4", options=None):
         side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
     return y_out
+
+
+def _decoder_linear(decoder) -> torch.nn.Linear:
+    """The nn.Linear(3R, R * input_dim) behind the reference's Decoder (lib/models.py:38-42: Sequential(Flatten, Linear));
+    an nn.Linear is taken as is."""
+    if isinstance(decoder, torch.nn.Linear):
+        return decoder
+    seq = getattr(decoder, "decoder", None)
+    lins = [m for m in (seq if seq is not None else decoder.modules()) if isinstance(m, torch.nn.Linear)]
+    if len(lins) != 1:
+        raise UnsupportedFunc("the fused decoder is ONE nn.Linear over latent[..., :3] (lib/models.py:26-51 with Fp=True)")
+    if seq is not None and getattr(decoder, "latent_dim", 3) != 3:
+        raise UnsupportedFunc("Decoder(Fp=False) reads all latent components; the fused epilogue covers the Fp=True decoder")
+    return lins[0]
+
+
+def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=None):
+    """The solve with its consumers fused into the output store.  For the reference's
+
+        latent = odeint(self.ode, z, t, method='rk4', options=dict(step_size=h))          lib/VAE.py:137
+        y      = self.dec(self.latent[..., :3])                                           lib/VAE.py:138
+        reg    = train_functions.latent_init_loss(self.latent[..., :3])                   lib/VAE.py:186
+
+    this returns ``(y, reg)`` -- ``y`` ``[len(t), B, R * input_dim]`` (what ``self.dec`` returns; the caller reshapes it to
+    ``[batch, n_samples, T, R]`` as lib/VAE.py:138 does), ``reg`` a 0-dim tensor -- without ever writing the
+    ``[len(t), B, R, L]`` trajectories: at L = 8 the kernels store 1/8 of the bytes (plus a byte of sign mask per region)
+    and the adjoint reads ``dL/dy`` instead of a trajectory-sized cotangent.  Gradients reach the ODE func's parameters, the
+    decoder's weight and bias, and y0 (or ``mean`` / ``std`` / ``eps`` with ``reparam=(eps, std, mean)``, y0 = None: the
+    fused producer of SURVEY 8(f1))."""
+    if method != "rk4":
+        raise NotImplementedError("the fused decoder epilogue implements the reference's method, rk4")
+    info = describe_func(func)
+    lin = _decoder_linear(decoder)
+    R, Ld = info.n_regions, info.latent_dim
+    if lin.in_features != 3 * R or lin.bias is None:
+        raise ValueError(f"the decoder must be nn.Linear({3 * R}, R * input_dim) with a bias")
+    eps = std = mean = None
+    if reparam is not None:
+        if y0 is not None:
+            raise ValueError("pass either y0 or reparam=(eps, std, mean)")
+        eps, std, mean = reparam
+        if eps.dim() != 4 or mean.shape != eps.shape[1:] or std.shape != eps.shape[1:] or eps.shape[2] != R or eps.shape[3] + 1 != Ld:
+            raise ValueError(f"eps must be [n_samples, batch, {R}, {Ld - 1}] and std / mean [batch, {R}, {Ld - 1}]")
+        ins = (eps, std, mean)
+    else:
+        if not isinstance(y0, torch.Tensor) or y0.dim() != 3 or y0.shape[1] != R or y0.shape[2] != Ld:
+            raise ValueError(f"y0 must be [B, {R}, {Ld}]")
+        ins = (y0,)
+    for x in (*ins, lin.weight, lin.bias):
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise RuntimeError("the fused UDE solver runs on fp32 CUDA tensors only; there is no CPU fallback")
+    options = {} if options is None else dict(options)
+    group = options.pop("process_group", None)
+    info.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)
+    unknown = set(options) - {"step_size"}
+    if unknown:
+        raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
+    t_cpu = t.detach().to("cpu")
+    if t.dim() != 1 or t.numel() < 2 or not bool((t_cpu[1:] > t_cpu[:-1]).all()):
+        raise ValueError("t must be a one dimensional, strictly increasing tensor")
+    (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), lin.weight.device)
+    params = [p for l in info.linears() for p in (l.weight, l.bias)]
+    need_tape = torch.is_grad_enabled() and any(x.requires_grad for x in (*ins, lin.weight, lin.bias, *params))
+    y_pred, side = _Rk4SolveDecoded.apply(y0, eps, std, mean, lin.weight, lin.bias, info, tables, n_steps, int(t.numel()),
+                                          need_tape, *params)
+    if group is not None:
+        from .dist import all_reduce_side
+        side = all_reduce_side(side, None if group is True else group)
+    install_side_channels(func, info, side)
+    return y_pred, side[7].to(torch.float32)
 
 
 def odeint_groups(funcs, y0, t, *, method="rk4", options=None):

@@ -34,9 +34,11 @@
  *                                 W[out,in] row-major, then b[out]
  *                                 (lib/models.py:118-124, 167-172, 208-223)
  *   tape          opaque, ude_plan().tape_bytes; written by *_forward,
- *                 read by *_backward (stage inputs, SoA)
+ *                 read by *_backward (stage inputs, SoA; rk4: one more record
+ *                 for the final state, used by the decoded entry points)
  *   side          double[8]: sum beta, sum gamma, sum beta^2, sum gamma^2,
- *                 sum Fa^2, N rows, n RHS evals, reserved — the reductions
+ *                 sum Fa^2, N rows, n RHS evals, sum of latent_init_loss
+ *                 (decoded entry points, else 0) — the reductions
  *                 behind posterior() (lib/models.py:152-156) and the Fa_norm
  *                 loss (lib/VAE.py:179-183); per group: [G, 8]
  *   g_side        float[5] per group: dL/d(side[0..4])
@@ -211,6 +213,45 @@ int ude_rk4_backward_reparam(const UdeDesc* desc, const float* theta /*dev*/, co
                              const int32_t* out_kind /*dev*/, const float* out_w /*dev*/, const float* tape /*dev*/,
                              const float* g_out /*dev*/, const float* g_side /*dev | NULL*/, float* g_y0 /*dev*/,
                              float* g_z /*dev*/, float* g_theta /*dev*/,
+                             void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+/*
+ * Fused consumer of the outputs.  The caller of the path reduces `latent` right away,
+ *     y_pred = self.dec(self.latent[..., :3])                        /root/reference/lib/VAE.py:138
+ *              Decoder: nn.Linear(n_regions * 3, n_regions * input_dim) on the flattened [.., R, 3] rows
+ *                                                                    /root/reference/lib/models.py:26-51
+ *     reg_loss = 0.1 * latent_init_loss(self.latent[..., :3])        /root/reference/lib/VAE.py:186,
+ *                                                                    /root/reference/lib/train_functions.py:116-126
+ * so the *_decoded entry points emit those instead of the [n_out,B,R,L] trajectories (8x fewer bytes at L = 8, and no
+ * eager loss passes over them):
+ *     y_pred   dev [n_out, B, dec.n_out]    decoder output of every output time (row 0 decodes y0)
+ *     side[7]  sum of latent_init_loss over all outputs / trajectories / regions / 3 components (fp64)
+ *     out_mask dev [n_out, B, R] bytes      bit 2c: component c < 0, bit 2c+1: component c > 1 (d reg / d latent for the adjoint)
+ * and the adjoint takes dL/dy_pred plus dL/dside[7] (= g_side[5]; g_side holds SIX floats here) and returns, next to
+ * dL/dy0 (dL/dz) and dL/dtheta, the decoder's gradients g_dec = [dW (dec.n_out x 3R, row-major) | db (dec.n_out)].
+ * The output states needed for dW are stage inputs already on the tape plus its last record (the final state).
+ * `rp` may be NULL (y0 given) or the fused reparam producer (then y0_out [B,R,L] receives the initial state and is the
+ * `y0` argument of the adjoint).  rk4, one weight set.  dec_partial: scratch, [ude_plan().n_ctas, dec.n_out*(3R+1)] floats.
+ */
+typedef struct UdeDecoder {
+    const float* weight;    /* dev [n_out, 3R]  Decoder.decoder[1].weight  (lib/models.py:40) */
+    const float* bias;      /* dev [n_out]                                                   */
+    int32_t n_out;          /* R * input_dim                                                 */
+} UdeDecoder;
+
+int ude_rk4_forward_decoded(const UdeDesc* desc, const float* theta /*dev*/, const float* y0 /*dev | NULL with rp*/,
+                            const UdeReparam* rp /*NULL: y0 given*/, int32_t n_steps, const float* dt /*dev*/, int32_t n_out,
+                            const int32_t* out_step /*dev*/, const int32_t* out_kind /*dev*/, const float* out_w /*dev*/,
+                            const UdeDecoder* dec, float* y_pred /*dev*/, uint8_t* out_mask /*dev*/, float* y0_out /*dev | NULL without rp*/,
+                            float* tape /*dev | NULL*/, double* side /*dev [8]*/,
+                            void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+int ude_rk4_backward_decoded(const UdeDesc* desc, const float* theta /*dev*/, const float* y0 /*dev*/, const UdeReparam* rp /*NULL*/,
+                             int32_t n_steps, const float* dt /*dev*/, int32_t n_out, const int32_t* out_step /*dev*/,
+                             const int32_t* out_kind /*dev*/, const float* out_w /*dev*/, const UdeDecoder* dec,
+                             const float* tape /*dev*/, const uint8_t* out_mask /*dev*/, const float* g_pred /*dev [n_out,B,dec.n_out]*/,
+                             const float* g_side /*dev [6] | NULL*/, float* g_y0 /*dev*/, float* g_z /*dev | NULL without rp*/,
+                             float* g_theta /*dev*/, float* g_dec /*dev*/, float* dec_partial /*dev scratch*/,
                              void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
 
 /* Controller options of torchdiffeq's RKAdaptiveStepsizeODESolver. */
