@@ -41,7 +41,8 @@ METRIC = "ude_trajectory_steps_per_sec_fwd_plus_adjoint"
 UNIT = "trajectory-steps/s"
 WORKLOAD = ("BASELINE configs[3]: synthetic ensemble, FaFp R=1 L=8 net [64,64,32] aug [64,64] (nn.Linear default init, "
             "aug head scaled by aug_head_scale=0.05 so that trajectories stay inside the RHS clamp), RK4(3/8) t=[0..8] h=1 "
-            "(8 steps), fused forward + discrete-adjoint backward")
+            "(8 steps), fused forward + discrete-adjoint backward; loss = MSE of the Decoder Linear(3->1) output against an ILI-shaped season + "
+            "0.1 latent_init_loss + kl_p(posterior) + 0.1 Fa_norm (lib/VAE.py:138-186)")
 
 
 def _spec():
@@ -199,12 +200,15 @@ def cpu_reference_step(B: int, threads: int, reps: int, spec=None, t=None, step_
     week = t.clone()
     y_ili = (0.02 + 0.5 * torch.exp(-((week - 5.0) / 4.0) ** 2)).reshape(-1, 1, 1)
     times, kind = [], "port"
+    dec = _decoder("cpu") if spec.n_regions == 1 else None       # the Decoder of lib/models.py:26-51 (torch ops on the trajectories)
     for i in range(reps + 1):
+        if dec is not None:
+            dec.zero_grad(set_to_none=True)
         func, kind, _ = reference_func(spec, theta)
         y0g = y0.clone().requires_grad_(True)
         t0 = time.perf_counter()
         y = odeint_ref.odeint(func, y0g, t, method="rk4", options=dict(step_size=h))
-        loss = _loss(y, y_ili, func)
+        loss = _loss(y, y_ili, func, dec)
         loss.backward()
         dt = time.perf_counter() - t0
         if i > 0:
@@ -212,23 +216,44 @@ def cpu_reference_step(B: int, threads: int, reps: int, spec=None, t=None, step_
     return statistics.median(times), kind
 
 
-def _loss(y, y_ili, func):
-    """The synthetic loss of SURVEY.md 8d: ILI-shaped MSE on the I compartment, the reference's
-    0.1 * latent_init_loss (lib/train_functions.py:116-126) on S,I,R, kl_p on posterior()
-    (lib/VAE.py:172-177, lib/train_functions.py:77-80) and 0.1 * Fa_norm (lib/VAE.py:179-183)."""
+DEC_W, DEC_B = [[0.05, 1.0, -0.03]], [0.01]     # the headline's Decoder Linear(3 -> 1) (lib/models.py:26-51), fixed values
+
+
+def _decoder(dev):
+    import torch
+    lin = torch.nn.Linear(3, 1)
+    with torch.no_grad():
+        lin.weight.copy_(torch.tensor(DEC_W))
+        lin.bias.copy_(torch.tensor(DEC_B))
+    return lin.to(dev)
+
+
+def _loss(y, y_ili, func, dec=None):
+    """The synthetic loss of SURVEY.md 8d: ILI-shaped MSE on the decoded prediction (lib/VAE.py:138,161; on the I
+    compartment when no decoder is given), the reference's 0.1 * latent_init_loss (lib/train_functions.py:116-126) on
+    S,I,R, kl_p on posterior() (lib/VAE.py:172-177, lib/train_functions.py:77-80) and 0.1 * Fa_norm (lib/VAE.py:179-183)."""
+    import torch
+    x = y[..., :3]
+    pred = y[..., 1] if dec is None else dec(x.reshape(y.shape[0], y.shape[1], -1))
+    y_ili = y_ili.to(y.device)
+    reg = (torch.where(x < 0, x.abs(), torch.zeros_like(x)) + torch.where(x > 1, (1 - x).abs(), torch.zeros_like(x))).sum()
+    return _loss_tail(pred, y_ili if dec is None else y_ili.reshape(-1, 1, 1), reg, y.shape[1], func)
+
+
+def _loss_tail(pred, y_ili, reg_sum, B, func):
+    """mse(pred, y_ili) + 0.1 * reg_sum / B + kl_p + 0.1 * Fa_norm / sqrt(B): shared by the plain path (pred / reg from torch ops on
+    the trajectories) and the fused-consumer path (pred / reg straight from ude_b200.odeint_decoded)."""
     import torch
     from torch.distributions import Normal, kl_divergence
-    x = y[..., :3]
-    mse = torch.mean((y[..., 1] - y_ili.to(y.device)) ** 2)
-    reg = 0.1 * (torch.where(x < 0, x.abs(), torch.zeros_like(x)) +
-                 torch.where(x > 1, (1 - x).abs(), torch.zeros_like(x))).sum() / y.shape[1]
-    loss = mse + reg
+    y = pred
+    mse = torch.mean((pred - y_ili) ** 2)
+    loss = mse + 0.1 * reg_sum / B
     if getattr(func, "params", None):
         post = func.posterior()
         prior = Normal(torch.tensor([0.8, 0.55], device=y.device), torch.tensor([0.2, 0.2], device=y.device))
         loss = loss + kl_divergence(prior, post).mean()
     if getattr(func, "tracker", None):
-        loss = loss + 0.1 * torch.norm(torch.stack(func.tracker)) / (y.shape[1] ** 0.5)
+        loss = loss + 0.1 * torch.norm(torch.stack(func.tracker)) / (B ** 0.5)
     return loss
 
 
@@ -491,6 +516,7 @@ def run_ours(args):
     info = ude_b200.describe_func(mod)
     t = torch.arange(float(N_STEPS_GRID + 1))
     y_ili = (0.02 + 0.5 * torch.exp(-((t - 5.0) / 4.0) ** 2)).reshape(-1, 1, 1).to(dev)
+    dec = _decoder(dev)
     (tables, n_steps) = _grid_on_device(t, t[1] - t[0], dev)
     n_out = t.numel()
     dt_t, os_t, ok_t, ow_t = tables
@@ -504,7 +530,7 @@ def run_ours(args):
         y0g = y0.clone().requires_grad_(True)
         mod.clear_tracking()
         y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=t[1] - t[0]))
-        loss = _loss(y, y_ili, mod)
+        loss = _loss(y, y_ili, mod, dec)
         g_out = torch.autograd.grad(loss, y, retain_graph=False)[0].contiguous()
         g_side = torch.tensor([1e-8, -1e-8, 1e-9, 1e-9, 1e-9], dtype=torch.float32, device=dev)
         del y, loss, y0g
@@ -581,18 +607,25 @@ def run_ours(args):
                 "unit": UNIT, "scaling": "weak"}
     check = dist_check(mod, dev, world, rank) if world > 1 else None
 
-    # ---- end-to-end leg: public API, host inputs, H2D + loss + backward + D2H every step
-    def step_e2e():
+    # ---- end-to-end legs: public API, host inputs, H2D + loss + backward + D2H every step.
+    #   fused consumers (the headline e2e): ude_b200.odeint_decoded -- decoder + latent_init_loss inside the solve
+    #   plain: ude_b200.odeint, then the same decoder / loss as torch ops on the [T,B,R,L] trajectories (what lib/VAE.py does)
+    def step_e2e(fused: bool):
         y0d = y0_host.to(dev, non_blocking=True).requires_grad_(True)
         mod.clear_tracking()
         mod.zero_grad(set_to_none=True)
+        dec.zero_grad(set_to_none=True)
         opts = dict(step_size=t[1] - t[0])
         if world > 1:
             opts["process_group"] = True
-        yy = ude_b200.odeint(mod, y0d, t, method="rk4", options=opts)
-        ls = _loss(yy, y_ili, mod)
+        if fused:
+            yp, reg = ude_b200.odeint_decoded(mod, dec, y0d, t, options=opts)
+            ls = _loss_tail(yp, y_ili, reg, yp.shape[1], mod)
+        else:
+            yy = ude_b200.odeint(mod, y0d, t, method="rk4", options=opts)
+            ls = _loss(yy, y_ili, mod, dec)
         ls.backward()
-        flat = torch.cat([p.grad.reshape(-1) for p in mod.parameters()])
+        flat = torch.cat([p.grad.reshape(-1) for p in (*mod.parameters(), *dec.parameters())])
         if world > 1:
             dist.all_reduce(flat)
         out = torch.cat([ls.detach().reshape(1), flat]).to("cpu")
@@ -603,19 +636,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = step_e2e()
-    barrier()
-    e2e_sec = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_sec = float(te.item())
+    def time_e2e(fused: bool):
+        e2e_steps = max(1, min(args.steps, 3))
+        step_e2e(fused)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = step_e2e(fused)
+        barrier()
+        sec = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([sec], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item()), r
+
+    plain_sec, res_plain = time_e2e(False)
+    e2e_sec, res = time_e2e(True)
     e2e_value = world * B * n_steps / e2e_sec
+    e2e_agree = float((res - res_plain).abs().max() / res_plain.abs().max())      # both legs compute the same loss and gradients
 
     if rank == 0:
         peak = C.c_double(0.0)
@@ -702,7 +740,11 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y0_host.numel() * 4),
-                    "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_sec * 1e3},
+                    "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_sec * 1e3,
+                    "api": "ude_b200.odeint_decoded (solve + Decoder + latent_init_loss fused, SURVEY 8f2), loss tail in torch, backward, gradients to host",
+                    "plain_odeint": {"value": world * B * n_steps / plain_sec, "ms_per_step": plain_sec * 1e3,
+                                     "api": "ude_b200.odeint, then Decoder + losses as torch ops on the [T,B,R,L] trajectories (lib/VAE.py:137-138,186)"},
+                    "fused_vs_plain_max_rel_diff": e2e_agree},
             "gpu_launches": 6 * args.steps,
             "clocks": clocks,
         }

@@ -13,7 +13,8 @@ The directory is named after the reference repository; ``ude_b200`` (repo root) 
 importable alias of this package.
 """
 from ._lib import UdeError, build, lib  # noqa: F401
-from .funcs import Decoder, Fa, FaFp, Fp, FuncInfo, UnsupportedFunc, describe_func  # noqa: F401
+from .funcs import (Bayes_Fa, Bayes_FaFp, Bayes_Fp, Decoder, Dense_Variational, Fa, FaFp, Fp, FuncInfo, UnsupportedFunc,  # noqa: F401
+                    describe_func)
 from . import dist, train  # noqa: F401
 from .train import GraphedIteration, run_epoch  # noqa: F401
 from .odeint import (flatten_parameters, odeint, odeint_decoded, odeint_groups, odeint_reparam, posterior_rows,  # noqa: F401
@@ -29,5 +30,5 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
 
 
 __all__ = ["odeint", "odeint_groups", "odeint_adjoint", "Fp", "Fa", "FaFp", "describe_func", "build", "lib", "UdeError",
-           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows", "flatten_parameters", "odeint_reparam", "odeint_decoded", "Decoder", "GraphedIteration", "run_epoch"]
+           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows", "flatten_parameters", "odeint_reparam", "odeint_decoded", "Decoder", "Bayes_Fp", "Bayes_Fa", "Bayes_FaFp", "Dense_Variational", "GraphedIteration", "run_epoch"]
 __version__ = "0.1.0"

@@ -20,6 +20,7 @@ UDE_MAX_LAYERS = 8
 UDE_OK = 0
 UDE_ERR_CAPACITY = -7
 FLAG_WEIGHTS_PACKED = 16
+FLAG_BAYES = 32
 KIND = {"Fp": 0, "Fa": 1, "FaFp": 2}
 METHOD = {"rk4": 0, "dopri5": 1}
 
@@ -147,7 +148,7 @@ EXPORTS = [
     "ude_abi_version", "ude_strerror", "ude_last_cuda_error", "ude_theta_size", "ude_macs_per_eval", "ude_plan",
     "ude_rk4_grid", "ude_rk4_forward", "ude_rk4_backward", "ude_dopri5_forward", "ude_dopri5_backward",
     "ude_measure_ffma_tflops", "ude_rk4_path", "ude_rk4_forward_reparam", "ude_rk4_backward_reparam",
-    "ude_rk4_forward_decoded", "ude_rk4_backward_decoded",
+    "ude_rk4_forward_decoded", "ude_rk4_backward_decoded", "ude_rk4_forward_bayes", "ude_rk4_backward_bayes",
 ]
 
 
@@ -194,6 +195,10 @@ def lib() -> C.CDLL:
         L.ude_rk4_backward_decoded.restype = C.c_int
         L.ude_rk4_backward_decoded.argtypes = [C.POINTER(UdeDesc), vp, vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp,
                                                C.POINTER(UdeDecoder), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_forward_bayes.restype = C.c_int
+        L.ude_rk4_forward_bayes.argtypes = [C.POINTER(UdeDesc), vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_backward_bayes.restype = C.c_int
+        L.ude_rk4_backward_bayes.argtypes = [C.POINTER(UdeDesc), vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         L.ude_dopri5_forward.restype = C.c_int
         L.ude_dopri5_forward.argtypes = [C.POINTER(UdeDesc), C.POINTER(UdeDopri5Opts), vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, i64, vp]

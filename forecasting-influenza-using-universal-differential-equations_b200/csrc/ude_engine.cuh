@@ -62,6 +62,16 @@ struct DecArgs {
     const float* g_pred;    // adjoint: [n_out][B][n_dec]
     float* partial;         // adjoint: per-CTA partial sums [gridDim.x][n_dec * (3R + 1)]  (dW row-major, then db)
 };
+// Bayesian ODE funcs (/root/reference/lib/in_development/models_bayes.py:30-48,69-265): every RHS evaluation
+// draws fresh weights  w_e = w_mean + z_e * |w_std|  shared by the whole batch.  The caller materialises the 4 * n_steps weight
+// sets; the kernels re-stage set e = 4 n + stage before evaluation e, and the adjoint folds each evaluation's weight gradient
+// G_e into two per-CTA sums:  A += G_e  (-> dL/dw_mean)  and  Bz += G_e * z_e  (-> dL/dw_std up to sign(w_std)).
+struct BayesArgs {
+    const float* w;         // packed weight sets [4 * n_steps][n_packed]; nullptr: mode off
+    const float* z;         // adjoint: packed noise [4 * n_steps][n_packed]
+    float* fold;            // adjoint: [2][gridDim.x][n_packed]  (A blocks, then Bz blocks)
+};
+BayesArgs& pending_bayes();
 DecArgs& pending_decoded();
 int& decoded_ctas();          // host: CTAs of the last decoded adjoint launch (= partial blocks written)
 __device__ __forceinline__ unsigned reg_mask_bits(float v0, float v1, float v2) {

@@ -94,6 +94,7 @@ static void base_model(const UdeDesc* d, ModelP& P) {
     P.Dc = (P.L - 3) * P.R;
     P.Dc_p = round4(P.Dc);
     P.hoist = P.Dc > 0;
+    P.bayes = (d->flags & UDE_FLAG_BAYES) != 0;
     P.R_p = round4(P.R);
     P.n_rate = d->n_rate_layers;
     P.n_aug = d->n_aug_layers;
@@ -167,9 +168,15 @@ static int plan_smem(ModelP& P, int TB, bool w_smem, bool g_smem, bool cold, int
             off += Ls[i].n_out_p * P.TBP;
         }
     }
-    // constants of the tile: alias the ACT rows (only alive in the tile prologue / epilogue)
+    // constants of the tile: alias the ACT rows (only alive in the tile prologue / epilogue) -- unless the weights change per
+    // evaluation (bayes): then every evaluation redoes the constant product and the rows stay
     P.off_XC = act0;
-    if (off - act0 < P.Dc_p * P.TBP) off = act0 + P.Dc_p * P.TBP;
+    P.off_GXC = 0;
+    if (P.bayes) {
+        P.off_XC = off;
+        off += P.Dc_p * P.TBP;
+        if (bwd) { P.off_GXC = off; off += P.Dc_p * P.TBP; }
+    } else if (off - act0 < P.Dc_p * P.TBP) off = act0 + P.Dc_p * P.TBP;
     // hoisted first-layer parts: c0 rows (both directions), D rows (adjoint); in the ring-mode adjoint both live in
     // tensor memory and D is dumped behind the constants' rows for the tile epilogue
     P.w_ring = ring;
@@ -340,6 +347,7 @@ static int choose_plan(const UdeDesc* d, ModelP& P, int n_state, int n_rbuf, boo
     for (int c = 0; c < nc; ++c)
         for (int t = 0; t < 2; ++t) {
             if (cands[c].ring && no_ring) continue;
+            if (P.bayes && c > 0) continue;      // per-evaluation weights: only the all-resident plans re-stage them
             if (plan_smem(P, tb_order[t], cands[c].w, cands[c].g, cands[c].cold, n_state, n_rbuf, bwd, cands[c].ring) <= budget)
                 return UDE_OK;
         }
@@ -368,6 +376,27 @@ static Workspace carve_workspace(void* base, const ModelP& P, int n_ctas, int co
     return w;
 }
 
+// Bayes mode: behind the usual carve, the packed weight sets and noise of all 4 * n_steps evaluations and the fold blocks
+struct BayesWs {
+    float* w;        // [n_evals][n_packed]
+    float* z;        // [n_evals][n_packed]
+    float* fold;     // [2][n_ctas][n_packed]
+    long long bytes;
+};
+static BayesWs bayes_carve(void* base, long long off, const ModelP& P, int n_steps, int n_ctas) {
+    BayesWs b;
+    const long long set = (long long)4 * n_steps * P.n_packed * 4;
+    off = align_up(off, 256);
+    b.w = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + set, 256);
+    b.z = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + set, 256);
+    b.fold = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)2 * n_ctas * P.n_packed * 4, 256);
+    b.bytes = off;
+    return b;
+}
+
 static int grid_size(const ModelP& P, long long B) {
     const DeviceInfo& di = device_info();
     const long long tiles = (B + P.TB - 1) / P.TB;
@@ -394,6 +423,10 @@ ReparamArgs& pending_reparam() {
 }
 // the *_decoded entry points park their arguments here for the launch they forward to; the adjoint launch records how many
 // per-CTA partial blocks it wrote
+BayesArgs& pending_bayes() {
+    static thread_local BayesArgs b = {};
+    return b;
+}
 DecArgs& pending_decoded() {
     static thread_local DecArgs d = {};
     return d;
@@ -540,11 +573,16 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     Workspace w = carve_workspace(nullptr, Pf, n_ctas, cold_max);
     plan->workspace_bytes = w.bytes;
     TcModel Mt;
-    const int path = method == UDE_METHOD_RK4 ? tc_choose(desc, Mt) : 0;
+    const int path = (method == UDE_METHOD_RK4 && !(desc->flags & UDE_FLAG_BAYES)) ? tc_choose(desc, Mt) : 0;
     if (path < 0) return path;
     // rk4: [n_steps][4 stages][Dn][B] stage inputs + ONE record for the final state (read by the decoded adjoint only)
     if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up(((long long)n_steps * 4 + 1) * Pf.Dn * desc->batch * 4, 256);
     else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
+    if (desc->flags & UDE_FLAG_BAYES) {       // per-evaluation weight sets (ude_rk4_*_bayes): FFMA engine, all-resident plans
+        if (method != UDE_METHOD_RK4 || (desc->flags & UDE_FLAG_FORCE_TENSOR)) return UDE_ERR_UNSUPPORTED;
+        if (!Pf.w_in_smem || Pf.cold_global || !Pb.w_in_smem || !Pb.g_in_smem || Pb.cold_global) return UDE_ERR_UNSUPPORTED;
+        plan->workspace_bytes = bayes_carve(nullptr, w.bytes, Pf, n_steps, n_ctas).bytes;
+    }
     plan->tile_traj = Pb.TB;
     plan->n_ctas = n_ctas;
     plan->smem_bytes_fwd = Pf.smem_floats * 4;
@@ -947,6 +985,110 @@ int ude_rk4_backward_reparam(const UdeDesc* desc, const float* theta, const UdeR
                           workspace, workspace_bytes, stream);
     pending_reparam() = ReparamArgs{};
     return st;
+}
+
+// ---- Bayesian ODE funcs: one weight set per RHS evaluation (include/ude_b200.h) -----------------------------------------
+static int bayes_common(const UdeDesc* desc, int n_steps, void* workspace, int64_t workspace_bytes, UdeDesc* d, ModelP* Pf, ModelP* Pb,
+                        int* n_ctas, Workspace* w, BayesWs* bw) {
+    int st = check_desc(desc);
+    if (st != UDE_OK) return st;
+    if (desc->n_groups != 1 || (desc->flags & UDE_FLAG_FORCE_TENSOR)) return UDE_ERR_UNSUPPORTED;
+    if (n_steps < 1 || !workspace) return UDE_ERR_INVALID;
+    if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+    *d = *desc;
+    d->flags |= UDE_FLAG_BAYES | UDE_FLAG_FORCE_FFMA;
+    if ((st = choose_plan(d, *Pf, F_NSTATE, 0, false)) != UDE_OK) return st;
+    if ((st = choose_plan(d, *Pb, B_NSTATE, 0, true)) != UDE_OK) return st;
+    if (!Pf->w_in_smem || Pf->cold_global || !Pb->w_in_smem || !Pb->g_in_smem || Pb->cold_global) return UDE_ERR_UNSUPPORTED;
+    const int cf = grid_size(*Pf, d->batch), cb = grid_size(*Pb, d->batch);
+    *n_ctas = cf > cb ? cf : cb;
+    *w = carve_workspace(workspace, *Pf, *n_ctas, 0);
+    *bw = bayes_carve(workspace, w->bytes, *Pf, n_steps, *n_ctas);
+    if (bw->bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    return UDE_OK;
+}
+
+int ude_rk4_forward_bayes(const UdeDesc* desc, const float* theta_evals, const float* y0, int32_t n_steps, const float* dt,
+                          int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w, float* y_out,
+                          float* tape, double* side, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!theta_evals || !y0 || !dt || !out_step || !out_kind || !out_w || !y_out || !side || n_out < 1) return UDE_ERR_INVALID;
+    UdeDesc d;
+    ModelP Pf, Pb;
+    Workspace w;
+    BayesWs bw;
+    int n_max = 0;
+    int st = bayes_common(desc, n_steps, workspace, workspace_bytes, &d, &Pf, &Pb, &n_max, &w, &bw);
+    if (st != UDE_OK) return st;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    pack_theta_kernel<<<dim3(Pf.n_rate + Pf.n_aug + 3, 4 * n_steps), 256, 0, s>>>(Pf, theta_evals, bw.w);
+    UDE_CUDA(cudaGetLastError());
+    const int n_ctas = grid_size(Pf, d.batch);
+    Rk4FwdArgs a{};
+    a.wpacked = bw.w;
+    a.y0 = y0;
+    a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+    a.y_out = y_out;
+    a.tape = tape;
+    a.side_partial = w.side_partial;
+    a.B = d.batch;
+    a.n_groups = 1;
+    a.rp = pending_reparam();
+    a.dec = pending_decoded();
+    a.bayes = BayesArgs{bw.w, nullptr, nullptr};
+    const int smem = Pf.smem_floats * 4;
+    if ((st = set_smem(rk4_fwd_kernel<true, false>, smem)) != UDE_OK) return st;
+    rk4_fwd_kernel<true, false><<<n_ctas, kThreads, smem, s>>>(Pf, a);
+    UDE_CUDA(cudaGetLastError());
+    reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int ude_rk4_backward_bayes(const UdeDesc* desc, const float* theta_evals, const float* z_evals, const float* y0, int32_t n_steps,
+                           const float* dt, int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                           const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_mean_zsum,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!theta_evals || !z_evals || !y0 || !dt || !out_step || !out_kind || !out_w || !tape || !g_out || !g_y0 || !g_mean_zsum || n_out < 1)
+        return UDE_ERR_INVALID;
+    UdeDesc d;
+    ModelP Pf, Pb;
+    Workspace w;
+    BayesWs bw;
+    int n_max = 0;
+    int st = bayes_common(desc, n_steps, workspace, workspace_bytes, &d, &Pf, &Pb, &n_max, &w, &bw);
+    if (st != UDE_OK) return st;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 pgrid(Pb.n_rate + Pb.n_aug + 3, 4 * n_steps);
+    if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED)) {
+        pack_theta_kernel<<<pgrid, 256, 0, s>>>(Pb, theta_evals, bw.w);
+        UDE_CUDA(cudaGetLastError());
+    }
+    pack_theta_kernel<<<pgrid, 256, 0, s>>>(Pb, z_evals, bw.z);       // the packing is a permutation + zero padding: the same map serves z
+    UDE_CUDA(cudaGetLastError());
+    const int n_ctas = grid_size(Pb, d.batch);
+    // the fold blocks are laid out for the CTAs of THIS launch: [2][n_ctas][n_packed] (inside the plan's [2][n_max][n_packed])
+    Rk4BwdArgs a{};
+    a.wpacked = bw.w;
+    a.y0 = y0;
+    a.g = GridTables{n_steps, dt, n_out, out_step, out_kind, out_w};
+    a.tape = tape;
+    a.g_out = g_out;
+    a.g_side = g_side;
+    a.g_y0 = g_y0;
+    a.slabs = w.slabs;
+    a.B = d.batch;
+    a.n_groups = 1;
+    a.rp = pending_reparam();
+    a.dec = pending_decoded();
+    decoded_ctas() = n_ctas;
+    a.bayes = BayesArgs{bw.w, bw.z, bw.fold};
+    const int smem = Pb.smem_floats * 4;
+    if ((st = set_smem(rk4_bwd_kernel<true, true, false>, smem)) != UDE_OK) return st;
+    rk4_bwd_kernel<true, true, false><<<n_ctas, kThreads, smem, s>>>(Pb, a);
+    UDE_CUDA(cudaGetLastError());
+    reduce_dtheta_kernel<<<dim3((Pb.n_theta + 255) / 256, 2), 256, 0, s>>>(Pb, bw.fold, n_ctas, g_mean_zsum);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
 }
 
 static int check_decoder(const UdeDesc* desc, const UdeDecoder* dec) {

@@ -58,6 +58,9 @@ struct ModelP {
     // evaluations of delta_0 (off_DL).  rate[0] / aug[0] describe the live block, rate_c / aug_c the constant one.
     LayerP rate_c, aug_c;
     int hoist;              // Dc > 0
+    int bayes;              // weights change at EVERY RHS evaluation (Bayes_* funcs, lib/in_development/models_bayes.py:30-48): the
+                            // constant product is redone per evaluation, so the tile's constants keep their own rows (off_XC does
+                            // not alias the ACT rows) and the adjoint sums dL/dx_const in off_GXC
     int n_theta;            // floats of one weight set (PyTorch layout)
     int n_packed;           // floats of the packed blob incl. kPadTail
     int n_packed_hot;       // leading part used by every RHS evaluation (all but the constant blocks of the first layers)
@@ -72,6 +75,7 @@ struct ModelP {
     int off_W, off_G;       // valid when the flags above are set
     int off_X;              // [Dn_p][TBP] live inputs
     int off_XC;             // [Dc_p][TBP] constant inputs of the tile (aliases the ACT rows: tile prologue / epilogue only)
+    int off_GXC;            // (bwd, bayes) [Dc_p][TBP] sum over evaluations of W0[:, const]^T delta_0
     int off_DL;             // (bwd) [n0_rate_p + n0_aug_p][TBP] sum over evaluations of the first layers' deltas
     int off_S;              // state rows: n_state buffers of [Dn_p][TBP]
     int off_GX;             // (bwd) dL/dx_live of one RHS evaluation, [Dn_p][TBP]

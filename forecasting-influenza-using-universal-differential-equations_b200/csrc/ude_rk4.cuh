@@ -29,6 +29,7 @@ struct Rk4FwdArgs {
     ReparamArgs rp;                 // rp.mean != nullptr: y0 is PRODUCED here (ude_engine.cuh) and lives in y_out[0]
     DecArgs dec;                    // dec.n_dec > 0: decoded outputs (ude_engine.cuh DecArgs); y_out then holds row 0 only,
                                     // and the tape gets one extra record (index 4 * n_steps): the final state
+    BayesArgs bayes;                // bayes.w != nullptr: one weight set per RHS evaluation (SMEM_W kernels only)
 };
 
 struct Rk4BwdArgs {
@@ -46,6 +47,7 @@ struct Rk4BwdArgs {
     long long tape_group_floats;
     ReparamArgs rp;         // rp.mean != nullptr: also write dL/dz (rp.g_z) from the finished dL/dy0 rows
     DecArgs dec;            // dec.n_dec > 0: cotangents arrive as dL/dy_pred [n_out,B,n_dec] + g_side[5] = dL/dreg (g_out unused)
+    BayesArgs bayes;        // bayes.w != nullptr: one weight set per RHS evaluation (SMEM_W + SMEM_G kernels only)
 };
 
 // Ring-mode prologue shared by the four FFMA-engine kernels (COLD variants): barriers, descriptor, first two fetches.
@@ -285,6 +287,44 @@ __device__ __forceinline__ void hoist_backward_epilogue(const ModelP& P, const f
     __syncthreads();
 }
 
+// Bayes mode, after the sweep of ONE evaluation (weights We, noise ze): the hoisted product's adjoint for this evaluation
+//   Gslab[const blocks] = delta_0 (x) x_const,   GXC += We[:, const]^T delta_0        (DL rows hold delta_0 of this evaluation only)
+// then the fold  A += G_e,  Bz += G_e * z_e  over the whole packed vector (hot part in shared memory, constant blocks in the
+// CTA's global slab), leaving G, the slab's constant blocks and DL zeroed for the next evaluation.
+// Pre: synced after rhs_backward_layers.  Post: synced.
+__device__ __forceinline__ void bayes_eval_epilogue(const ModelP& P, const float* __restrict__ We, const float* __restrict__ ze,
+                                                    float* smem, float* __restrict__ G, float* __restrict__ Gslab,
+                                                    float* __restrict__ A, float* __restrict__ Bz, int warp, int lane) {
+    const int TB = P.TB, TBP = P.TBP;
+    if (P.hoist) {
+        LayerP Lr = P.rate_c, La = P.aug_c;
+        Lr.act_off = P.off_DL;
+        La.act_off = P.off_DL + (P.n_rate > 0 ? P.rate[0].n_out_p * TBP : 0);
+        const int w0 = P.n_rate > 0 ? dw_units(Lr) : 0, w1 = P.n_aug > 0 ? dw_units(La) : 0;
+        for (int u = warp; u < w0 + w1; u += kWarps) {
+            if (u < w0) dw_run(Lr, smem, Gslab, TB, TBP, u, lane);
+            else dw_run(La, smem, Gslab, TB, TBP, u - w0, lane);
+        }
+        if (P.n_rate > 0) {
+            for (int u = warp; u < bwd_units(Lr, P.mt_shift); u += kWarps) bwd_run(Lr, nullptr, We, smem, TBP, P.off_GXC, P.mt_shift, u, lane);
+            __syncthreads();
+        }
+        if (P.n_aug > 0) {
+            for (int u = warp; u < bwd_units(La, P.mt_shift); u += kWarps) bwd_run(La, nullptr, We, smem, TBP, P.off_GXC, P.mt_shift, u, lane);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.dl_rows * TBP; i += kThreads) smem[P.off_DL + i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < P.n_packed; i += kThreads) {       // every entry has one owning thread: plain read-modify-writes
+        float g;
+        if (i < P.n_packed_hot) { g = G[i]; G[i] = 0.f; }
+        else { g = Gslab[i]; Gslab[i] = 0.f; }
+        A[i] += g;
+        Bz[i] = fmaf(g, __ldg(ze + i), Bz[i]);
+    }
+    __syncthreads();
+}
+
 // One output row's cotangent: the live components come back in gl[], the constant ones are added straight into the
 // caller's g_y0 row (each row is owned by one thread; the lines stay in L2) -- no shared-memory rows for that running
 // sum.  128-bit accesses when the row allows it (the live lanes of the first quad are rewritten with their own values).
@@ -355,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
     long long g_cur = 0;
     const long long out_group = (long long)a.g.n_out * B * P.R * L, y0_group = B * P.R * L;
     const bool decoded = a.dec.n_dec > 0;      // outputs leave as y_pred / reg / mask (single weight set)
+    const bool bayes = SMEM_W && a.bayes.w != nullptr;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long grp = grouped ? tile / tiles_per_group : 0;
@@ -377,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
         else load_y0_tile(P, smem, a_y0, b0, nvalid, true, P.hoist != 0);
         __syncthreads();
         if (ring) hoist_c0_ring(P, a_wpacked, smem, warp, lane, 0u);
-        else hoist_c0(P, a_wpacked, smem, warp, lane);          // constant part of both first layers, once per tile
+        else if (!bayes) hoist_c0(P, a_wpacked, smem, warp, lane);          // constant part of both first layers, once per tile
         // output 0 = y0 (torchdiffeq: solution[0] = y0) and Y = dynamic part of y0
         for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
             const int r = idx >> P.tb_shift, b = idx & (TB - 1);
@@ -399,6 +440,11 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_fwd_kernel(const __grid_co
             int j_next = j;
 #pragma unroll 1
             for (int stage = 0; stage < 4; ++stage) {
+                if (SMEM_W && bayes) {      // this evaluation's weight set (the previous one's readers are behind a CTA barrier)
+                    const float* We = a.bayes.w + (long long)(n * 4 + stage) * P.n_packed;
+                    stage_weights_tma(smem + P.off_W, We, P.n_packed_hot, &wbar, wphase);
+                    hoist_c0(P, We, smem, warp, lane);
+                }
                 if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, 0u);
                 else rhs_forward_layers(P, Wp, smem, warp, lane);
                 UDE_PROF_DECL;
@@ -560,6 +606,11 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
+    const bool bayes = SMEM_W && SMEM_G && a.bayes.w != nullptr;     // one weight set per RHS evaluation (ude_engine.cuh BayesArgs)
+    float* const bayesA = bayes ? a.bayes.fold + (long long)blockIdx.x * P.n_packed : nullptr;
+    float* const bayesBz = bayes ? a.bayes.fold + ((long long)gridDim.x + blockIdx.x) * P.n_packed : nullptr;
+    if (bayes)
+        for (int i = threadIdx.x; i < P.n_packed; i += kThreads) { bayesA[i] = 0.f; bayesBz[i] = 0.f; }
     const bool decoded = a.dec.n_dec > 0;      // cotangents arrive as dL/dy_pred + dL/dreg (ude_engine.cuh DecArgs)
     const float g_reg = (decoded && a.g_side) ? __ldg(a.g_side + 5) : 0.f;
     float* const dpart = decoded ? a.dec.partial + (long long)blockIdx.x * (a.dec.n_dec * (P.Dn + 1)) : nullptr;
@@ -629,8 +680,10 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             }
         }
         __syncthreads();
+        if (bayes)
+            for (int i = threadIdx.x; i < P.Dc_p * TBP; i += kThreads) smem[P.off_GXC + i] = 0.f;
         if (ring) hoist_c0_ring(P, a_wpacked, smem, warp, lane, tmem);
-        else hoist_c0(P, a_wpacked, smem, warp, lane);
+        else if (!bayes) hoist_c0(P, a_wpacked, smem, warp, lane);
 
         int j = a.g.n_out - 1;
         for (int n = n_steps - 1; n >= 0; --n) {
@@ -695,6 +748,12 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
             __syncthreads();
 #pragma unroll 1
             for (int stage = 3; stage >= 0; --stage) {
+                const float* We = nullptr;
+                if (bayes) {        // this evaluation's weight set (the previous one's readers are behind a CTA barrier)
+                    We = a.bayes.w + (long long)(n * 4 + stage) * P.n_packed;
+                    stage_weights_tma(smem + P.off_W, We, P.n_packed_hot, &wbar, wphase);
+                    hoist_c0(P, We, smem, warp, lane);
+                }
                 if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, tmem);
                 else rhs_forward_layers(P, Wp, smem, warp, lane);
                 UDE_PROF_DECL;
@@ -714,6 +773,8 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
                 if (ring) rhs_backward_layers_ring(P, wr, smem, smem + P.off_GB, warp, lane, tmem);
                 else if (tm_acc) rhs_backward_layers<true>(P, Wp, smem, smem + P.off_GB, warp, lane, tmem);
                 else rhs_backward_layers<false>(P, Wp, smem, G, warp, lane);
+                if (bayes)
+                    bayes_eval_epilogue(P, We, a.bayes.z + (long long)(n * 4 + stage) * P.n_packed, smem, G, Gslab, bayesA, bayesBz, warp, lane);
                 UDE_PROF_RESTART();
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
@@ -772,6 +833,20 @@ __global__ void __launch_bounds__(kThreads, MINB) rk4_bwd_kernel(const __grid_co
         }
         __syncthreads();
         if (ring && P.c0_tm) dl_tm_dump(P, smem, P.off_DL, tmem, warp, lane);      // D: tensor memory -> rows behind the constants
+        if (bayes) {        // the hoisted adjoint ran per evaluation: only the summed dL/dx_const is left to hand over
+            if (P.hoist) {
+                const int Lc = L - 3;
+                for (int idx = threadIdx.x; idx < P.R * TB; idx += kThreads) {
+                    const int r = idx >> P.tb_shift, b = idx & (TB - 1);
+                    if (b < nvalid) {
+                        float* dst = a_g_y0 + ((b0 + b) * P.R + r) * (long long)L;
+                        const float* src = smem + P.off_GXC + (r * Lc) * TBP + b;
+                        for (int l = 3; l < L; ++l) dst[l] += src[(l - 3) * TBP];
+                    }
+                }
+                __syncthreads();
+            }
+        } else
         hoist_backward_epilogue(P, a_wpacked, smem, Gslab, a_y0, a_g_y0, b0, nvalid, warp, lane);
         if (a.rp.mean) {        // fused reparam: dL/dz rows from the finished dL/dy0 rows (same thread wrote them)
             const int Lm1 = L - 1;

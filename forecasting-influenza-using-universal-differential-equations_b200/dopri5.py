@@ -130,6 +130,8 @@ class Dopri5Stats:
 
 
 def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
+    if info.bayes:
+        raise NotImplementedError("Bayes_* funcs (weights re-drawn at every RHS evaluation) are fused for rk4, the reference's method")
     opts = _opts(rtol, atol, options, int(y0.shape[0]))
     t_dev = t_cpu.to(torch.float64).to(y0.device)
     theta = info.theta()

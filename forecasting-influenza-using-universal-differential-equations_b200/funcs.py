@@ -155,6 +155,143 @@ class FaFp(_UdeFunc):
 
 
 # ---------------------------------------------------------------------------------------
+# Bayesian ODE funcs -- mirror of /root/reference/lib/in_development/models_bayes.py
+# ---------------------------------------------------------------------------------------
+class Dense_Variational(nn.Module):
+    """Linear layer with a factorised Gaussian over its weights, re-sampled at EVERY call:
+    ``w = w_mean + z * |w_std|`` (models_bayes.py:12-48).  Same parameter names (``w_mean, w_std, b_mean, b_std``: the
+    ``state_dict`` keys), same initialisation (:34-42), ``make_prior`` / ``make_posterior`` for the KL term (:50-62)."""
+
+    def __init__(self, in_features, out_features, bias=True, prior_std=1.0):
+        super().__init__()
+        if not bias:
+            raise NotImplementedError("the reference only builds Dense_Variational layers with a bias")
+        self.in_features, self.out_features, self.prior_std, self.bias = in_features, out_features, prior_std, True
+        self.w_mean = nn.Parameter(torch.empty(out_features, in_features))
+        self.w_std = nn.Parameter(torch.empty(out_features, in_features))
+        self.b_mean = nn.Parameter(torch.empty(out_features))
+        self.b_std = nn.Parameter(torch.empty(out_features))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.w_mean, a=5 ** 0.5)
+        nn.init.constant_(self.w_std, 0.1)
+        bound = 1 / self.in_features ** 0.5
+        nn.init.uniform_(self.b_mean, -bound, bound)
+        nn.init.constant_(self.b_std, 0.1)
+
+    def make_z(self):
+        with torch.no_grad():
+            self.z = [torch.randn_like(self.w_mean), torch.randn_like(self.b_mean)]
+
+    def forward(self, x):
+        self.make_z()
+        return nn.functional.linear(x, self.w_mean + self.z[0] * torch.abs(self.w_std), self.b_mean + self.z[1] * torch.abs(self.b_std))
+
+    def make_prior(self):
+        self.prior = [Normal(torch.zeros_like(self.w_mean), self.prior_std * torch.ones_like(self.w_mean)),
+                      Normal(torch.zeros_like(self.b_mean), self.prior_std * torch.ones_like(self.b_mean))]
+        return self.prior
+
+    def make_posterior(self):
+        self.posterior = [Normal(self.w_mean, torch.abs(self.w_std)), Normal(self.b_mean, torch.abs(self.b_std))]
+        return self.posterior
+
+    def extra_repr(self):
+        return f"in_features={self.in_features}, out_features={self.out_features}, bias=True"
+
+
+def _var_modules(n_in: int, sizes: Sequence[int], n_head: int, prior_std: float) -> nn.ModuleList:
+    """Flatten, DV, (ELU, DV)*, DV -- the index layout of models_bayes.py:78-84 (state_dict keys)."""
+    mods = nn.ModuleList([nn.Flatten()])
+    widths = [n_in, *sizes]
+    mods.append(Dense_Variational(widths[0], widths[1], prior_std=prior_std))
+    for a, b in zip(widths[1:-1], widths[2:]):
+        mods.append(nn.ELU(inplace=True))
+        mods.append(Dense_Variational(a, b, prior_std=prior_std))
+    mods.append(Dense_Variational(widths[-1], n_head, prior_std=prior_std))
+    return mods
+
+
+class _BayesFunc(_UdeFunc):
+    def __init__(self, n_regions, latent_dim):
+        super().__init__(n_regions, latent_dim)
+        self.uncertainty = "bayes"
+
+    def get_kl(self):
+        """Mean KL(posterior || prior) over the variational layers (models_bayes.py:118-128, 174-184, 254-265); differentiable
+        torch ops on the parameters -- the fused solve does not touch it."""
+        from torch.distributions import kl_divergence
+        kl, count = 0, 0
+        for net in self.children():
+            for layer in net:
+                if isinstance(layer, Dense_Variational):
+                    kl = kl + sum(kl_divergence(q, p).mean() for q, p in zip(layer.make_posterior(), layer.make_prior())) / 2
+                    count += 1
+        return kl / count
+
+
+class Bayes_Fp(_BayesFunc):
+    """models_bayes.py:69-128."""
+    ode_type = "Fp"
+
+    def __init__(self, n_regions=1, latent_dim=8, net_sizes=(20, 20), prior_std=0.1, **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.Fp_net = _var_modules(n_regions * latent_dim, list(net_sizes), 2 * n_regions, prior_std)
+
+    def forward(self, t, x):
+        dyn, _ = self._rates(self.Fp_net, x)
+        return self._finish(dyn, x)
+
+
+class Bayes_Fa(_BayesFunc):
+    """models_bayes.py:131-184."""
+    ode_type = "Fa"
+
+    def __init__(self, n_regions=1, latent_dim=8, aug_net_sizes=(32, 32), nhidden_fa=32, prior_std=0.1, **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.aug_net = _var_modules(n_regions * latent_dim, list(aug_net_sizes), 3 * n_regions, prior_std)
+
+    def forward(self, t, x):
+        fa = _run(self.aug_net, x).reshape(-1, self.n_regions, 3)
+        out = self._finish(fa, x)
+        self.tracker.append(fa)
+        return out
+
+
+class Bayes_FaFp(_BayesFunc):
+    """models_bayes.py:186-265 (the rate net is called Fp_net here, not net as in lib/models.py FaFp)."""
+    ode_type = "FaFp"
+
+    def __init__(self, n_regions=1, latent_dim=8, net_sizes=(20, 20), aug_net_sizes=(32, 32), prior_std=0.1, **kwargs):
+        super().__init__(n_regions, latent_dim)
+        self.Fp_net = _var_modules(n_regions * latent_dim, list(net_sizes), 2 * n_regions, prior_std)
+        self.aug_net = _var_modules(n_regions * latent_dim, list(aug_net_sizes), 3 * n_regions, prior_std)
+        self.Fa_w = 1.0
+
+    def forward(self, t, x):
+        dyn, _ = self._rates(self.Fp_net, x)
+        fa = _run(self.aug_net, x).reshape(-1, self.n_regions, 3)
+        out = self._finish(dyn + self.Fa_w * fa, x)
+        self.tracker.append(fa)
+        return out
+
+
+class _VarLayer:
+    """A Dense_Variational layer (ours or the reference's) seen through nn.Linear's attribute names: weight / bias are the
+    means; w_std / b_std ride along."""
+
+    def __init__(self, m):
+        self.module = m
+        self.in_features, self.out_features = m.in_features, m.out_features
+        self.weight, self.bias, self.w_std, self.b_std = m.w_mean, m.b_mean, m.w_std, m.b_std
+
+
+def _is_variational(m) -> bool:
+    return all(hasattr(m, a) for a in ("w_mean", "w_std", "b_mean", "b_std"))
+
+
+# ---------------------------------------------------------------------------------------
 # recognition of a reference-protocol module (ours, lib.models.*, or tuning/tune_node.py:63 Fp)
 # ---------------------------------------------------------------------------------------
 @dataclass
@@ -168,6 +305,7 @@ class FuncInfo:
     rate_head_elu: bool = False      # ELU between the last hidden layer and the head (tune_node.py Fp)
     aug_head_elu: bool = False
     kernels: Optional[str] = None    # None: library picks; 'ffma' | 'tensor' pin the RK4 kernel family
+    bayes: bool = False              # Dense_Variational layers: weights re-sampled at every RHS evaluation (rk4, FFMA engine)
 
     def desc(self, batch: int, n_groups: int = 1) -> "_lib.UdeDesc":
         d = _lib.UdeDesc()
@@ -206,10 +344,11 @@ def _linear_chain(net, what: str):
     """Validate Linear, (ELU, Linear)*, [ELU,] Linear (an optional leading Flatten is skipped).
     Returns (linears, elu_before_head)."""
     mods = [m for m in net if not isinstance(m, nn.Flatten)]
+    mods = [_VarLayer(m) if _is_variational(m) else m for m in mods]
     lin: List[nn.Linear] = []
     expect_linear = True
     for i, m in enumerate(mods):
-        if isinstance(m, nn.Linear):
+        if isinstance(m, (nn.Linear, _VarLayer)):
             if m.bias is None:
                 raise UnsupportedFunc(f"{what}: Linear without bias")
             lin.append(m)
@@ -225,8 +364,10 @@ def _linear_chain(net, what: str):
     # the reference puts an ELU before every hidden Linear except the head: positions must be
     # Linear, ELU, Linear, ..., ELU, Linear, Linear
     n_elu = sum(isinstance(m, nn.ELU) for m in mods)
-    if not isinstance(mods[-1], nn.Linear):
+    if not isinstance(mods[-1], (nn.Linear, _VarLayer)):
         raise UnsupportedFunc(f"{what}: the last layer must be Linear")
+    if len({type(l) for l in lin}) != 1:
+        raise UnsupportedFunc(f"{what}: nn.Linear and Dense_Variational layers cannot be mixed")
     head_elu = isinstance(mods[-2], nn.ELU)                  # nn.Sequential style (tuning/tune_node.py:68-75)
     if n_elu != len(lin) - (1 if head_elu else 2):
         raise UnsupportedFunc(f"{what}: layer pattern is not Linear,(ELU,Linear)*,[ELU,]Linear")
@@ -245,8 +386,9 @@ def describe_func(func) -> FuncInfo:
         raise UnsupportedFunc(
             "the fused UDE solver integrates Fp / Fa / FaFp modules (lib/models.py protocol) only; "
             f"got {type(func).__name__}.  There is deliberately no generic-callable or CPU fallback.")
-    if getattr(func, "uncertainty", "none") != "none":
-        raise UnsupportedFunc("Bayesian ODE funcs (per-stage weight re-sampling) are not fused yet")
+    unc = getattr(func, "uncertainty", "none")
+    if unc not in ("none", "bayes"):
+        raise UnsupportedFunc(f"unknown uncertainty mode {unc!r}")
     R = int(getattr(func, "n_regions", getattr(func, "n_region", 0)))
     L = int(func.latent_dim)
     rate: List[nn.Linear] = []
@@ -255,7 +397,7 @@ def describe_func(func) -> FuncInfo:
     if kind == "Fp":
         rate, r_elu = _linear_chain(func.Fp_net if hasattr(func, "Fp_net") else func.net, "Fp net")
     elif kind == "FaFp":
-        rate, r_elu = _linear_chain(func.net, "FaFp.net")
+        rate, r_elu = _linear_chain(func.Fp_net if unc == "bayes" else func.net, "FaFp.net")     # models_bayes.py:194 names it Fp_net
         aug, a_elu = _linear_chain(func.aug_net, "FaFp.aug_net")
     else:
         aug, a_elu = _linear_chain(func.aug_net, "Fa.aug_net")
@@ -264,4 +406,7 @@ def describe_func(func) -> FuncInfo:
             raise UnsupportedFunc("layer widths do not match n_regions * latent_dim / the head size")
     if L < 3:
         raise UnsupportedFunc("latent_dim must be >= 3 (S, I, R)")
-    return FuncInfo(kind, R, L, rate, aug, float(getattr(func, "Fa_w", 1.0)), r_elu, a_elu)
+    bayes = any(isinstance(l, _VarLayer) for l in (*rate, *aug))
+    if bayes != (unc == "bayes"):
+        raise UnsupportedFunc("uncertainty == 'bayes' goes with Dense_Variational layers (and only with them)")
+    return FuncInfo(kind, R, L, rate, aug, float(getattr(func, "Fa_w", 1.0)), r_elu, a_elu, bayes=bayes)

@@ -267,6 +267,73 @@ class _Rk4SolveReparam(torch.autograd.Function):
         return (g_eps, g_std, g_mean, None, None, None, None, None, *grads)
 
 
+class _Rk4SolveBayes(torch.autograd.Function):
+    """(y0, z [4 * n_steps, n_theta]; means..., stds...) -> (y_out, side): Bayesian ODE funcs.  Evaluation e of the
+    solve runs with theta_e = mean + z_e * |std| (models_bayes.py:44-48); the adjoint returns dL/dmean = sum_e dL/dtheta_e and
+    dL/dstd = sign(std) * sum_e dL/dtheta_e * z_e."""
+
+    @staticmethod
+    def forward(ctx, y0, z, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool, n_par: int, *params):
+        L = _lib.lib()
+        dev = y0.device
+        B, R, Ld = y0.shape
+        desc = info.desc(B)
+        desc.flags |= _lib.FLAG_BAYES
+        plan = _lib.UdePlan()
+        with torch.cuda.device(dev):
+            _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan (bayes)")
+            mean = torch.cat([p.detach().reshape(-1) for p in params[:n_par]])
+            std = torch.cat([p.detach().reshape(-1) for p in params[n_par:]])
+            z_c = z.detach().contiguous()
+            theta_e = torch.addcmul(mean, z_c, std.abs())              # [4 * n_steps, n_theta]
+            y0_c = y0.detach().contiguous()
+            y_out = torch.empty((n_out, B, R, Ld), dtype=torch.float32, device=dev)
+            side = torch.empty(8, dtype=torch.float64, device=dev)
+            ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
+            tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
+            dt, out_step, out_kind, out_w = tables
+            st = L.ude_rk4_forward_bayes(C.byref(desc), _ptr(theta_e), _ptr(y0_c), n_steps, _ptr(dt), n_out, _ptr(out_step),
+                                         _ptr(out_kind), _ptr(out_w), _ptr(y_out), _ptr(tape), _ptr(side), _ptr(ws),
+                                         int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward_bayes")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out, ctx.n_par = info, tables, n_steps, n_out, n_par
+        ctx.plan_ws = int(plan.workspace_bytes)
+        empty = torch.empty(0, device=dev)
+        ctx.save_for_backward(theta_e if need_tape else empty, z_c, std, y0_c, tape if need_tape else empty, ws if need_tape else empty)
+        ctx.has_tape = need_tape
+        ctx.param_meta = [(p.shape, p.numel()) for p in params[:n_par]]
+        return y_out, side
+
+    @staticmethod
+    def backward(ctx, g_out, g_side):
+        if not ctx.has_tape:
+            raise RuntimeError("fused odeint was run without a tape (no input required grad)")
+        L = _lib.lib()
+        theta_e, z_c, std, y0_c, tape, ws = ctx.saved_tensors
+        dev = y0_c.device
+        desc = ctx.info.desc(y0_c.shape[0])
+        desc.flags |= _lib.FLAG_BAYES | _lib.FLAG_WEIGHTS_PACKED
+        with torch.cuda.device(dev):
+            if g_out is None:
+                g_out = torch.zeros((ctx.n_out, *y0_c.shape), dtype=torch.float32, device=dev)
+            g_out = g_out.contiguous().float()
+            gs = g_side[:5].to(torch.float32).contiguous() if g_side is not None else None
+            g_y0 = torch.empty_like(y0_c)
+            g2 = torch.empty((2, std.numel()), dtype=torch.float32, device=dev)
+            dt, out_step, out_kind, out_w = ctx.tables
+            st = L.ude_rk4_backward_bayes(C.byref(desc), _ptr(theta_e), _ptr(z_c), _ptr(y0_c), ctx.n_steps, _ptr(dt), ctx.n_out,
+                                          _ptr(out_step), _ptr(out_kind), _ptr(out_w), _ptr(tape), _ptr(g_out), _ptr(gs), _ptr(g_y0),
+                                          _ptr(g2), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward_bayes")
+        g_std = g2[1] * torch.sign(std)
+        gm, gsd, off = [], [], 0
+        for shape, n in ctx.param_meta:
+            gm.append(g2[0, off:off + n].view(shape))
+            gsd.append(g_std[off:off + n].view(shape))
+            off += n
+        return (g_y0, None, None, None, None, None, None, None, *gm, *gsd)
+
+
 class _Rk4SolveDecoded(torch.autograd.Function):
     """(y0 | eps, std, mean; dec_w, dec_b; *params) -> (y_pred [T, B, n_dec], side [8] fp64 with side[7] = the
     latent_init_loss sum): the decoder and the reg loss are applied where the outputs are produced, the trajectories are
@@ -494,6 +561,9 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
 
     group = options.pop("process_group", None)        # fused-path extra: all-reduce the side sums over this group
     info.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)   # fused-path extra: pin the kernel family
+    bayes_z = options.pop("bayes_z", None)            # fused-path extra: the weight noise of a Bayes_* func, [4 * n_steps, n_theta]
+    if bayes_z is not None and not info.bayes:
+        raise ValueError("options['bayes_z'] goes with a Bayes_* func")
     unknown = set(options) - {"step_size", "interp", "perturb", "grid_constructor"}
     if unknown:
         raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
@@ -502,8 +572,21 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         raise NotImplementedError("only step_size grids with linear interpolation are fused")
     (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
     params = [p for l in info.linears() for p in (l.weight, l.bias)]
-    need_tape = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
-    y_out, side = _Rk4Solve.apply(y0, info, tables, n_steps, int(t.numel()), need_tape, *params)
+    if info.bayes:
+        # Bayes_* funcs draw new weights at every RHS evaluation (models_bayes.py:30-48).  The noise of all 4 * n_steps
+        # evaluations comes from ONE torch.randn call on the current CUDA generator (the reference draws layer by layer at each
+        # call: same distribution, different stream); options['bayes_z'] supplies it explicitly (tests, replays).
+        stds = [p for l in info.linears() for p in (l.w_std, l.b_std)]
+        n_theta = sum(p.numel() for p in params)
+        if bayes_z is None:
+            bayes_z = torch.randn(4 * n_steps, n_theta, dtype=torch.float32, device=y0.device)
+        elif tuple(bayes_z.shape) != (4 * n_steps, n_theta) or bayes_z.device != y0.device or bayes_z.dtype != torch.float32:
+            raise ValueError(f"bayes_z must be a float32 [{4 * n_steps}, {n_theta}] tensor on y0's device")
+        need_tape = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (*params, *stds)))
+        y_out, side = _Rk4SolveBayes.apply(y0, bayes_z, info, tables, n_steps, int(t.numel()), need_tape, len(params), *params, *stds)
+    else:
+        need_tape = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
+        y_out, side = _Rk4Solve.apply(y0, info, tables, n_steps, int(t.numel()), need_tape, *params)
     if group is not None:
         from .dist import all_reduce_side
         side = all_reduce_side(side, None if group is True else group)
@@ -524,6 +607,8 @@ def odeint_reparam(func, eps, std, mean, t, *, method="rk4", options=None):
     if eps.dim() != 4 or mean.shape != eps.shape[1:] or std.shape != eps.shape[1:]:
         raise ValueError("eps must be [n_samples, batch, R, L-1] and std / mean [batch, R, L-1]")
     info = describe_func(func)
+    if info.bayes:
+        raise NotImplementedError("Bayes_* funcs go through ude_b200.odeint (method='rk4')")
     if eps.shape[2] != info.n_regions or eps.shape[3] + 1 != info.latent_dim:
         raise ValueError(f"eps must be [n_samples, batch, {info.n_regions}, {info.latent_dim - 1}]")
     for x in (eps, std, mean):
@@ -580,6 +665,8 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
     if method != "rk4":
         raise NotImplementedError("the fused decoder epilogue implements the reference's method, rk4")
     info = describe_func(func)
+    if info.bayes:
+        raise NotImplementedError("Bayes_* funcs go through ude_b200.odeint (method='rk4')")
     lin = _decoder_linear(decoder)
     R, Ld = info.n_regions, info.latent_dim
     if lin.in_features != 3 * R or lin.bias is None:
@@ -637,6 +724,8 @@ def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
         raise ValueError(f"y0 must be [G={len(funcs)}, B_g, R, L]")
     infos = [_check_common(f, y0[g], t, method, None) for g, f in enumerate(funcs)]
     i0 = infos[0]
+    if any(i.bayes for i in infos):
+        raise NotImplementedError("Bayes_* funcs go through ude_b200.odeint (method='rk4')")
     sig0 = (i0.kind, i0.n_regions, i0.latent_dim, [l.weight.shape for l in i0.linears()], float(i0.fa_w),
             i0.rate_head_elu, i0.aug_head_elu)
     for i in infos[1:]:

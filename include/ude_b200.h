@@ -106,6 +106,8 @@ typedef struct UdeDesc {
  * nothing has written to it since, so it still holds the packed weight images -- the adjoint does not build them again.
  * (One launch less per training step; what loss.backward() right after odeint() looks like, lib/VAE.py:201-203.) */
 #define UDE_FLAG_WEIGHTS_PACKED 16
+/* ude_plan only: size the workspace for the ude_rk4_*_bayes entry points (set by them internally for the launch). */
+#define UDE_FLAG_BAYES 32
 
 typedef enum UdeMethod { UDE_METHOD_RK4 = 0, UDE_METHOD_DOPRI5 = 1 } UdeMethod;
 
@@ -253,6 +255,29 @@ int ude_rk4_backward_decoded(const UdeDesc* desc, const float* theta /*dev*/, co
                              const float* g_side /*dev [6] | NULL*/, float* g_y0 /*dev*/, float* g_z /*dev | NULL without rp*/,
                              float* g_theta /*dev*/, float* g_dec /*dev*/, float* dec_partial /*dev scratch*/,
                              void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+/*
+ * Bayesian ODE funcs: Bayes_Fp / Bayes_Fa / Bayes_FaFp of
+ * /root/reference/lib/in_development/models_bayes.py:69-265 are the same three RHS functions over Dense_Variational
+ * layers (:12-48), which draw NEW weights at every forward call, i.e. at every RHS evaluation of the solve:
+ *     w = w_mean + z * |w_std|,  z ~ N(0, 1) per call, shared by the whole batch                    (:30-48)
+ * The caller materialises the 4 * n_steps weight sets (evaluation e = 4 * step + stage, theta layout each):
+ *     theta_evals dev [4 * n_steps, n_theta],   z_evals dev [4 * n_steps, n_theta] (adjoint only)
+ * and the adjoint returns  g_mean_zsum dev [2, n_theta]:  row 0 = sum_e dL/dtheta_e (= dL/dw_mean),
+ * row 1 = sum_e dL/dtheta_e * z_e (dL/dw_std = row 1 * sign(w_std)).  The KL term (get_kl, :118-128) stays with the caller.
+ * FFMA engine; models whose weights and gradient accumulators fit in shared memory (else UDE_ERR_UNSUPPORTED);
+ * workspace from ude_plan() with UDE_FLAG_BAYES set in desc->flags.  Everything else as ude_rk4_forward / _backward.
+ */
+int ude_rk4_forward_bayes(const UdeDesc* desc, const float* theta_evals /*dev*/, const float* y0 /*dev*/, int32_t n_steps,
+                          const float* dt /*dev*/, int32_t n_out, const int32_t* out_step /*dev*/, const int32_t* out_kind /*dev*/,
+                          const float* out_w /*dev*/, float* y_out /*dev*/, float* tape /*dev | NULL*/, double* side /*dev [8]*/,
+                          void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+int ude_rk4_backward_bayes(const UdeDesc* desc, const float* theta_evals /*dev*/, const float* z_evals /*dev*/, const float* y0 /*dev*/,
+                           int32_t n_steps, const float* dt /*dev*/, int32_t n_out, const int32_t* out_step /*dev*/,
+                           const int32_t* out_kind /*dev*/, const float* out_w /*dev*/, const float* tape /*dev*/,
+                           const float* g_out /*dev*/, const float* g_side /*dev | NULL*/, float* g_y0 /*dev*/,
+                           float* g_mean_zsum /*dev [2, n_theta]*/, void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
 
 /* Controller options of torchdiffeq's RKAdaptiveStepsizeODESolver. */
 typedef struct UdeDopri5Opts {

@@ -164,6 +164,29 @@ class OracleFunc(torch.nn.Module):
         return out
 
 
+class BayesOracleFunc(OracleFunc):
+    """The Bayes_Fp / Bayes_Fa / Bayes_FaFp funcs of /root/reference/lib/in_development/models_bayes.py:69-265: the same
+    RHS over Dense_Variational layers, whose weights are re-drawn at EVERY call (:30-48):
+        w = w_mean + z * |w_std|        (z ~ N(0,1) per call; here row ``n_evals`` of the given ``z`` [n_calls, n_theta])
+    ``mean`` / ``std`` are flat in theta order (W then b per layer).  Pinned against the real classes (their ``make_z``
+    replaced by a reader of the same z) in tests/test_bayes.py."""
+
+    def __init__(self, spec: UdeSpec, mean: torch.Tensor, std: torch.Tensor, z: torch.Tensor, fa_w: float = 1.0):
+        super().__init__(spec, mean, fa_w)
+        self.std = torch.nn.Parameter(std.detach().clone())
+        self.z = z.detach().clone()
+
+    def forward(self, t, x):
+        theta_e = self.theta + self.z[self.n_evals] * torch.abs(self.std)
+        f, p, fa = ude_rhs(self.spec, theta_e, x, self.Fa_w)
+        self.n_evals += 1
+        if p is not None:
+            self.params.append(p)
+        if fa is not None:
+            self.tracker.append(fa)
+        return f
+
+
 def theta_from_module(mod: torch.nn.Module) -> Tuple[UdeSpec, torch.Tensor, float]:
     """Read (spec, flat theta, Fa_w) off a reference-protocol module
     (lib.models.Fp / Fa / FaFp or anything with the same attributes)."""

@@ -1,0 +1,194 @@
+"""Bayesian ODE funcs (per-evaluation weight re-sampling, lib/in_development/models_bayes.py).
+CPU part: the oracle's BayesOracleFunc is pinned against the REAL reference classes (where /root/reference exists), and
+the package's mirror classes share their state_dict layout and KL term.  GPU part: the fused kernels against the oracle."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import odeint_ref
+from oracle.ude_rhs import BayesOracleFunc, UdeSpec, synth_y0
+from tests.util import RTOL_PARITY, rel_err
+
+REF = "/root/reference"
+CASES = [("Bayes_Fp", "Fp", 1, 8, (20, 20), ()), ("Bayes_Fa", "Fa", 2, 4, (), (32, 32)), ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64)),
+         ("Bayes_FaFp", "FaFp", 3, 8, (20, 20), (32, 32))]
+
+
+def _build(pkg, cls, R, L, net, aug, seed=0):
+    torch.manual_seed(seed)
+    kw = {}
+    if net:
+        kw["net_sizes"] = list(net)
+    if aug:
+        kw["aug_net_sizes"] = list(aug)
+    return getattr(pkg, cls)(n_regions=R, latent_dim=L, **kw)
+
+
+def _var_layers(mod):
+    nets = [getattr(mod, n) for n in ("Fp_net", "aug_net") if hasattr(mod, n)]
+    return [m for net in nets for m in net if hasattr(m, "w_mean")]
+
+
+def _flat(mod):
+    ls = _var_layers(mod)
+    mean = torch.cat([p.detach().reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)])
+    std = torch.cat([p.detach().reshape(-1) for l in ls for p in (l.w_std, l.b_std)])
+    return mean, std
+
+
+def _feed_z(mod, z):
+    """Replace every layer's make_z by a reader of z[call] (theta order: W then b per layer)."""
+    state = {"call": 0, "seen": 0}
+    ls = _var_layers(mod)
+    offs, off = [], 0
+    for l in ls:
+        offs.append(off)
+        off += l.w_mean.numel() + l.b_mean.numel()
+
+    def make(l, o):
+        def make_z():
+            row = z[state["call"]]
+            nw = l.w_mean.numel()
+            l.z = [row[o:o + nw].reshape(l.w_mean.shape), row[o + nw:o + nw + l.b_mean.numel()]]
+            state["seen"] += 1
+            if state["seen"] == len(ls):
+                state["seen"] = 0
+                state["call"] += 1
+        return make_z
+    for l, o in zip(ls, offs):
+        l.make_z = make(l, o)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "lib")), reason="reference tree not present")
+@pytest.mark.parametrize("cls,kind,R,L,net,aug", CASES)
+def test_oracle_matches_real_reference_bayes_classes(cls, kind, R, L, net, aug):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import lib.in_development.models_bayes as ref
+    mod = _build(ref, cls, R, L, net, aug)
+    mean, std = _flat(mod)
+    with torch.no_grad():       # negative stds exercise the |.|
+        for l in _var_layers(mod)[:1]:
+            l.w_std.mul_(-1.0)
+    mean, std = _flat(mod)
+    spec = UdeSpec(kind, R, L, tuple(net), tuple(aug))
+    t = torch.arange(4.)
+    n_calls = 4 * 3
+    z = torch.randn(n_calls, mean.numel(), generator=torch.Generator().manual_seed(5))
+    y0 = synth_y0(6, R, L, seed=1)
+    _feed_z(mod, z)
+    y0a = y0.clone().requires_grad_(True)
+    ya = odeint_ref.odeint(mod, y0a, t, method="rk4", options=dict(step_size=1.0))
+    f = BayesOracleFunc(spec, mean, std, z)
+    y0b = y0.clone().requires_grad_(True)
+    yb = odeint_ref.odeint(f, y0b, t, method="rk4", options=dict(step_size=1.0))
+    assert torch.equal(ya, yb)
+    G = torch.randn(ya.shape, generator=torch.Generator().manual_seed(6))
+    (ya * G).sum().backward()
+    (yb * G).sum().backward()
+    assert rel_err(y0b.grad, y0a.grad) <= 2e-6          # same graph up to the order of a few additions
+    ls = _var_layers(mod)
+    gm = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)])
+    gs = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_std, l.b_std)])
+    assert rel_err(f.theta.grad, gm) <= 2e-6 and rel_err(f.std.grad, gs) <= 2e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "lib")), reason="reference tree not present")
+@pytest.mark.parametrize("cls,kind,R,L,net,aug", CASES)
+def test_mirror_classes_interchange_checkpoints_and_kl(cls, kind, R, L, net, aug):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import lib.in_development.models_bayes as ref
+
+    import ude_b200
+    a, b = _build(ref, cls, R, L, net, aug, seed=3), _build(ude_b200, cls, R, L, net, aug, seed=4)
+    assert list(a.state_dict().keys()) == list(b.state_dict().keys())
+    b.load_state_dict(a.state_dict(), strict=True)
+    assert b.uncertainty == "bayes" and b.ode_type == a.ode_type
+    assert float(a.get_kl()) == pytest.approx(float(b.get_kl()), rel=1e-6)
+    info = ude_b200.describe_func(b)
+    assert info.bayes and info.kind == kind
+    assert ude_b200.describe_func(a).bayes          # the reference's own instance is recognised as well
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls,kind,R,L,net,aug,B,grid", [
+    ("Bayes_Fp", "Fp", 1, 8, (20, 20), (), 300, "weekly"),
+    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 200, "weekly"),
+    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 150, "interp"),
+    ("Bayes_Fa", "Fa", 2, 4, (), (32, 32), 97, "weekly"),
+    ("Bayes_FaFp", "FaFp", 3, 8, (20, 20), (32, 32), 120, "daily"),
+    ("Bayes_Fp", "Fp", 2, 3, (20, 20), (), 64, "weekly"),
+])
+def test_fused_bayes_solve_matches_oracle(cls, kind, R, L, net, aug, B, grid):
+    import ude_b200
+    mod = _build(ude_b200, cls, R, L, net, aug, seed=7)
+    with torch.no_grad():
+        for l in _var_layers(mod):
+            l.w_std.mul_(0.3)
+            l.b_std.mul_(0.3)
+        _var_layers(mod)[0].w_std.mul_(-1.0)
+        if aug:     # keep the correction term small (see oracle.ude_rhs.init_theta)
+            mod.aug_net[-1].w_mean.mul_(0.05); mod.aug_net[-1].b_mean.mul_(0.05); mod.aug_net[-1].w_std.mul_(0.05); mod.aug_net[-1].b_std.mul_(0.05)
+    mean, std = _flat(mod)
+    spec = UdeSpec(kind, R, L, tuple(net), tuple(aug))
+    if grid == "weekly":
+        t, h = torch.arange(5.), 1.0
+    elif grid == "daily":
+        t = torch.arange(15.) / 7
+        h = t[1] - t[0]
+    else:
+        t, h = torch.linspace(1, 21, 21) / 7, 1.0
+    n_steps = {"weekly": 4, "daily": 14, "interp": 3}[grid]
+    z = torch.randn(4 * n_steps, mean.numel(), generator=torch.Generator().manual_seed(11))
+    y0 = synth_y0(B, R, L, seed=2)
+    G = torch.randn(t.numel(), B, R, L, generator=torch.Generator().manual_seed(12))
+    c = torch.tensor([0.3, -0.2, 0.1])
+
+    def loss(y, f):
+        out = (y * G.to(y.device)).sum()
+        if spec.has_rate:
+            post = f.posterior()
+            out = out + c[0] * post.mean.sum() * B + c[1] * post.stddev.sum() * B
+        if spec.has_aug:
+            out = out + c[2] * torch.norm(torch.stack(f.tracker)) * B ** 0.5
+        return out
+
+    f = BayesOracleFunc(spec, mean, std, z)
+    y0r = y0.clone().requires_grad_(True)
+    yr = odeint_ref.odeint(f, y0r, t, method="rk4", options=dict(step_size=h))
+    assert f.n_evals == 4 * n_steps
+    loss(yr, f).backward()
+
+    mod = mod.cuda()
+    y0g = y0.cuda().requires_grad_(True)
+    mod.clear_tracking()
+    y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=h, bayes_z=z.cuda()))
+    loss(y, mod).backward()
+    ls = _var_layers(mod)
+    gm = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)])
+    gs = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_std, l.b_std)])
+    assert rel_err(y, yr) <= RTOL_PARITY
+    assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
+    assert rel_err(gm, f.theta.grad) <= RTOL_PARITY
+    assert rel_err(gs, f.std.grad) <= RTOL_PARITY
+
+
+@pytest.mark.gpu
+def test_bayes_default_noise_and_rejections():
+    import ude_b200
+    mod = _build(ude_b200, "Bayes_FaFp", 1, 8, (20, 20), (32, 32)).cuda()
+    y0 = synth_y0(64, 1, 8, seed=3).cuda()
+    t = torch.arange(4.)
+    torch.manual_seed(0)
+    ya = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0))
+    torch.manual_seed(0)
+    yb = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0))
+    yc = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0))
+    assert torch.equal(ya, yb) and not torch.equal(ya, yc)          # noise from the CUDA generator: reproducible, re-drawn per call
+    with pytest.raises(ude_b200.UdeError):
+        ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0, kernels="tensor"))
+    with pytest.raises(NotImplementedError):
+        ude_b200.odeint(mod, y0, t, method="dopri5", options=dict(per_trajectory=True))
