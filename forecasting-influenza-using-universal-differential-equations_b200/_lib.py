@@ -83,6 +83,8 @@ class UdeDopri5Opts(C.Structure):
         ("dfactor", C.c_double),
         ("max_steps", C.c_int32),
         ("max_attempts", C.c_int32),
+        ("shared_step", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -216,7 +218,7 @@ def lib() -> C.CDLL:
 
 
 class UdeError(RuntimeError):
-    pass
+    status = None       # the UdeStatus code when the error came from the C ABI
 
 
 def check(status: int, what: str) -> None:
@@ -225,4 +227,6 @@ def check(status: int, what: str) -> None:
         msg = L.ude_strerror(status).decode()
         if status == -4:
             msg += " — " + L.ude_last_cuda_error().decode()
-        raise UdeError(f"{what}: {msg} (status {status})")
+        err = UdeError(f"{what}: {msg} (status {status})")
+        err.status = status
+        raise err

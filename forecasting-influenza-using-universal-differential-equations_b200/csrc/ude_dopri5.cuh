@@ -11,10 +11,13 @@
 //   tx[s][i][d][b]  stage inputs x_1..x_6 (x_1 = y_s); step index n_accept holds the final state
 //   tt[s][b]        (t0, dt) as two fp64
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ude_engine.cuh"
 #include "ude_rk4.cuh"
 
 namespace ude {
+namespace cg = cooperative_groups;
 
 constexpr int kDopriStages = 6;          // stage inputs stored per accepted step
 constexpr int kMaxTB = 64;
@@ -41,6 +44,9 @@ struct DopriOpts {
     float rtol, atol;
     double first_step, safety, ifactor, dfactor;
     int max_steps, max_attempts;
+    int shared_step;        // torchdiffeq's batch semantics: ONE error norm (RMS over the whole [B,R,L] tensor), one dt and one
+                            // accept / reject decision for all trajectories; the grid is launched cooperatively (one tile per CTA)
+                            // and the norms are summed across CTAs (warp shuffles -> CTA -> global partials -> grid barrier)
 };
 
 struct DopriFwdArgs {
@@ -56,6 +62,7 @@ struct DopriFwdArgs {
     float* cold;
     long long B;
     DopriOpts o;
+    double* gpart;          // shared_step: [2][gridDim.x][2] partial sums of the batch-wide norms
 };
 
 struct DopriBwdArgs {
@@ -141,9 +148,43 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     const float rtol = a.o.rtol, atol = a.o.atol;
     const float inv_n = 1.0f / (float)(R * L);
     const long long stage_sz = (long long)Dn * B;
+    // ---- shared-step mode: batch-wide sums of two per-trajectory quantities (threads >= TB contribute 0).  Fixed summation
+    // order everywhere (shuffle tree, warps in order, CTAs in order): every CTA computes the SAME bits and takes the same decision.
+    const bool shared = a.o.shared_step != 0;
+    const double inv_nB = 1.0 / ((double)B * R * L);
+    __shared__ double s_tot[2];
+    int gphase = 0;
+    auto grid_sum2 = [&](double v0, double v1, double& t0, double& t1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        if (lane == 0) { red[2 * warp] = v0; red[2 * warp + 1] = v1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c0 = 0.0, c1 = 0.0;
+            for (int w = 0; w < kWarps; ++w) { c0 += red[2 * w]; c1 += red[2 * w + 1]; }
+            double* dst = a.gpart + ((size_t)gphase * gridDim.x + blockIdx.x) * 2;
+            dst[0] = c0; dst[1] = c1;
+            __threadfence();
+        }
+        cg::this_grid().sync();
+        if (threadIdx.x == 0) {
+            const volatile double* src = a.gpart + (size_t)gphase * gridDim.x * 2;
+            double c0 = 0.0, c1 = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c) { c0 += src[2 * c]; c1 += src[2 * c + 1]; }
+            s_tot[0] = c0; s_tot[1] = c1;
+        }
+        __syncthreads();
+        t0 = s_tot[0]; t1 = s_tot[1];
+        gphase ^= 1;
+        __syncthreads();
+    };
 
     // one RHS evaluation at X; `record`: 0 none, 1 straight into the thread's accumulators, 2 into SA (attempt)
     auto eval_into = [&](float* Kdst, int record, int nvalid) {
+        if (shared) record = 1;     // the reference's lists hold EVERY evaluation: probe and rejected attempts included
         if (ring) rhs_forward_layers_ring(P, wr, smem, warp, lane, 0u);
         else rhs_forward_layers(P, Wp, smem, warp, lane);
         for (int idx = threadIdx.x; idx < R * TB; idx += kThreads) {
@@ -219,11 +260,15 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 SA[0 * RS + r * TBP + b] = s1;          // SA is free until the first attempt
             }
             __syncthreads();
+            float s0 = 0.f, s1 = 0.f;
+            if (threadIdx.x < TB)
+                for (int r = 0; r < R; ++r) { s0 += PART[r * TBP + threadIdx.x]; s1 += SA[r * TBP + threadIdx.x]; }
+            double g0 = 0.0, g1 = 0.0;
+            if (shared) grid_sum2(threadIdx.x < nvalid ? (double)s0 : 0.0, threadIdx.x < nvalid ? (double)s1 : 0.0, g0, g1);
             if (threadIdx.x < TB) {
                 const int b = threadIdx.x;
-                float s0 = 0.f, s1 = 0.f;
-                for (int r = 0; r < R; ++r) { s0 += PART[r * TBP + b]; s1 += SA[r * TBP + b]; }
-                const float d0 = sqrtf(s0 * inv_n), d1 = sqrtf(s1 * inv_n);
+                const float d0 = shared ? sqrtf((float)(g0 * inv_nB)) : sqrtf(s0 * inv_n);
+                const float d1 = shared ? sqrtf((float)(g1 * inv_nB)) : sqrtf(s1 * inv_n);
                 const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : fabsf(0.01f * d0 / d1);
                 s_h0[b] = h0;
                 s_dtold[b] = d1;
@@ -251,12 +296,15 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 for (int c = 0; c < 3; ++c) smem[P.off_X + (3 * r + c) * TBP + b] = SY[(3 * r + c) * TBP + b];
             }
             __syncthreads();
+            float s2 = 0.f;
+            if (threadIdx.x < TB)
+                for (int r = 0; r < R; ++r) s2 += PART[r * TBP + threadIdx.x];
+            double g2 = 0.0, g2b = 0.0;
+            if (shared) grid_sum2(threadIdx.x < nvalid ? (double)s2 : 0.0, 0.0, g2, g2b);
             if (threadIdx.x < TB) {
                 const int b = threadIdx.x;
-                float s2 = 0.f;
-                for (int r = 0; r < R; ++r) s2 += PART[r * TBP + b];
                 const float h0 = s_h0[b], d1 = s_dtold[b];
-                const float d2 = fabsf(sqrtf(s2 * inv_n) / h0);
+                const float d2 = fabsf((shared ? sqrtf((float)(g2 * inv_nB)) : sqrtf(s2 * inv_n)) / h0);
                 float h1;
                 if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
                 else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
@@ -342,12 +390,15 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 PART[r * TBP + b] = s;
             }
             __syncthreads();
+            float s_err = 0.f;
+            if (threadIdx.x < TB)
+                for (int r = 0; r < R; ++r) s_err += PART[r * TBP + threadIdx.x];
+            double ge = 0.0, geb = 0.0;
+            if (shared) grid_sum2(threadIdx.x < nvalid ? (double)s_err : 0.0, 0.0, ge, geb);
             if (threadIdx.x < TB) {
                 const int b = threadIdx.x;
                 const bool active = s_j[b] < a.n_out && s_status[b] == 0;
-                float s = 0.f;
-                for (int r = 0; r < R; ++r) s += PART[r * TBP + b];
-                const float ratio = sqrtf(s * inv_n);
+                const float ratio = shared ? sqrtf((float)(ge * inv_nB)) : sqrtf(s_err * inv_n);
                 const bool accept = active && (ratio <= 1.0f);
                 const double dt = s_dt[b];
                 double dt_next;
@@ -405,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                         SY[row] = y1v;
                         SK[row] = f1;                               // FSAL
                     }
-                    if (b < nvalid) {
+                    if (b < nvalid && !shared) {
                         side.sb += SA[0 * RS + o]; side.sg += SA[1 * RS + o]; side.sb2 += SA[2 * RS + o];
                         side.sg2 += SA[3 * RS + o]; side.sf2 += SA[4 * RS + o];
                         side.rows += 6;

@@ -11,6 +11,7 @@ static int dopri_opts(const UdeDopri5Opts* o, DopriOpts& d) {
     d.dfactor = o->dfactor > 0 ? o->dfactor : 0.2;
     d.max_steps = o->max_steps;
     d.max_attempts = o->max_attempts;
+    d.shared_step = o->shared_step != 0;
     return UDE_OK;
 }
 }  // namespace ude
@@ -49,11 +50,17 @@ int ude_dopri5_forward(const UdeDesc* desc, const UdeDopri5Opts* opts, const flo
     a.cold = w.cold;
     a.B = desc->batch;
     a.o = o;
+    a.gpart = reinterpret_cast<double*>(w.slabs);      // the adjoint's slab area is idle in the forward (>= 4 * n_ctas doubles)
+    if (o.shared_step && (desc->batch + P.TB - 1) / P.TB > n_ctas) return UDE_ERR_CAPACITY;     // one resident tile per CTA
     const int smem = P.smem_floats * 4;
+    void* kargs[2] = {&P, &a};
 #define UDE_LAUNCH_DFWD(W, C)                                                             \
     do {                                                                                  \
         if ((st = set_smem(dopri5_fwd_kernel<W, C>, smem)) != UDE_OK) return st;          \
-        dopri5_fwd_kernel<W, C><<<n_ctas, kThreads, smem, s>>>(P, a);                     \
+        if (o.shared_step)                                                                \
+            UDE_CUDA(cudaLaunchCooperativeKernel((const void*)dopri5_fwd_kernel<W, C>, dim3(n_ctas), dim3(kThreads), kargs, smem, s)); \
+        else                                                                              \
+            dopri5_fwd_kernel<W, C><<<n_ctas, kThreads, smem, s>>>(P, a);                 \
     } while (0)
     if (P.cold_global) UDE_LAUNCH_DFWD(false, true);
     else if (P.w_in_smem) UDE_LAUNCH_DFWD(true, false);

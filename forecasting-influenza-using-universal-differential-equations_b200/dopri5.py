@@ -1,10 +1,19 @@
 """Adaptive Dopri5 front end — ``odeint(func, y0, t, rtol=, atol=)`` with torchdiffeq's default
 method (the one the reference reaches at /root/reference/lib/train_functions.py:190).
 
-Batch semantics: torchdiffeq uses ONE step size for the whole batch (RMS error norm over the
-entire tensor).  The fused kernels run one controller PER TRAJECTORY, i.e. exactly what
-torchdiffeq computes when called on each row alone (B == 1); see DESIGN.md.  Side channels
-cover accepted stages only (1 + 6 * n_accept evaluations per trajectory).
+Batch semantics.  torchdiffeq uses ONE step size for the whole batch (RMS error norm over the
+entire tensor).  Two fused modes:
+* shared step (``options['per_trajectory'] = False``, and the DEFAULT when the batch fits one
+  resident tile per SM): torchdiffeq's semantics -- one norm, one dt, one accept / reject for
+  all trajectories (cooperative launch, batch-wide norms summed across CTAs); the side channels
+  cover EVERY evaluation (the initial-step probe and rejected attempts too), as the reference's
+  python lists do.
+* per trajectory (``options['per_trajectory'] = True``; the fallback, with a warning, for
+  batches beyond the shared mode's capacity): one controller per trajectory, i.e. what
+  torchdiffeq computes when called on each row alone (B == 1); side channels cover accepted
+  stages only (1 + 6 * n_accept evaluations per trajectory).  See DESIGN.md.
+The adjoint replays the accepted steps with their step sizes frozen (discrete adjoint of the
+accepted-step map); side-channel cotangents act through accepted evaluations.
 
 Extra (fused-path only) options: ``max_accepted_steps`` (tape capacity, default 256) and
 ``return_stats=True`` -> ``(y, stats)`` with per-trajectory accepted / rejected counts.
@@ -34,18 +43,10 @@ def _opts(rtol, atol, options, batch: int = 1) -> "_lib.UdeDopri5Opts":
     unknown = set(options) - known
     if unknown:
         raise ValueError(f"unexpected dopri5 options {sorted(unknown)}")
-    if options.get("per_trajectory", None) is False:
-        raise NotImplementedError("the fused Dopri5 runs one controller per trajectory (see DESIGN.md); "
-                                  "torchdiffeq's shared-step batch control (one RMS norm and one dt for the whole "
-                                  "tensor) is not fused")
-    if batch > 1 and "per_trajectory" not in options:
-        # the default call must not silently differ from torchdiffeq's batch semantics: say so, once per site
-        warnings.warn(
-            "ude_b200.odeint(method='dopri5') controls the step size PER TRAJECTORY (= torchdiffeq applied to every row "
-            "alone); torchdiffeq itself uses one error norm and one step size for the whole batch, and its side-channel "
-            "lists also hold rejected and probe evaluations.  Results agree to the controller's tolerance, not step for "
-            "step.  Pass options={'per_trajectory': True} to acknowledge.", PerTrajectoryStepControl, stacklevel=4)
     o = _lib.UdeDopri5Opts()
+    # per_trajectory: True -> one controller per row; False -> torchdiffeq's shared step (error if the batch does not fit);
+    # absent -> shared step when it fits, else per trajectory with a warning (dopri5_solve)
+    o.shared_step = 0 if (options.get("per_trajectory", None) is True or batch == 1) else 1
     o.rtol = float(rtol)
     o.atol = float(atol)
     fs = options.get("first_step", None)
@@ -136,7 +137,19 @@ def dopri5_solve(func, info: FuncInfo, y0, t_cpu, rtol, atol, options):
     t_dev = t_cpu.to(torch.float64).to(y0.device)
     theta = info.theta()
     need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
-    y_out, side, counts = _Dopri5Solve.apply(theta, y0, info, t_dev, opts, need_tape)
+    try:
+        y_out, side, counts = _Dopri5Solve.apply(theta, y0, info, t_dev, opts, need_tape)
+    except _lib.UdeError as e:
+        if not (opts.shared_step and e.status == _lib.UDE_ERR_CAPACITY and "per_trajectory" not in options):
+            raise
+        # the default call must not silently differ from torchdiffeq's batch semantics: say so
+        warnings.warn(
+            f"ude_b200.odeint(method='dopri5'): a batch of {int(y0.shape[0])} trajectories exceeds the shared-step mode (one "
+            "resident tile per SM); falling back to one controller PER TRAJECTORY (= torchdiffeq applied to every row alone). "
+            "Results agree to the controller's tolerance, not step for step, and the side channels then cover accepted stages "
+            "only.  Pass options={'per_trajectory': True} to acknowledge.", PerTrajectoryStepControl, stacklevel=3)
+        opts.shared_step = 0
+        y_out, side, counts = _Dopri5Solve.apply(theta, y0, info, t_dev, opts, need_tape)
     worst = int(counts[:, 2].max())          # torchdiffeq asserts on these conditions; so do we
     if worst != 0:
         raise _lib.UdeError("fused dopri5: " + STATUS_TEXT.get(worst, f"status {worst}"))

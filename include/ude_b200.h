@@ -286,6 +286,12 @@ typedef struct UdeDopri5Opts {
     double  safety, ifactor, dfactor;   /* 0.9, 10, 0.2                            */
     int32_t max_steps;           /* cap on ACCEPTED steps per trajectory (tape)   */
     int32_t max_attempts;        /* cap on attempted steps per trajectory         */
+    int32_t shared_step;         /* 0: one controller per trajectory.  1: torchdiffeq's batch semantics -- ONE RMS error norm
+                                  * over the whole [B,R,L] tensor, one dt, one accept / reject for all trajectories (cooperative
+                                  * launch, norms summed across CTAs); side sums then cover EVERY evaluation (initial-step probe
+                                  * and rejected attempts too, as the reference's lists do).  Needs batch <= tile_traj * n_ctas of
+                                  * ude_plan (UDE_ERR_CAPACITY otherwise).                                                 */
+    int32_t reserved;
 } UdeDopri5Opts;
 
 /*

@@ -158,7 +158,8 @@ def _select_initial_step(func, t0, y0, order, rtol, atol, f0, per_traj):
     y1 = y0 + _bc(h0, y0, per_traj) * f0
     n_p0, n_f0 = _side_lens(func)
     f1 = func(t0 + h0, y1)
-    _side_pop(func, n_p0, n_f0)      # probe evaluation: not a side-channel row of the fused path
+    if per_traj:
+        _side_pop(func, n_p0, n_f0)  # per-trajectory mode (not torchdiffeq's): the probe is not a side-channel row of the fused path
     d2 = torch.abs(_rms((f1 - f0) / scale, per_traj) / h0)
     tiny = (d1 <= 1e-15) & (d2 <= 1e-15)
     h1 = torch.where(tiny,
@@ -266,9 +267,10 @@ def _integrate_dopri5(func, y0, t, rtol, atol, options):
             for alpha_i, beta_i in zip(DOPRI5_ALPHA, DOPRI5_BETA):
                 yi = y_cur + _weighted_sum(ks, beta_i, dts)
                 ks.append(func(t1c + alpha_i * dt, yi))
-            # side channels: the fused path tracks ACCEPTED stages only;
-            # pull this attempt's rows back out and re-append them below if accepted.
-            side_p, side_f = _side_pop(func, n_p0, n_f0)
+            # side channels: torchdiffeq (shared step) leaves EVERY evaluation in the reference's lists, rejected attempts
+            # included; the per-trajectory mode of the fused path tracks ACCEPTED stages only: pull this
+            # attempt's rows back out and re-append them below if accepted.
+            side_p, side_f = _side_pop(func, n_p0, n_f0) if per_traj else ([], [])
             y1 = yi                                                 # c_sol == beta[-1] (FSAL)
             f1 = ks[-1]
             with torch.no_grad():

@@ -1,4 +1,4 @@
-"""GPU parity of the fused per-trajectory Dopri5 (forward + adjoint over the accepted-step tape)."""
+"""GPU parity of the fused Dopri5 (per-trajectory and shared-step controllers; forward + adjoint over the accepted-step tape)."""
 import numpy as np
 import pytest
 import torch
@@ -15,6 +15,7 @@ def _solve(g, **extra):
     mod.clear_tracking()
     if float(g["first_step"]) > 0:
         extra.setdefault("first_step", float(g["first_step"]))
+    extra.setdefault("per_trajectory", True)            # the goldens hold per-trajectory solves
     y, stats = ude_b200.odeint(mod, y0, torch.from_numpy(g["t"]), rtol=float(g["rtol"]), atol=float(g["atol"]),
                                options=dict(return_stats=True, **extra))
     return mod, y0, y, stats
@@ -99,7 +100,7 @@ def test_step_count_agreement_large_batch():
     ref = odeint_ref.odeint(OracleFunc(spec, theta), y0, t, rtol=1e-5, atol=1e-9, options=dict(per_trajectory=True, stats=st))
     mod = module_from_spec(spec, theta, 1.0, "cuda")
     with torch.no_grad():
-        y, stats = ude_b200.odeint(mod, y0.cuda(), t, rtol=1e-5, atol=1e-9, options=dict(return_stats=True))
+        y, stats = ude_b200.odeint(mod, y0.cuda(), t, rtol=1e-5, atol=1e-9, options=dict(return_stats=True, per_trajectory=True))
     same = (stats.n_accept.cpu().long() == st.n_accept).float().mean().item()
     err = rel_err(y, ref)
     print(f"accepted-step counts identical for {same * 100:.1f}% of trajectories; max rel err {err:.3e}")
@@ -114,24 +115,99 @@ def test_failure_status_is_reported():
         _solve(g, max_num_steps=2)
 
 
-def test_batch_semantics_must_be_acknowledged():
-    """torchdiffeq steps the whole batch with ONE step size; the fused path controls every trajectory on its own.  The
-    default call on a batch says so; B == 1 (where the two coincide) and an explicit
-    options['per_trajectory'] = True are silent; the shared-step mode is an explicit error, not a silent substitute."""
+def test_batch_semantics():
+    """torchdiffeq steps the whole batch with ONE step size.  The default call does the same (shared-step mode) whenever the
+    batch fits one resident tile per SM; beyond that it falls back to one controller per trajectory and SAYS so (ADVICE r1);
+    options['per_trajectory'] = True / False pin the mode (False on an oversized batch is an error, not a silent substitute)."""
     import warnings
 
     import ude_b200
+    from oracle.ude_rhs import synth_y0
     from ude_b200.dopri5 import PerTrajectoryStepControl
     g = load_golden("dopri5_fafp_r1")
     mod = module_from_spec(g["spec"], torch.from_numpy(g["theta"]), g["fa_w"], "cuda")
     y0 = torch.from_numpy(g["y0"]).cuda()
     t = torch.from_numpy(g["t"])
+    big = synth_y0(148 * 64 + 1, 1, 8, seed=0).cuda()
     with torch.no_grad():
-        with pytest.warns(PerTrajectoryStepControl):
-            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9)
         with warnings.catch_warnings():
             warnings.simplefilter("error", PerTrajectoryStepControl)
+            _, st_def = ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(return_stats=True))
+            _, st_sh = ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(return_stats=True, per_trajectory=False))
+            _, st_pt = ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(return_stats=True, per_trajectory=True))
             ude_b200.odeint(mod, y0[:1], t, rtol=1e-5, atol=1e-9)
-            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(per_trajectory=True))
-        with pytest.raises(NotImplementedError):
-            ude_b200.odeint(mod, y0, t, rtol=1e-5, atol=1e-9, options=dict(per_trajectory=False))
+        assert int(st_def.n_attempts.min()) == int(st_def.n_attempts.max())          # one controller for the whole batch
+        assert torch.equal(st_def.n_accept, st_sh.n_accept)
+        assert int(st_pt.n_attempts.min()) != int(st_pt.n_attempts.max())            # one per trajectory
+        with pytest.warns(PerTrajectoryStepControl):
+            ude_b200.odeint(mod, big, t, rtol=1e-3, atol=1e-6)
+        with pytest.raises(ude_b200.UdeError):
+            ude_b200.odeint(mod, big, t, rtol=1e-3, atol=1e-6, options=dict(per_trajectory=False))
+
+
+@pytest.mark.parametrize("R,B,rtol,first_step", [(1, 700, 1e-5, None), (3, 257, 1e-4, None), (49, 2048, 1e-5, None), (1, 300, 1e-1, 0.01)])
+def test_shared_step_mode_is_torchdiffeq_on_the_batch(R, B, rtol, first_step):
+    """Shared-step mode against the oracle's restatement of torchdiffeq on the WHOLE batch tensor: same accepted / rejected
+    step sequence, same outputs, and side sums over every evaluation (2 + 6 * attempts calls, or 1 + 6 * attempts with a given
+    first step), exactly what the reference's python lists would hold."""
+    import ude_b200
+    from oracle import odeint_ref
+    from oracle.ude_rhs import OracleFunc, UdeSpec, init_theta, synth_y0
+    spec = UdeSpec("FaFp", R, 8, (64, 64, 32), (64, 64))
+    theta = init_theta(spec, seed=21)
+    y0 = synth_y0(B, R, 8, seed=22)
+    t = torch.arange(9.) if R < 49 else torch.arange(5.)
+    atol = 1e-9 if rtol < 1e-2 else 1e-1
+    opts = {} if first_step is None else dict(first_step=first_step)
+    f = OracleFunc(spec, theta)
+    st = odeint_ref.Dopri5Stats()
+    with torch.no_grad():
+        ref = odeint_ref.odeint(f, y0, t, rtol=rtol, atol=atol, options=dict(stats=st, **opts))
+    sums = f.side_sums()
+    mod = module_from_spec(spec, theta, 1.0, "cuda")
+    mod.clear_tracking()
+    with torch.no_grad():
+        y, stats = ude_b200.odeint(mod, y0.cuda(), t, rtol=rtol, atol=atol, options=dict(return_stats=True, per_trajectory=False, **opts))
+    n_acc, n_att = int(stats.n_accept[0]), int(stats.n_attempts[0])
+    assert int(stats.n_accept.min()) == int(stats.n_accept.max()) == n_acc
+    print(f"R={R} B={B}: accepted {n_acc} (oracle {int(st.n_accept)}), attempts {n_att} (oracle {int(st.n_accept + st.n_reject)}), "
+          f"max rel err {rel_err(y, ref):.2e}")
+    assert n_acc == int(st.n_accept) and n_att == int(st.n_accept + st.n_reject)
+    assert rel_err(y, ref) <= RTOL_PARITY
+    # posterior() over every evaluation: mean and unbiased std of (beta, gamma), and ||tracker||_F
+    n_rows = float(sums[5])
+    assert n_rows == B * R * (f.n_evals)
+    post = mod.posterior()
+    mean_ref = sums[0:2] / n_rows
+    std_ref = torch.sqrt((sums[2:4] - n_rows * mean_ref ** 2) / (n_rows - 1))
+    # statistics of an ADAPTIVE solve are as good as the solve: two fp32 implementations agree to the controller's tolerance
+    # (10 x rtol bar, as for the trajectories of the per-trajectory mode), to the parity bar when no decision is data dependent
+    bar = RTOL_PARITY if first_step is not None else max(RTOL_PARITY, 10 * rtol)
+    assert rel_err(post.mean, mean_ref) <= bar and rel_err(post.stddev, std_ref) <= 10 * bar
+    assert abs(float(torch.norm(torch.stack(mod.tracker))) - float(sums[4].sqrt())) <= bar * float(sums[4].sqrt())
+
+
+def test_shared_step_backward_deterministic_controller():
+    """With a controller that takes no data-dependent decision (every step accepted, growth capped by ifactor, first step given)
+    autograd through torchdiffeq has nothing to differentiate in the step sizes: the fused adjoint must match it."""
+    import ude_b200
+    from oracle import odeint_ref
+    from oracle.ude_rhs import OracleFunc, UdeSpec, init_theta, synth_y0
+    spec = UdeSpec("FaFp", 1, 8, (64, 64, 32), (64, 64))
+    theta = init_theta(spec, seed=5)
+    B = 333
+    y0 = synth_y0(B, 1, 8, seed=6)
+    t = torch.arange(5.)
+    G = torch.randn(5, B, 1, 8, generator=torch.Generator().manual_seed(7))
+    kw = dict(rtol=1e-1, atol=1e-1)
+    f = OracleFunc(spec, theta)
+    y0r = y0.clone().requires_grad_(True)
+    yr = odeint_ref.odeint(f, y0r, t, options=dict(first_step=0.01), **kw)
+    (yr * G).sum().backward()
+    mod = module_from_spec(spec, theta, 1.0, "cuda")
+    y0g = y0.cuda().requires_grad_(True)
+    y = ude_b200.odeint(mod, y0g, t, options=dict(first_step=0.01, per_trajectory=False), **kw)
+    (y * G.cuda()).sum().backward()
+    assert rel_err(y, yr) <= RTOL_PARITY
+    assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
+    assert rel_err(flat_grad(mod), f.theta.grad) <= RTOL_PARITY

@@ -142,10 +142,14 @@ def test_dopri5_per_trajectory_equals_batch_of_one_runs():
     for b in range(5):
         f.clear_tracking()
         s1 = odeint_ref.Dopri5Stats()
-        yb = odeint_ref.odeint(f, y0[b:b + 1], t, rtol=1e-6, atol=1e-9, options=dict(stats=s1))
-        acc += f.side_sums()
+        yb = odeint_ref.odeint(f, y0[b:b + 1], t, rtol=1e-6, atol=1e-9, options=dict(stats=s1))       # torchdiffeq's own (shared) mode
+        n_calls = f.side_sums()[5]
         assert float((ya[:, b:b + 1] - yb).abs().max()) < 1e-9
         assert int(st.n_accept[b]) == s1.n_accept and int(st.n_reject[b]) == s1.n_reject
+        assert int(n_calls) == 2 + 6 * (s1.n_accept + s1.n_reject)     # its lists hold EVERY evaluation (probe, rejected attempts)
+        f.clear_tracking()
+        odeint_ref.odeint(f, y0[b:b + 1], t, rtol=1e-6, atol=1e-9, options=dict(per_trajectory=True))   # accepted stages only
+        acc += f.side_sums()
     assert rel_err(total_side, acc) < 1e-9
 
 
