@@ -395,6 +395,21 @@ def secondary_configs(dev, ffma_peak_tflops: float, with_cpu: bool) -> dict:
         sec, kind = cpu_reference_step(2048, 1, 2, spec1, t)
         rec["cpu_ms_per_iter_1_thread"] = sec * 1e3
         rec["cpu_kind"] = kind
+    # the same iteration + a capturable Adam step replayed from ONE CUDA graph (ude_b200.GraphedIteration); a fresh
+    # module: its gradient buffers are created on the capture stream
+    try:
+        mod_g = _module(spec1, init_theta(spec1, 0), dev)
+        opt = torch.optim.Adam(mod_g.parameters(), lr=1e-3, capturable=True)
+
+        def step_fn(y):
+            mod_g.clear_tracking()
+            yy = ude_b200.odeint(mod_g, y, t, method="rk4", options=dict(step_size=t[1] - t[0]))
+            return (yy[..., 1] ** 2).mean()
+        it = ude_b200.GraphedIteration(step_fn, list(mod_g.parameters()), opt, grad_lim=300.0)
+        rec["ms_per_iter_cuda_graph_incl_adam"] = _cuda_timed(lambda: it(y0), reps=20, warm=3)
+        rec["ms_per_iter_cuda_graph_wall"] = _wall_timed(lambda: it(y0), reps=20, warm=3)
+    except Exception as e:
+        rec["cuda_graph_error"] = f"{type(e).__name__}: {e}"
     out["training shape B=2048 FaFp R=1, 7 weekly RK4 steps, fwd+backprop"] = rec
 
     # ---- configs[2]: 49 states x 256 latent samples (x b), 28 daily RK4 steps

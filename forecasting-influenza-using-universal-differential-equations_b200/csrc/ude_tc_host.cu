@@ -9,13 +9,13 @@ namespace ude {
 
 static inline int round16(int x) { return (x + 15) & ~15; }
 
-// Trajectories from which the layer products count as "real dense contractions" (BASELINE north_star):
-// below this the 128-trajectory tiles cannot fill the 148 SMs and the FFMA engine (32/64-trajectory
-// tiles) is the better fit.
-static long long tc_min_batch() {
-    const DeviceInfo& di = device_info();
-    return (long long)(di.ok ? di.n_sm : 148) * kTcTile;
-}
+// Batch from which the covered models (R = 1, nets up to 64 wide) run on the tensor path.  Measured on the B200
+// (tools/engine_crossover.py, profiles/r02_engine_crossover.txt; fwd + adjoint of the headline model replayed from a CUDA graph):
+// ONE 128-trajectory tile takes 0.80 ms for 7 steps on the tcgen05 engine, one 32/64-trajectory tile 1.05 ms on the FFMA
+// engine (its layer phases are CTA-wide barriers around register-tiled products), and the gap only widens with the batch
+// (B = 8192: 0.85 vs 2.04 ms, B = 18944: 0.88 vs 3.73 ms).  So the tensor path is the default at EVERY batch size; the FFMA
+// engine serves what it does not cover (R > 1, wide / deep nets, Dopri5, Bayes_* funcs, weight-set groups).
+static long long tc_min_batch() { return 1; }
 static const int kTcSmemLimit = 227 * 1024 - 2048;      // per-CTA opt-in limit minus the static part (~1.2 KB) and alignment slack
 
 static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes, int head_elu, int& th) {

@@ -85,9 +85,10 @@ class GraphedIteration:
         if entry is None:
             entry = self._capture(inputs, key)
         graph, static_in, loss, norm, ok = entry
-        for s, x in zip(static_in, inputs):
-            if s.data_ptr() != x.data_ptr():
-                s.copy_(x, non_blocking=True)
+        with torch.no_grad():       # static inputs may be leaves that require grad (dL/dy0 wanted)
+            for s, x in zip(static_in, inputs):
+                if s.data_ptr() != x.data_ptr():
+                    s.copy_(x, non_blocking=True)
         graph.replay()
         self.last_norm, self.last_ok = norm, ok
         return loss

@@ -45,7 +45,7 @@ def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg):
         # the same model through the single-set entry point: same kernels, same tiles -> same bits
         mod = module_from_spec(spec, thetas[g], 1.0, "cuda")
         y0s = y0[g].cuda().requires_grad_(True)
-        ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=h))
+        ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=h, kernels="ffma"))      # the grouped launch runs the FFMA engine
         (ys * Gc[g].cuda()).sum().backward()
         # per-trajectory results do not depend on the tiling: same bits; dtheta is a sum over tiles whose size follows the
         # TOTAL batch in the grouped launch (64 instead of 32 trajectories): same value to fp32 summation round-off
@@ -79,7 +79,7 @@ def test_group_side_channels_are_per_model():
         mod = module_from_spec(spec, thetas[g], 1.0, "cuda")
         mod.clear_tracking()
         with torch.no_grad():
-            ude_b200.odeint(mod, y0[g], t, method="rk4", options=dict(step_size=1.0))
+            ude_b200.odeint(mod, y0[g], t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
         p = mod.posterior()
         assert rel_err(posts[g].mean, p.mean) <= 1e-6 and rel_err(posts[g].stddev, p.stddev) <= 1e-5
     assert not torch.equal(posts[0].mean, posts[1].mean)
@@ -106,7 +106,7 @@ def test_many_groups_fan_out():
     assert torch.isfinite(y).all() and torch.isfinite(y0.grad).all()
     mod = module_from_spec(spec, thetas[17], 1.0, "cuda")
     y0s = y0[17].detach().clone().requires_grad_(True)
-    ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=1.0))
+    ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
     (ys[..., :3] ** 2).sum().backward()
     assert torch.equal(ys, y[17])
     assert torch.equal(y0s.grad, y0.grad[17])
