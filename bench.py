@@ -688,7 +688,7 @@ def run_ours(args):
         path = int(L.ude_rk4_path(C.byref(desc)))
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tr = json.load(f)
             if tr.get("batch") == B and tr.get("grid_steps") == n_steps:
                 traffic = tr.get("bwd_dram_bytes_per_launch")

@@ -79,13 +79,25 @@ class _UdeFunc(nn.Module):
         self.uncertainty = "none"
         self.params: list = []
         self.tracker: list = []
+        self._side_sums: list = []      # fused solves: the raw side sums behind the entries of `params` (one per solve)
 
     # -- reference protocol -----------------------------------------------------------
     def clear_tracking(self):
         self.params = []
         self.tracker = []
+        self._side_sums = []
 
     def posterior(self) -> Normal:
+        """Normal(mean, unbiased std) over every (beta, gamma) row since clear_tracking() (lib/models.py:152-156).  After fused
+        solves the rows exist only as in-kernel sums: ONE solve is served by the surrogate entry in `params` (exactly what
+        the reference's expression returns on it); SEVERAL solves are pooled exactly from the raw sums (their surrogate rows
+        would weight every solve equally, whatever its row count)."""
+        sums, self._side_sums = self._side_sums, []
+        if len(sums) > 1 and len(sums) == len(self.params):
+            from .odeint import posterior_moments
+            self.params = []
+            mean, std = posterior_moments(torch.stack(sums).sum(0))
+            return Normal(mean.to(torch.float32), std.to(torch.float32), validate_args=False)
         rows = torch.stack(self.params).reshape(-1, 2)
         self.params = []
         # Argument validation reads a device flag back to the host (a sync, and illegal under CUDA-graph capture);

@@ -496,22 +496,41 @@ class _Rk4SolveGroups(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------
 # side channels -> the reference's python-list protocol
 # ---------------------------------------------------------------------------------------
-def posterior_rows(side: torch.Tensor) -> torch.Tensor:
-    """A [2, 2] tensor whose column mean / unbiased std equal the mean / std of every
-    (beta, gamma) row the reference would have stacked (lib/models.py:152-156)."""
+def _safe_sqrt(v: torch.Tensor) -> torch.Tensor:
+    """sqrt with a finite (zero) gradient at 0, like torch.norm / std of a constant: sqrt'(0) = inf would turn a zero
+    cotangent into NaN."""
+    pos = v > 0
+    return torch.where(pos, torch.sqrt(torch.where(pos, v, torch.ones_like(v))), torch.zeros_like(v))
+
+
+def posterior_moments(side: torch.Tensor):
+    """(mean [2], unbiased std [2]) of every (beta, gamma) row behind the side sums (one solve: side [8]; several: the SUM of
+    their side vectors -- sums, sums of squares and N pool exactly)."""
     n = side[5]
     mean = side[0:2] / n
     var = (side[2:4] - n * mean * mean) / (n - 1.0)
-    std = torch.sqrt(torch.clamp(var, min=0.0))
+    return mean, _safe_sqrt(torch.clamp(var, min=0.0))
+
+
+def posterior_rows(side: torch.Tensor) -> torch.Tensor:
+    """A [2, 2] tensor whose column mean / unbiased std equal the mean / std of every
+    (beta, gamma) row the reference would have stacked (lib/models.py:152-156)."""
+    mean, std = posterior_moments(side)
     half = std / math.sqrt(2.0)
     return torch.stack([mean - half, mean + half]).to(torch.float32)
 
 
 def install_side_channels(func, info: FuncInfo, side: torch.Tensor) -> None:
+    """Hand the in-kernel reductions to the reference's list protocol.  Reference-owned modules (lib.models.*) get ONE surrogate
+    entry per solve, exact for `posterior()` / `torch.norm(torch.stack(tracker))` with one solve between `clear_tracking()`
+    and the read (what lib/VAE.py:121,173,180 does); this package's own classes additionally keep the raw sums
+    (`_side_sums`) and pool any number of solves exactly in their `posterior()`."""
     if info.rate_layers and isinstance(getattr(func, "params", None), list):
         func.params.append(posterior_rows(side))
+        if isinstance(getattr(func, "_side_sums", None), list):
+            func._side_sums.append(side)
     if info.aug_layers and isinstance(getattr(func, "tracker", None), list):
-        func.tracker.append(torch.sqrt(side[4]).to(torch.float32))
+        func.tracker.append(_safe_sqrt(side[4]).to(torch.float32))         # ||stack of per-solve norms|| pools exactly
 
 
 # ---------------------------------------------------------------------------------------
@@ -700,11 +719,12 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
     need_tape = torch.is_grad_enabled() and any(x.requires_grad for x in (*ins, lin.weight, lin.bias, *params))
     y_pred, side = _Rk4SolveDecoded.apply(y0, eps, std, mean, lin.weight, lin.bias, info, tables, n_steps, int(t.numel()),
                                           need_tape, *params)
-    if group is not None:
+    reg = side[7].to(torch.float32)          # this rank's trajectories only (a per-trajectory sum, like y_pred): a sharded trainer adds
+    if group is not None:                    # its local terms and all-reduces gradients; posterior() / tracker need GLOBAL sums
         from .dist import all_reduce_side
         side = all_reduce_side(side, None if group is True else group)
     install_side_channels(func, info, side)
-    return y_pred, side[7].to(torch.float32)
+    return y_pred, reg
 
 
 def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
