@@ -437,9 +437,18 @@ def secondary_configs(dev, ffma_peak_tflops: float, with_cpu: bool) -> dict:
     n_acc, n_att = float(st.n_accept.float().sum()), float(st.n_attempts.float().sum())
     # forward: 6 evaluations per attempt (+ f0 + the initial-step probe) at 2 flop/MAC; adjoint: 6 per ACCEPTED step (+ f0) at 4
     flops = (2 * (6 * n_att + 2 * 2048) + 4 * (6 * n_acc + 2048)) * spec49.macs_per_eval()
-    out["configs[1] FaFp R=49 y0 [2048,49,8] Dopri5 rtol 1e-5 atol 1e-9 t=[0..8] fwd+adjoint"] = {
+    rec1 = {
         "ms_per_iter": ms, "epoch_153_iters_s": ms * 153e-3, "accepted_steps_mean": n_acc / 2048, "attempted_steps_mean": n_att / 2048,
-        "accepted_trajectory_steps_per_s": n_acc / (ms * 1e-3), "frac_ffma": flops / (ms * 1e-3) / peak}
+        "accepted_trajectory_steps_per_s": n_acc / (ms * 1e-3), "frac_ffma": flops / (ms * 1e-3) / peak,
+        "controller": "one per trajectory (options['per_trajectory'] = True)"}
+    # torchdiffeq's own batch semantics: ONE error norm / step size / decision for all 2048 x 49 x 8 states (the default mode at this size)
+    ms_s = _cuda_timed(fwd_bwd(mod49, y0, t, rtol=1e-5, atol=1e-9, method="dopri5", options=dict(per_trajectory=False)))
+    with torch.no_grad():
+        _, st_s = ude_b200.odeint(mod49, y0, t, rtol=1e-5, atol=1e-9, method="dopri5", options=dict(per_trajectory=False, return_stats=True))
+    rec1["shared_step"] = {"ms_per_iter": ms_s, "epoch_153_iters_s": ms_s * 153e-3, "accepted_steps": int(st_s.n_accept[0]),
+                           "attempted_steps": int(st_s.n_attempts[0]),
+                           "controller": "torchdiffeq batch semantics: one RMS norm over the whole tensor, cooperative launch"}
+    out["configs[1] FaFp R=49 y0 [2048,49,8] Dopri5 rtol 1e-5 atol 1e-9 t=[0..8] fwd+adjoint"] = rec1
 
     # ---- configs[4]: 64 weight-set groups per GPU (512 over 8), Fp hidden 32, 2048 trajectories each, 56 outputs
     specg = UdeSpec("Fp", 1, 8, (32, 32), ())

@@ -127,7 +127,8 @@ def test_posterior_pools_several_solves_exactly():
     odeint_ref.odeint(f, ya, ta, method="rk4", options=dict(step_size=1.0))
     odeint_ref.odeint(f, yb, tb, method="rk4", options=dict(step_size=1.0))
     norm_ref = torch.norm(torch.cat([x.reshape(-1) for x in f.tracker]))
-    post_ref = f.posterior()
+    rows = torch.cat([p.reshape(-1, 2) for p in f.params])          # every (beta, gamma) row of both solves
+    post_ref = torch.distributions.Normal(rows.mean(0), rows.std(0))
     mod = module_from_spec(spec, theta, 1.0, "cuda")
     mod.clear_tracking()
     ude_b200.odeint(mod, ya.cuda(), ta, method="rk4", options=dict(step_size=1.0))
