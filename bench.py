@@ -457,17 +457,29 @@ def secondary_configs(dev, ffma_peak_tflops: float, with_cpu: bool) -> dict:
     y0 = synth_y0(G * Bg, 1, 8, seed=3).reshape(G, Bg, 1, 8).to(dev)
     t = torch.linspace(1, 56, 56) / 7
 
-    def step_g():
+    def step_g():       # 64 separate modules: their 6 x 64 parameter tensors are gathered / scattered by torch every iteration
         y0g = y0.clone().requires_grad_(True)
         for m in mods:
             m.zero_grad(set_to_none=True)
         y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=1.0))
         (y[..., 1] ** 2).mean().backward()
 
-    ms = _cuda_timed(step_g)
+    ms_sep = _cuda_timed(step_g)
+    flat = ude_b200.flatten_group_parameters(mods)       # the same weights as ONE [G, n_theta] leaf: no gather, one gradient tensor
+
+    def step_flat():
+        y0g = y0.clone().requires_grad_(True)
+        flat.grad = None
+        y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=1.0), theta=flat)
+        (y[..., 1] ** 2).mean().backward()
+
+    ms = _cuda_timed(step_flat)
     ts = G * Bg * 8 / (ms * 1e-3)
     out["configs[4] 64 groups x Fp(R=1,L=8,[32,32]) x 2048 trajectories, RK4 h=1 t=[1/7..8] (8 grid steps, 56 outputs) fwd+adjoint"] = {
-        "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * specg.macs_per_eval() / peak}
+        "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * specg.macs_per_eval() / peak,
+        "how": "one forward + one adjoint launch over the tiles of all groups (tcgen05 engine), weights as one [G, n_theta] leaf "
+               "(ude_b200.flatten_group_parameters)",
+        "ms_per_iter_separate_module_parameters": ms_sep}
     return out
 
 

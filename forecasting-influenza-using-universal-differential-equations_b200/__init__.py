@@ -17,7 +17,7 @@ from .funcs import (Bayes_Fa, Bayes_FaFp, Bayes_Fp, Decoder, Dense_Variational, 
                     describe_func)
 from . import dist, train  # noqa: F401
 from .train import GraphedIteration, run_epoch  # noqa: F401
-from .odeint import (flatten_parameters, odeint, odeint_decoded, odeint_groups, odeint_reparam, posterior_rows,  # noqa: F401
+from .odeint import (flatten_group_parameters, flatten_parameters, odeint, odeint_decoded, odeint_groups, odeint_reparam, posterior_rows,  # noqa: F401
                      rk4_grid_tables)
 
 
@@ -30,5 +30,5 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
 
 
 __all__ = ["odeint", "odeint_groups", "odeint_adjoint", "Fp", "Fa", "FaFp", "describe_func", "build", "lib", "UdeError",
-           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows", "flatten_parameters", "odeint_reparam", "odeint_decoded", "Decoder", "Bayes_Fp", "Bayes_Fa", "Bayes_FaFp", "Dense_Variational", "GraphedIteration", "run_epoch"]
+           "UnsupportedFunc", "rk4_grid_tables", "posterior_rows", "flatten_parameters", "flatten_group_parameters", "odeint_reparam", "odeint_decoded", "Decoder", "Bayes_Fp", "Bayes_Fa", "Bayes_FaFp", "Dense_Variational", "GraphedIteration", "run_epoch"]
 __version__ = "0.1.0"

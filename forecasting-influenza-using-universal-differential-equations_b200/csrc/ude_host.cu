@@ -550,6 +550,24 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
         if ((st = ude_plan(&d1, method, n_steps, plan)) != UDE_OK) return st;
         plan->workspace_bytes = align_up(plan->workspace_bytes, 256) * desc->n_groups;
         plan->tape_bytes = align_up(plan->tape_bytes, 256) * desc->n_groups;
+        {
+            TcModel Mt;
+            const int path = tc_choose(desc, Mt);
+            if (path < 0) return path;
+            if (path == 1) {          // tcgen05 engine, all groups in one launch
+                int tc_ctas = 0;
+                long long tc_ws = 0;
+                tc_plan_info(desc, Mt, &tc_ws, &tc_ctas);
+                if (tc_ws > plan->workspace_bytes) plan->workspace_bytes = tc_ws;
+                plan->tile_traj = kTcTile;
+                plan->n_ctas = tc_ctas;
+                plan->smem_bytes_fwd = Mt.smem_bytes_fwd;
+                plan->smem_bytes_bwd = Mt.smem_bytes_bwd;
+                plan->weights_in_smem = 1;
+                plan->path = 3;
+                return UDE_OK;
+            }
+        }
         GroupedPlan gp;
         if (grouped_single_launch(desc, n_steps, nullptr, gp)) {      // one launch for all groups (same tape layout)
             if (gp.bytes > plan->workspace_bytes) plan->workspace_bytes = gp.bytes;
@@ -750,6 +768,14 @@ int ude_rk4_forward(const UdeDesc* desc, const float* theta, const float* y0, in
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     if (desc->n_groups != 1) {
+        {   // the tensor-core kernels walk the tiles of ALL groups in one launch when they cover the model
+            TcModel Mt;
+            const int path = tc_choose(desc, Mt);
+            if (path < 0) return path;
+            if (path == 1)
+                return tc_forward(desc, Mt, theta, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, y_out, tape, side,
+                                  workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+        }
         GroupedPlan gp;
         if (grouped_single_launch(desc, n_steps, workspace, gp)) {
             if (gp.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
@@ -847,6 +873,14 @@ int ude_rk4_backward(const UdeDesc* desc, const float* theta, const float* y0, i
     if (n_steps < 1 || n_out < 1) return UDE_ERR_INVALID;
     if (!device_info().ok) return UDE_ERR_NO_DEVICE;
     if (desc->n_groups != 1) {
+        {   // the tensor-core kernels walk the tiles of ALL groups in one launch when they cover the model
+            TcModel Mt;
+            const int path = tc_choose(desc, Mt);
+            if (path < 0) return path;
+            if (path == 1)
+                return tc_backward(desc, Mt, theta, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, tape, g_out, g_side,
+                                   g_y0, g_theta, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+        }
         GroupedPlan gp;
         if (grouped_single_launch(desc, n_steps, workspace, gp)) {
             if (gp.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;

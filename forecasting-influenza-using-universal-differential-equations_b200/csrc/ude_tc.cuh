@@ -39,6 +39,12 @@ struct TcFwdArgs {
     long long B;
     ReparamArgs rp;         // rp.mean != nullptr: y0 is produced in the prologue (ude_engine.cuh) and written as output 0
     DecArgs dec;            // dec.n_dec == 1: decoded outputs (ude_engine.cuh DecArgs; the tensor path is R = 1, one decoder output)
+    // Weight-set groups (UdeDesc::n_groups = G > 1, BASELINE configs[4]): ONE launch walks the tiles of all G group-major
+    // sub-problems (B = trajectories of ONE group); the weight blob is re-staged when a CTA's next tile belongs to another group;
+    // side partials are kept per tile and trajectory warp: side_partial [n_tiles][4][8].
+    int n_groups;
+    long long blob_stride;          // bytes between the packed blobs of two groups
+    long long tape_group_floats;    // floats between the tapes of two groups
 };
 
 struct TcBwdArgs {
@@ -53,6 +59,9 @@ struct TcBwdArgs {
     long long B;
     ReparamArgs rp;         // rp.mean != nullptr: also dL/dz (rp.g_z) in the epilogue
     DecArgs dec;            // dec.n_dec == 1: cotangents arrive as dL/dy_pred + g_side[5] = dL/dreg (g_out unused)
+    int n_groups;           // see TcFwdArgs; slabs are then per TILE: [n_tiles][slab_floats], g_side [G][5]
+    long long blob_stride;
+    long long tape_group_floats;
 };
 
 // ----------------------------------------------------------------------------------
@@ -608,7 +617,7 @@ struct TcChain {
 // just produced into NH partial dot products; the helper warps park theirs in shared memory, the trajectory warp of
 // the same lane quarter adds them up one lock-step slot later.
 constexpr int kTcBarSweep = 12;     // named barriers 12..15: backward sweep, lane quarter q
-constexpr int kTcBarFlush = 4;      // backward sweep: gradient staging buffer (the 8 epilogue warps)
+constexpr int kTcBarTile = 4;       // the 8 epilogue warps at a tile boundary (weight-set groups: before the blob is re-staged)
 struct TcHeadScratch {
     uint64_t bar[2][4];             // helper warps -> trajectory warp of the lane quarter, per chain (count kTcSlots - 1);
                                     // the partial sums themselves travel through the chain's (idle) TMEM accumulator
@@ -935,7 +944,8 @@ __device__ __forceinline__ void tc_decode_vjp(const DecArgs& d, float g_reg, int
 }
 
 template <int R, int L>
-__global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcFwdArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcFwdArgs a_in) {
+    const TcFwdArgs& a = a_in;
     constexpr int D0 = R * L, DN = 3 * R;
     static_assert(D0 <= 16, "tensor path: R*L <= 16");
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -960,7 +970,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     uint32_t wphase = 0;
-    tc_stage_blob(smem + M.off_w, a.blob, (uint32_t)M.blob_bytes, &wbar, wphase);
+    const bool grouped = a.n_groups > 1;
+    const long long tiles_per_group = (a.B + kTcTile - 1) / kTcTile;
+    long long g_cur = grouped ? (long long)blockIdx.x / tiles_per_group : 0;       // group of this CTA's first tile
+    tc_stage_blob(smem + M.off_w, a.blob + g_cur * a.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
 
     TcCtx c;
     c.abuf_p = smem + M.off_abuf;
@@ -996,7 +1009,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     SideAcc side;
     side.clear();
     const long long B = a.B;
-    const long long n_tiles = (B + kTcTile - 1) / kTcTile;
+    const long long n_tiles = tiles_per_group * a.n_groups;
     const long long tape_stage = (long long)DN * B;
 
     if (warp >= kTcEpiWarps) {
@@ -1008,7 +1021,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     } else {
     if (kTcRegHandOver) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long b0 = tile * kTcTile;
+        const long long grp = grouped ? tile / tiles_per_group : 0;
+        const long long b0 = (tile - grp * tiles_per_group) * kTcTile;
+        // this group's views of the caller's arrays (group-major layouts, include/ude_b200.h); `a` shadows the launch arguments
+        TcFwdArgs ag = a_in;
+        if (grouped) {
+            ag.y0 += grp * B * D0;
+            ag.y_out += grp * (long long)a_in.g.n_out * B * D0;
+            if (ag.tape) ag.tape += grp * a_in.tape_group_floats;
+            if (grp != g_cur) {     // the issuer waits for this tile's first operands: no product reads the weights now
+                asm volatile("bar.sync %0, %1;" ::"n"(kTcBarTile), "n"(32 * kTcEpiWarps) : "memory");
+                tc_stage_blob(smem + M.off_w, a_in.blob + grp * a_in.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
+                g_cur = grp;
+            }
+        }
+        const TcFwdArgs& a = ag;
         const bool valid = is_traj && (b0 + c.t < B);
         float x[D0], y[DN], k1[DN], k2[DN], k3[DN];
 #pragma unroll
@@ -1127,10 +1154,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
                 }
             }
         }
+        if (grouped && is_traj) {      // side sums per tile and trajectory warp (summed per group, in tile order, afterwards)
+            double v[8] = {side.sb, side.sg, side.sb2, side.sg2, side.sf2, (double)side.rows, 0.0, side.reg};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+            }
+            v[6] = 4.0 * a.g.n_steps;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c.lane == i) a.side_partial[(tile * 4 + c.q) * 8 + i] = v[i];
+            side.clear();
+        }
     }
     }
     tc_prof_dump(c);
-    tc_side_reduce(side, 4.0 * a.g.n_steps, red, a.side_partial + (long long)blockIdx.x * 8);
+    if (!grouped) tc_side_reduce(side, 4.0 * a.g.n_steps, red, a.side_partial + (long long)blockIdx.x * 8);
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tc_tmem_free<128>(c.tmem);
@@ -1438,7 +1478,8 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
 }
 
 template <int R, int L>
-__global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcBwdArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcBwdArgs a_in) {
+    const TcBwdArgs& a = a_in;
     constexpr int D0 = R * L, DN = 3 * R;
     static_assert(D0 <= 16, "tensor path: R*L <= 16");
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -1464,7 +1505,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     uint32_t wphase = 0;
-    tc_stage_blob(smem + M.off_w, a.blob, (uint32_t)M.blob_bytes, &wbar, wphase);
+    const bool grouped = a.n_groups > 1;
+    const long long tiles_per_group = (a.B + kTcTile - 1) / kTcTile;
+    long long g_cur = grouped ? (long long)blockIdx.x / tiles_per_group : 0;       // group of this CTA's first tile
+    tc_stage_blob(smem + M.off_w, a.blob + g_cur * a.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
 
     TcCtx c;
     c.abuf_p = smem + M.off_abuf;
@@ -1512,7 +1556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     const float g_reg = (decoded && a.g_side) ? __ldg(a.g_side + 5) : 0.f;
 
     const long long B = a.B;
-    const long long n_tiles = (B + kTcTile - 1) / kTcTile;
+    const long long n_tiles = tiles_per_group * a.n_groups;
     const long long tape_stage = (long long)DN * B;
     const int n_steps = a.g.n_steps;
 
@@ -1525,7 +1569,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     } else {
     if (kTcRegHandOver) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcEpiRegs));
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long b0 = tile * kTcTile;
+        const long long grp = grouped ? tile / tiles_per_group : 0;
+        const long long b0 = (tile - grp * tiles_per_group) * kTcTile;
+        // this group's views of the caller's arrays; per-tile gradient slab (summed per group, in tile order, afterwards)
+        TcBwdArgs ag = a_in;
+        if (grouped) {
+            ag.y0 += grp * B * D0;
+            ag.g_y0 += grp * B * D0;
+            ag.g_out += grp * (long long)a_in.g.n_out * B * D0;
+            ag.tape += grp * a_in.tape_group_floats;
+            slab = a_in.slabs + tile * M.slab_floats;
+            if (a_in.g_side) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) gs[i] = __ldg(a_in.g_side + grp * 5 + i);
+            }
+            if (grp != g_cur) {     // the issuer waits for this tile's first operands: no product reads the weights now
+                asm volatile("bar.sync %0, %1;" ::"n"(kTcBarTile), "n"(32 * kTcEpiWarps) : "memory");
+                tc_stage_blob(smem + M.off_w, a_in.blob + grp * a_in.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
+                g_cur = grp;
+            }
+        }
+        const TcBwdArgs& a = ag;
         const bool valid = is_traj && (b0 + c.t < B);
         float x[D0], lam[DN], cb[D0], kb[4][DN];
 #pragma unroll
@@ -1718,7 +1782,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
 // utility kernels of the tensor path
 // ===================================================================================
 // theta (PyTorch layout) -> weight images (bf16 x3, zero padded) + bias block.  One block per layer.
-__global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* __restrict__ theta, uint8_t* __restrict__ blob) {
+__global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* __restrict__ theta_all, uint8_t* __restrict__ blob_all,
+                               long long blob_stride) {
+    const float* __restrict__ theta = theta_all + (size_t)blockIdx.y * M.n_theta;       // weight set blockIdx.y
+    uint8_t* __restrict__ blob = blob_all + (size_t)blockIdx.y * blob_stride;
     const int li = blockIdx.x;
     const TcLayer& Lp = li < M.n_rate ? M.rate[li] : M.aug[li - M.n_rate];
     uint16_t* img = reinterpret_cast<uint16_t*>(blob + Lp.w_off);
@@ -1754,7 +1821,9 @@ __global__ void tc_pack_kernel(const __grid_constant__ TcModel M, const float* _
 }
 
 // side[0..7] = sum over CTA partials (fixed order)
-__global__ void tc_reduce_side_kernel(const double* __restrict__ partial, int n_parts, double* __restrict__ side) {
+__global__ void tc_reduce_side_kernel(const double* __restrict__ partial_all, int n_parts, double* __restrict__ side_all) {
+    const double* __restrict__ partial = partial_all + (size_t)blockIdx.x * n_parts * 8;      // weight set blockIdx.x
+    double* __restrict__ side = side_all + (size_t)blockIdx.x * 8;
     const int i = threadIdx.x;
     if (i >= 8) return;
     double s = 0.0;
@@ -1764,8 +1833,11 @@ __global__ void tc_reduce_side_kernel(const double* __restrict__ partial, int n_
 }
 
 // g_theta[e] = sum over CTA slabs (fixed order => deterministic)
-__global__ void tc_reduce_dtheta_kernel(const __grid_constant__ TcModel M, const float* __restrict__ slabs, int n_slabs,
-                                        float* __restrict__ g_theta) {
+__global__ void tc_reduce_dtheta_kernel(const __grid_constant__ TcModel M, const float* __restrict__ slabs_all, int n_slabs,
+                                        float* __restrict__ g_theta_all) {
+    // weight set blockIdx.y owns slabs [y * n_slabs, (y + 1) * n_slabs)
+    const float* __restrict__ slabs = slabs_all + (size_t)blockIdx.y * n_slabs * M.slab_floats;
+    float* __restrict__ g_theta = g_theta_all + (size_t)blockIdx.y * M.n_theta;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M.n_theta) return;
     int sidx = -1;

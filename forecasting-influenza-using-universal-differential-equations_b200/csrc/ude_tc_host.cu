@@ -75,7 +75,6 @@ static bool tc_fill_layers(TcModel& M, TcLayer* Ls, int n, const int32_t* sizes,
 // descriptor -> TcModel; false when the tensor path does not cover the configuration
 static bool tc_build_model(const UdeDesc* d, TcModel& M) {
     memset(&M, 0, sizeof(M));
-    if (d->n_groups != 1) return false;
     M.kind = d->kind;
     M.R = d->n_regions;
     M.L = d->latent_dim;
@@ -172,31 +171,37 @@ struct TcWorkspace {
     float* slabs;
     long long bytes;
 };
-static TcWorkspace tc_carve(void* base, const TcModel& M, int n_ctas) {
+// One weight set: a blob, side partials and gradient slabs per CTA.  G weight sets in one launch (UdeDesc::n_groups): G blobs,
+// side partials per tile and trajectory warp, gradient slabs per TILE (summed per group in tile order afterwards).
+static long long tc_blob_stride(const TcModel& M) { return align_up(M.blob_bytes, 256); }
+static long long tc_tiles(long long B, int G) { return (B / G + kTcTile - 1) / kTcTile * G; }
+static TcWorkspace tc_carve(void* base, const TcModel& M, int n_ctas, long long B = 0, int G = 1) {
     TcWorkspace w;
     long long off = 0;
+    const long long tiles = G > 1 ? tc_tiles(B, G) : 0;
     w.blob = reinterpret_cast<uint8_t*>(base) + off;
-    off = align_up(off + M.blob_bytes, 256);
+    off = align_up(off + tc_blob_stride(M) * G, 256);
     w.side_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
-    off = align_up(off + (long long)n_ctas * 8 * 8, 256);
+    off = align_up(off + (G > 1 ? tiles * 4 : (long long)n_ctas) * 8 * 8, 256);
     w.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
-    off = align_up(off + (long long)n_ctas * M.slab_floats * 4, 256);
+    off = align_up(off + (G > 1 ? tiles : (long long)n_ctas) * M.slab_floats * 4, 256);
     w.bytes = off;
     return w;
 }
-static int tc_grid(long long B) {
+static int tc_grid(long long B, int G = 1) {
     const DeviceInfo& di = device_info();
-    const long long tiles = (B + kTcTile - 1) / kTcTile;
+    const long long tiles = tc_tiles(B, G);
     const int n_sm = di.ok ? di.n_sm : 148;
     return (int)(tiles < n_sm ? tiles : n_sm);
 }
 
 int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
                       float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
-    const int n_ctas = tc_grid(desc->batch);
-    TcWorkspace w = tc_carve(workspace, M, n_ctas);
+    const int G = desc->n_groups;
+    const int n_ctas = tc_grid(desc->batch, G);
+    TcWorkspace w = tc_carve(workspace, M, n_ctas, desc->batch, G);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
-    tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
+    tc_pack_kernel<<<dim3(M.n_rate + M.n_aug, G), 256, 0, s>>>(M, theta, w.blob, tc_blob_stride(M));
     UDE_CUDA(cudaGetLastError());
     static thread_local TcTable tab_storage;
     TcTable* tab = &tab_storage;
@@ -208,9 +213,13 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     a.y_out = y_out;
     a.tape = tape;
     a.side_partial = w.side_partial;
-    a.B = desc->batch;
+    a.B = desc->batch / G;
     a.rp = pending_reparam();
     a.dec = pending_decoded();
+    a.n_groups = G;
+    a.blob_stride = tc_blob_stride(M);
+    a.tape_group_floats = align_up(((long long)g.n_steps * 4 + 1) * 3 * M.R * (desc->batch / G) * 4, 256) / 4;
+    if (G > 1 && (a.rp.mean || a.dec.n_dec > 0)) return UDE_ERR_UNSUPPORTED;
     int st;
 #define UDE_TC_FWD(RR, LL)                                                                     \
     do {                                                                                       \
@@ -222,7 +231,7 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
     else UDE_TC_FWD(1, 16);
 #undef UDE_TC_FWD
     UDE_CUDA(cudaGetLastError());
-    tc_reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
+    tc_reduce_side_kernel<<<G, 32, 0, s>>>(w.side_partial, G > 1 ? (int)(tc_tiles(desc->batch, G) / G) * 4 : n_ctas, side);
     UDE_CUDA(cudaGetLastError());
     return UDE_OK;
 }
@@ -230,14 +239,16 @@ int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const 
 int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
                        const float* tape, const float* g_out, const float* g_side, float* g_y0, float* g_theta,
                        void* workspace, int64_t workspace_bytes, cudaStream_t s) {
-    const int n_ctas = tc_grid(desc->batch);
-    TcWorkspace w = tc_carve(workspace, M, n_ctas);
+    const int G = desc->n_groups;
+    const int n_ctas = tc_grid(desc->batch, G);
+    TcWorkspace w = tc_carve(workspace, M, n_ctas, desc->batch, G);
     if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
     if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED)) {
-        tc_pack_kernel<<<M.n_rate + M.n_aug, 256, 0, s>>>(M, theta, w.blob);
+        tc_pack_kernel<<<dim3(M.n_rate + M.n_aug, G), 256, 0, s>>>(M, theta, w.blob, tc_blob_stride(M));
         UDE_CUDA(cudaGetLastError());
     }
-    UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)n_ctas * M.slab_floats * 4, s));
+    const long long n_slabs = G > 1 ? tc_tiles(desc->batch, G) : n_ctas;
+    UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)n_slabs * M.slab_floats * 4, s));
     static thread_local TcTable tab_storage;
     TcTable* tab = &tab_storage;
     tc_build_table(M, *tab, true);
@@ -250,10 +261,14 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     a.g_side = g_side;
     a.g_y0 = g_y0;
     a.slabs = w.slabs;
-    a.B = desc->batch;
+    a.B = desc->batch / G;
     a.rp = pending_reparam();
     a.dec = pending_decoded();
     decoded_ctas() = n_ctas;
+    a.n_groups = G;
+    a.blob_stride = tc_blob_stride(M);
+    a.tape_group_floats = align_up(((long long)g.n_steps * 4 + 1) * 3 * M.R * (desc->batch / G) * 4, 256) / 4;
+    if (G > 1 && (a.rp.mean || a.dec.n_dec > 0)) return UDE_ERR_UNSUPPORTED;
     int st;
 #define UDE_TC_BWD(RR, LL)                                                                     \
     do {                                                                                       \
@@ -265,14 +280,14 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     else UDE_TC_BWD(1, 16);
 #undef UDE_TC_BWD
     UDE_CUDA(cudaGetLastError());
-    tc_reduce_dtheta_kernel<<<(M.n_theta + 255) / 256, 256, 0, s>>>(M, w.slabs, n_ctas, g_theta);
+    tc_reduce_dtheta_kernel<<<dim3((M.n_theta + 255) / 256, G), 256, 0, s>>>(M, w.slabs, (int)(n_slabs / G), g_theta);
     UDE_CUDA(cudaGetLastError());
     return UDE_OK;
 }
 
 void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas) {
-    *n_ctas = tc_grid(d->batch);
-    *workspace_bytes = tc_carve(nullptr, M, *n_ctas).bytes;
+    *n_ctas = tc_grid(d->batch, d->n_groups);
+    *workspace_bytes = tc_carve(nullptr, M, *n_ctas, d->batch, d->n_groups).bytes;
 }
 
 }  // namespace ude

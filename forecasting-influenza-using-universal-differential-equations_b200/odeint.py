@@ -727,7 +727,25 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
     return y_pred, reg
 
 
-def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
+def flatten_group_parameters(funcs) -> torch.Tensor:
+    """Re-home the weights of G same-architecture ODE funcs as rows of ONE ``[G, n_theta]`` leaf tensor (theta order per row) and
+    return it: ``odeint_groups(funcs, ..., theta=flat)`` then hands the buffer to the kernels without gathering 6 G tensors, the
+    gradient of the whole sweep arrives as ``flat.grad`` (one tensor: one optimizer over ``[flat]`` trains all G models -- Adam is
+    element-wise), and the modules keep seeing the current values (their parameters become views of the rows)."""
+    funcs = list(funcs)
+    infos = [describe_func(f) for f in funcs]
+    rows = [torch.cat([p.detach().reshape(-1) for l in i.linears() for p in (l.weight, l.bias)]) for i in infos]
+    if len({r.numel() for r in rows}) != 1:
+        raise ValueError("all funcs of a grouped solve must share one architecture")
+    flat = torch.stack(rows).requires_grad_(True)
+    for g, i in enumerate(infos):
+        ps = [p for l in i.linears() for p in (l.weight, l.bias)]
+        for p, v in zip(ps, split_like(flat.detach()[g], ps)):
+            p.data = v
+    return flat
+
+
+def odeint_groups(funcs, y0, t, *, method="rk4", options=None, theta=None):
     """G independent UDE models integrated side by side (BASELINE configs[4]: the hyper-parameter sweeps of
     tuning/tune_node.py train every configuration with its own ``odeint`` call, :204,227 — here they share ONE).
 
@@ -742,7 +760,14 @@ def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
         raise ValueError("funcs is empty")
     if not isinstance(y0, torch.Tensor) or y0.dim() != 4 or y0.shape[0] != len(funcs):
         raise ValueError(f"y0 must be [G={len(funcs)}, B_g, R, L]")
-    infos = [_check_common(f, y0[g], t, method, None) for g, f in enumerate(funcs)]
+    if theta is not None:
+        # the weights arrive as ONE [G, n_theta] tensor (flatten_group_parameters): funcs[0] describes the architecture of all
+        infos = [_check_common(funcs[0], y0[0], t, method, None)]
+        n_theta = sum(p.numel() for l in infos[0].linears() for p in (l.weight, l.bias))
+        if tuple(theta.shape) != (len(funcs), n_theta) or theta.device != y0.device or theta.dtype != torch.float32:
+            raise ValueError(f"theta must be a float32 [{len(funcs)}, {n_theta}] tensor on y0's device")
+    else:
+        infos = [_check_common(f, y0[g], t, method, None) for g, f in enumerate(funcs)]
     i0 = infos[0]
     if any(i.bayes for i in infos):
         raise NotImplementedError("Bayes_* funcs go through ude_b200.odeint (method='rk4')")
@@ -763,7 +788,8 @@ def odeint_groups(funcs, y0, t, *, method="rk4", options=None):
         raise ValueError("t must be strictly increasing")
     (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), y0.device)
     # one cat over all G x (W, b) tensors, one batched side-channel computation: the glue must not cost G x a dozen launches
-    theta = torch.cat([p.reshape(-1) for i in infos for l in i.linears() for p in (l.weight, l.bias)]).view(len(funcs), -1)
+    if theta is None:
+        theta = torch.cat([p.reshape(-1) for i in infos for l in i.linears() for p in (l.weight, l.bias)]).view(len(funcs), -1)
     need_tape = torch.is_grad_enabled() and (theta.requires_grad or y0.requires_grad)
     y_out, side = _Rk4SolveGroups.apply(theta, y0, i0, tables, n_steps, int(t.numel()), need_tape)
     if i0.rate_layers:

@@ -49,11 +49,20 @@ class GraphedIteration:
 
     # ---- one eager iteration (also the warm-up and the body that is captured)
     def _iteration(self, inputs):
-        for p in self.params:
-            if p.grad is not None:
-                p.grad.zero_()
         loss = self.step_fn(*inputs)
-        loss.backward()
+        # torch.autograd.grad + explicit writes into the (static) .grad buffers instead of loss.backward(): no AccumulateGrad
+        # nodes take part, so parameters that were trained eagerly before (their accumulator nodes remember the stream they
+        # were created on) can be captured all the same
+        got = torch.autograd.grad(loss, self.params, allow_unused=True)
+        with torch.no_grad():
+            for p, g in zip(self.params, got):
+                if g is None:
+                    if p.grad is not None:
+                        p.grad.zero_()
+                elif p.grad is None:
+                    p.grad = g.detach().clone()
+                else:
+                    p.grad.copy_(g)
         grads = [p.grad for p in self.params if p.grad is not None]
         norm = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads])) if grads else loss.new_zeros(())
         ok = torch.ones((), device=loss.device)
@@ -94,6 +103,11 @@ class GraphedIteration:
         return loss
 
     def _capture(self, inputs, key):
+        # Autograd graphs of earlier EAGER iterations may linger in reference cycles; they keep the parameters' gradient
+        # accumulator nodes alive, and those remember the (legacy default) stream they were created on -- which the capture
+        # stream must not synchronise with.  Collect them so that the warm-up below re-creates the nodes on its own stream.
+        import gc
+        gc.collect()
         dev = inputs[0].device
         static_in = [x.detach().clone().requires_grad_(x.requires_grad) for x in inputs]
         # optimizer state must exist before capture (lazy init), grads must be allocated: warm up on a side stream

@@ -122,7 +122,7 @@ typedef struct UdePlan {
     int32_t smem_bytes_bwd;
     int32_t weights_in_smem;    /* 1: staged once per CTA with a TMA bulk copy    */
     int32_t path;               /* kernel family the call will run: 0 FFMA engine, 1 tcgen05 engine (ude_rk4_path),
-                                 * 2 FFMA engine, all weight-set groups in one launch.  The two engines round
+                                 * 2 FFMA engine, all weight-set groups in one launch, 3 tcgen05 engine, all groups in one launch.  The two engines round
                                  * differently (both inside the 1e-5 bar): pin UDE_FLAG_FORCE_* for bit-reproducibility
                                  * across batch sizes / shard counts.                                            */
 } UdePlan;

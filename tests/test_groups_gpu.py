@@ -15,12 +15,13 @@ def _models(spec, G, seed):
     return thetas, [module_from_spec(spec, th, 1.0, "cuda") for th in thetas]
 
 
+@pytest.mark.parametrize("kernels", ["ffma", "tensor"])
 @pytest.mark.parametrize("kind,L,nets,aug,G,Bg", [
     ("Fp", 8, (32, 32), (), 5, 300),            # tune_node.py:170 widths, ragged tiles
     ("Fp", 16, (32, 32), (), 3, 64),
     ("FaFp", 8, (64, 64, 32), (64, 64), 4, 130),
 ])
-def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg):
+def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg, kernels):
     import ude_b200
     from oracle import odeint_ref
     from oracle.ude_rhs import OracleFunc, UdeSpec, synth_y0
@@ -35,7 +36,7 @@ def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg):
     y0g = y0.cuda().requires_grad_(True)
     for m in mods:
         m.clear_tracking()
-    y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=h))
+    y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=h, kernels=kernels))
     assert y.shape == (G, t.numel(), Bg, 1, L)
     (y * Gc.cuda()).sum().backward()
     grouped = [(y[g].detach().clone(), y0g.grad[g].clone(), flat_grad(mods[g]).clone()) for g in range(G)]
@@ -45,7 +46,7 @@ def test_groups_equal_separate_solves_and_oracle(kind, L, nets, aug, G, Bg):
         # the same model through the single-set entry point: same kernels, same tiles -> same bits
         mod = module_from_spec(spec, thetas[g], 1.0, "cuda")
         y0s = y0[g].cuda().requires_grad_(True)
-        ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=h, kernels="ffma"))      # the grouped launch runs the FFMA engine
+        ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=h, kernels=kernels))      # the same engine as the grouped launch
         (ys * Gc[g].cuda()).sum().backward()
         # per-trajectory results do not depend on the tiling: same bits; dtheta is a sum over tiles whose size follows the
         # TOTAL batch in the grouped launch (64 instead of 32 trajectories): same value to fp32 summation round-off
@@ -85,9 +86,10 @@ def test_group_side_channels_are_per_model():
     assert not torch.equal(posts[0].mean, posts[1].mean)
 
 
-def test_many_groups_fan_out():
-    """64 groups x 2048 trajectories (the per-GPU share of configs[4]) in ONE forward and ONE backward launch (plan path
-    2): finite, and group 17 equals its own single-set solve."""
+@pytest.mark.parametrize("kernels,path", [("ffma", 2), (None, 3)])
+def test_many_groups_fan_out(kernels, path):
+    """64 groups x 2048 trajectories (the per-GPU share of configs[4]) in ONE forward and ONE backward launch (plan path 2: FFMA
+    engine, 3: tcgen05 engine = the default): finite, and group 17 equals its own single-set solve."""
     import ctypes as C
 
     import ude_b200
@@ -97,16 +99,18 @@ def test_many_groups_fan_out():
     G, Bg = 64, 2048
     thetas, mods = _models(spec, G, seed=100)
     plan = _lib.UdePlan()
-    desc = ude_b200.describe_func(mods[0]).desc(G * Bg, n_groups=G)
-    assert ude_b200.lib().ude_plan(C.byref(desc), 0, 8, C.byref(plan)) == 0 and plan.path == 2, "not the single-launch grouped path"
+    info = ude_b200.describe_func(mods[0])
+    info.kernels = kernels
+    desc = info.desc(G * Bg, n_groups=G)
+    assert ude_b200.lib().ude_plan(C.byref(desc), 0, 8, C.byref(plan)) == 0 and plan.path == path, "not the single-launch grouped path"
     t = torch.linspace(1, 56, 56) / 7
     y0 = synth_y0(G * Bg, 1, 8, seed=3).reshape(G, Bg, 1, 8).cuda().requires_grad_(True)
-    y = ude_b200.odeint_groups(mods, y0, t, method="rk4", options=dict(step_size=1.0))
+    y = ude_b200.odeint_groups(mods, y0, t, method="rk4", options=dict(step_size=1.0, kernels=kernels))
     (y[..., :3] ** 2).sum().backward()
     assert torch.isfinite(y).all() and torch.isfinite(y0.grad).all()
     mod = module_from_spec(spec, thetas[17], 1.0, "cuda")
     y0s = y0[17].detach().clone().requires_grad_(True)
-    ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
+    ys = ude_b200.odeint(mod, y0s, t, method="rk4", options=dict(step_size=1.0, kernels=kernels))
     (ys[..., :3] ** 2).sum().backward()
     assert torch.equal(ys, y[17])
     assert torch.equal(y0s.grad, y0.grad[17])

@@ -21,11 +21,12 @@ mods = [module_from_spec(spec, init_theta(spec, rank * G + g), 1.0, dev) for g i
 y0 = synth_y0(G * Bg, 1, 8, seed=3 + rank).reshape(G, Bg, 1, 8).to(dev)
 t = torch.linspace(1, 56, 56) / 7
 
+flat = ude_b200.flatten_group_parameters(mods)       # the weights of this rank's models as ONE [G, n_theta] leaf (one optimizer trains them all)
+
 def step():
     y0g = y0.clone().requires_grad_(True)
-    for m in mods:
-        m.zero_grad(set_to_none=True)
-    y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=1.0))
+    flat.grad = None
+    y = ude_b200.odeint_groups(mods, y0g, t, method="rk4", options=dict(step_size=1.0), theta=flat)
     (y[..., 1] ** 2).mean().backward()
 
 for _ in range(3):
@@ -45,7 +46,7 @@ if world > 1:
 if rank == 0:
     ms = float(ms)
     print(json.dumps({"config": f"configs[4]: {G * world} weight-set groups x Fp(R=1,L=8,[32,32]) x {Bg} trajectories over {world} GPU(s), "
-                                "RK4 h=1 t=[1/7..8] (8 grid steps, 56 outputs), grouped fwd + adjoint launch per rank, no collective",
+                                "RK4 h=1 t=[1/7..8] (8 grid steps, 56 outputs), ONE grouped fwd + ONE grouped adjoint launch per rank (tcgen05 engine), weights as one [G, n_theta] leaf, no collective",
                       "n_gpus": world, "groups_per_gpu": G, "ms_per_iter": ms, "trajectory_steps_per_s": world * G * Bg * 8 / (ms * 1e-3)}))
 if world > 1:
     dist.destroy_process_group()
