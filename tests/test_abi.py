@@ -118,7 +118,7 @@ def test_descriptor_validation_and_plan(built_lib):
 def test_group_plan_is_g_single_group_plans(built_lib):
     """n_groups = G (BASELINE configs[4]): the tape is G per-group blocks of the single-set plan (group-major layouts,
     include/ude_b200.h), the workspace at least that, theta size stays per group; batch must divide by G.  Small models
-    run all groups in ONE launch (plan.path == 2) with tiles sized for the total batch."""
+    run all groups in ONE launch (plan.path == 3 on the tcgen05 engine, 2 on the FFMA engine with tiles sized for the total batch)."""
     from ude_b200 import _lib
     one = _desc("Fp", 1, 8, [32, 32, 2], [], B=2048)
     p1 = _lib.UdePlan()
@@ -131,8 +131,73 @@ def test_group_plan_is_g_single_group_plans(built_lib):
     assert pg.workspace_bytes >= 512 * up(p1.workspace_bytes)
     assert pg.tape_bytes == 512 * up(p1.tape_bytes)
     assert pg.n_theta == p1.n_theta == built_lib.ude_theta_size(C.byref(grp))
+    assert pg.path == 3 and pg.tile_traj == 128 and pg.n_ctas == 148          # default: all groups in one tcgen05 launch
+    grp.flags |= 4                                                              # UDE_FLAG_FORCE_FFMA
+    assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) == 0
     assert pg.path == 2 and pg.tile_traj == 64 and pg.n_ctas == 2 * 148
+    grp.flags &= ~4
     grp.batch = 512 * 2048 + 1
     assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["rk4"], 56, C.byref(pg)) != 0
     grp.batch = 512 * 2048
     assert built_lib.ude_plan(C.byref(grp), _lib.METHOD["dopri5"], 56, C.byref(pg)) == -2      # UDE_ERR_UNSUPPORTED
+
+
+def test_plan_paths_and_modes_host_only(built_lib):
+    """ude_plan is host arithmetic (148 SMs assumed without a GPU): kernel family per configuration, the Bayes and group
+    modes' sizes, and the explicit rejections."""
+    import ude_b200
+    from ude_b200 import _lib
+    L = built_lib
+
+    def plan(mod, B, n_steps=8, kernels=None, groups=1, flags=0, method=0):
+        info = ude_b200.describe_func(mod)
+        info.kernels = kernels
+        d = info.desc(B * groups, n_groups=groups)
+        d.flags |= flags
+        p = _lib.UdePlan()
+        return L.ude_plan(C.byref(d), method, n_steps, C.byref(p)), p
+
+    us = ude_b200.FaFp(1, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    st, p = plan(us, 1)
+    assert st == 0 and p.path == 1 and p.tile_traj == 128          # tcgen05 engine at every batch size
+    st, p1 = plan(us, 1 << 20)
+    assert st == 0 and p1.path == 1 and p1.n_ctas == 148
+    assert p1.tape_bytes >= (8 * 4 + 1) * 3 * (1 << 20) * 4          # stage inputs + ONE record for the final state
+    st, p = plan(us, 4096, kernels="ffma")
+    assert st == 0 and p.path == 0
+    st, pb = plan(us, 4096, flags=_lib.FLAG_BAYES)
+    assert st == 0 and pb.path == 0 and pb.workspace_bytes > p.workspace_bytes + 2 * 32 * 11813 * 4     # weight sets + noise of 32 evaluations
+    assert plan(us, 4096, flags=_lib.FLAG_BAYES | 8)[0] == -2          # Bayes funcs: FFMA engine only
+    assert plan(us, 4096, flags=_lib.FLAG_BAYES, method=1)[0] == -2   # ... and rk4 only
+    states = ude_b200.FaFp(49, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    st, p = plan(states, 8192, n_steps=28)
+    assert st == 0 and p.path == 0 and p.tile_traj == 32 and p.weights_in_smem == 0     # ring plan: weights stream through shared memory
+    assert plan(states, 8192, kernels="tensor")[0] == -2
+    assert plan(states, 2048, flags=_lib.FLAG_BAYES)[0] == -2          # too wide for the all-resident plans
+    sweep = ude_b200.Fp(1, 8, net_sizes=[32, 32])
+    st, p = plan(sweep, 2048, groups=64)
+    assert st == 0 and p.path == 3 and p.n_ctas == 148                 # all groups in one tcgen05 launch
+    st, p = plan(sweep, 2048, groups=64, kernels="ffma")
+    assert st == 0 and p.path == 2
+
+
+def test_front_end_argument_checks_need_no_gpu():
+    """The Python front ends validate before they touch the device: wrong shapes / devices / modes raise, nothing falls back."""
+    import ude_b200
+    us = ude_b200.FaFp(1, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
+    dec = ude_b200.Decoder(1, 8, 1)
+    t = torch.arange(4.)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ude_b200.odeint(us, torch.zeros(4, 1, 8), t, method="rk4", options=dict(step_size=1.0))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ude_b200.odeint_decoded(us, dec, torch.zeros(4, 1, 8), t, options=dict(step_size=1.0))
+    with pytest.raises(ValueError):
+        ude_b200.odeint_decoded(us, torch.nn.Linear(4, 1), torch.zeros(4, 1, 8), t)
+    with pytest.raises(ude_b200.UnsupportedFunc):
+        ude_b200.odeint_decoded(us, ude_b200.Decoder(1, 8, 1, Fp=False), torch.zeros(4, 1, 8), t)
+    bayes = ude_b200.Bayes_FaFp(1, 8)
+    assert ude_b200.describe_func(bayes).bayes
+    with pytest.raises(NotImplementedError):
+        ude_b200.odeint_decoded(bayes, dec, torch.zeros(4, 1, 8), t)
+    with pytest.raises(ude_b200.UnsupportedFunc):
+        ude_b200.describe_func(torch.nn.Linear(3, 3))
