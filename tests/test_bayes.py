@@ -192,3 +192,38 @@ def test_bayes_default_noise_and_rejections():
         ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0, kernels="tensor"))
     with pytest.raises(NotImplementedError):
         ude_b200.odeint(mod, y0, t, method="dopri5", options=dict(per_trajectory=True))
+
+
+@pytest.mark.gpu
+def test_bayes_with_zero_noise_equals_the_deterministic_func_over_many_tiles():
+    """z = 0 makes every evaluation's weight set the mean: several tiles per CTA, ragged last tile -- the per-evaluation
+    re-staging, the per-evaluation constant products and the fold must reproduce the plain FFMA-engine solve of an FaFp module
+    that holds the means (trajectories bit for bit, gradients to summation round-off; dL/dw_std is exactly zero)."""
+    import ude_b200
+    B = 148 * 64 * 2 + 37
+    mod = _build(ude_b200, "Bayes_FaFp", 1, 8, (64, 64, 32), (64, 64), seed=9).cuda()
+    with torch.no_grad():
+        mod.aug_net[-1].w_mean.mul_(0.05); mod.aug_net[-1].b_mean.mul_(0.05)
+    plain = ude_b200.FaFp(1, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64]).cuda()
+    with torch.no_grad():
+        for dst_net, src_net in ((plain.net, mod.Fp_net), (plain.aug_net, mod.aug_net)):
+            for d, s_ in zip([m for m in dst_net if isinstance(m, torch.nn.Linear)], [m for m in src_net if hasattr(m, "w_mean")]):
+                d.weight.copy_(s_.w_mean); d.bias.copy_(s_.b_mean)
+    t = torch.arange(4.)
+    y0 = synth_y0(B, 1, 8, seed=4).cuda()
+    G = torch.randn(4, B, 1, 8, generator=torch.Generator().manual_seed(3)).cuda()
+    n_theta = sum(p.numel() for l in _var_layers(mod) for p in (l.w_mean, l.b_mean))
+    ya0 = y0.clone().requires_grad_(True)
+    ya = ude_b200.odeint(mod, ya0, t, method="rk4", options=dict(step_size=1.0, bayes_z=torch.zeros(12, n_theta, device="cuda")))
+    (ya * G).sum().backward()
+    yb0 = y0.clone().requires_grad_(True)
+    yb = ude_b200.odeint(plain, yb0, t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
+    (yb * G).sum().backward()
+    assert torch.equal(ya, yb)
+    assert rel_err(ya0.grad, yb0.grad) <= 1e-6
+    ls = _var_layers(mod)
+    gm = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)])
+    gs = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_std, l.b_std)])
+    gp = torch.cat([p.grad.reshape(-1) for net in (plain.net, plain.aug_net) for m in net if isinstance(m, torch.nn.Linear) for p in (m.weight, m.bias)])
+    assert rel_err(gm, gp) <= 3e-6
+    assert float(gs.abs().max()) == 0.0
