@@ -1,0 +1,161 @@
+"""Seeded random configurations (kind x R x L x widths x depth x grid x batch x mode) through the fused path against the
+oracle: the plan selection (tile size, resident / ring / cold plans, hoisting on or off, engine) sees shapes no hand-written
+case lists -- odd widths, L = 3 (no constants to hoist), deep nets, ragged tiles -- in the plain, decoded, reparam and Bayes
+modes.  Every case must meet the 1e-5 parity bar on outputs and on every gradient.  The oracle runs in fp64 here: with the
+large, cancelling gradient sums these random losses produce, the fp32 oracle itself sits up to 6e-6 from the fp64 result, so a
+1e-5 bar between two fp32 implementations would measure the oracle's round-off, not the kernels'."""
+import os
+import random
+
+import pytest
+import torch
+
+from tests.util import RTOL_PARITY, flat_grad, module_from_spec, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    rng = random.Random(seed)
+    kind = rng.choice(["Fp", "Fa", "FaFp"])
+    R = rng.choice([1, 1, 2, 3, 5, 7, 10])
+    L = rng.choice([3, 4, 5, 8, 8, 16])
+    depth = rng.choice([1, 2, 2, 3, 4])
+    widths = lambda: tuple(rng.choice([5, 12, 20, 32, 33, 64]) for _ in range(depth))
+    net = widths() if kind != "Fa" else ()
+    aug = widths() if kind != "Fp" else ()
+    B = rng.choice([1, 7, 33, 64, 100, 257])
+    grid = rng.choice(["weekly", "daily", "interp"])
+    mode = rng.choice(["plain", "plain", "decoded", "reparam", "bayes"])
+    return kind, R, L, net, aug, B, grid, mode
+
+
+def _grid(name):
+    if name == "weekly":
+        return torch.arange(4.), 1.0
+    if name == "daily":
+        t = torch.arange(11.) / 7
+        return t, t[1] - t[0]
+    return torch.linspace(1, 15, 15) / 7, 1.0
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("UDE_FUZZ_N", "48"))))       # UDE_FUZZ_N=1000 for a long hunt
+def test_random_configuration_matches_oracle(seed):
+    import ude_b200
+    from oracle import odeint_ref
+    from oracle.ude_rhs import BayesOracleFunc, OracleFunc, UdeSpec, init_theta, synth_y0
+    kind, R, L, net, aug, B, grid, mode = _case(seed)
+    spec = UdeSpec(kind, R, L, net, aug)
+    theta = init_theta(spec, seed=seed)
+    t, h = _grid(grid)
+    g = torch.Generator().manual_seed(seed)
+    y0 = synth_y0(B, R, L, seed=seed + 1)
+    n_steps = {"weekly": 3, "daily": 10, "interp": 2}[grid]
+    fa_w = 0.7 if kind == "FaFp" else 1.0
+    print(f"seed {seed}: {kind} R={R} L={L} net={net} aug={aug} B={B} {grid} {mode}")
+
+    if mode == "bayes":
+        cls = {"Fp": "Bayes_Fp", "Fa": "Bayes_Fa", "FaFp": "Bayes_FaFp"}[kind]
+        kw = {}
+        if net:
+            kw["net_sizes"] = list(net)
+        if aug:
+            kw["aug_net_sizes"] = list(aug)
+        torch.manual_seed(seed)
+        mod = getattr(ude_b200, cls)(n_regions=R, latent_dim=L, **kw)
+        layers = [m for n_ in ("Fp_net", "aug_net") if hasattr(mod, n_) for m in getattr(mod, n_) if hasattr(m, "w_mean")]
+        with torch.no_grad():
+            for l in layers:
+                l.w_std.mul_(0.2); l.b_std.mul_(0.2)
+            if aug:
+                for p in (mod.aug_net[-1].w_mean, mod.aug_net[-1].b_mean, mod.aug_net[-1].w_std, mod.aug_net[-1].b_std):
+                    p.mul_(0.05)
+        if kind == "FaFp":
+            mod.Fa_w = fa_w
+        mean = torch.cat([p.detach().reshape(-1) for l in layers for p in (l.w_mean, l.b_mean)])
+        std = torch.cat([p.detach().reshape(-1) for l in layers for p in (l.w_std, l.b_std)])
+        z = torch.randn(4 * n_steps, mean.numel(), generator=g)
+        f = BayesOracleFunc(spec, mean.double(), std.double(), z.double(), fa_w).double()
+    else:
+        f = OracleFunc(spec, theta.double(), fa_w).double()
+        mod = module_from_spec(spec, theta, fa_w, "cpu")
+    mod = mod.cuda()
+    n_dec = R
+    dec_w, dec_b = 0.3 * torch.randn(n_dec, 3 * R, generator=g), 0.1 * torch.randn(n_dec, generator=g)
+    G = torch.randn(t.numel(), B, R, L, generator=g)
+    Gd = torch.randn(t.numel(), B, n_dec, generator=g)
+
+    def tail(func):
+        out = 0.0
+        if spec.has_rate:
+            post = func.posterior()
+            out = out + 0.3 * B * post.mean.sum()
+            if B * R >= 16:     # the std of a handful of nearly equal fp32 rates is ill conditioned: d std / d x_i = (x_i - mean) / ((N-1) std)
+                out = out - 0.2 * B * post.stddev.sum()
+        if spec.has_aug:
+            out = out + 0.1 * B ** 0.5 * torch.norm(torch.stack(func.tracker))
+        return out
+
+    # ---- oracle
+    if mode == "reparam":
+        S, b = (B, 1) if B < 4 else (B // 2 if B % 2 == 0 else B, 2 if B % 2 == 0 else 1)
+        mean_r = torch.tensor([0.9, 0.02] + [0.0] * (L - 3)).expand(b, R, L - 1) + 0.01 * torch.randn(b, R, L - 1, generator=g)
+        std_r = (torch.tensor([0.1, 0.05] + [1.0] * (L - 3)) * 0.3).expand(b, R, L - 1).clone()
+        eps = torch.randn(S, b, R, L - 1, generator=g)
+        e_, s_, m_ = (x.double().clone().requires_grad_(True) for x in (eps, std_r, mean_r))
+        zz = e_ * s_ + m_
+        y0r = torch.cat([zz[..., :2].abs(), (1 - zz[..., :2].abs().sum(-1)).unsqueeze(-1), zz[..., 2:]], -1).reshape(S * b, R, L) + 1e-5
+    else:
+        y0r = y0.double().clone().requires_grad_(True)
+    # fp64 solve on the SAME fp32-built grid (the grid arithmetic is part of the path: ude_rk4_grid restates it bit for bit)
+    grid64 = odeint_ref.rk4_grid(t, h).double()
+    lat = odeint_ref.odeint(f, y0r, t.double(), method="rk4", options=dict(grid_constructor=lambda *_: grid64))
+    if mode == "decoded":
+        wr, br = dec_w.double().clone().requires_grad_(True), dec_b.double().clone().requires_grad_(True)
+        x3 = lat[..., :3]
+        yr = torch.nn.functional.linear(x3.reshape(t.numel(), B, 3 * R), wr, br)
+        regr = (torch.where(x3 < 0, x3.abs(), torch.zeros_like(x3)) + torch.where(x3 > 1, (1 - x3).abs(), torch.zeros_like(x3))).sum()
+        ((yr * Gd.double()).sum() + 0.5 * regr + tail(f)).backward()
+    else:
+        yr = lat
+        ((yr * G.double()).sum() + tail(f)).backward()
+
+    # ---- fused
+    opts = dict(step_size=h)
+    mod.clear_tracking()
+    if mode == "reparam":
+        e2, s2, m2 = (x.cuda().requires_grad_(True) for x in (eps, std_r, mean_r))
+        y = ude_b200.odeint_reparam(mod, e2, s2, m2, t, options=opts)
+        ((y * G.cuda()).sum() + tail(mod)).backward()
+        assert rel_err(s2.grad, s_.grad) <= RTOL_PARITY and rel_err(m2.grad, m_.grad) <= RTOL_PARITY
+    elif mode == "decoded":
+        lin = torch.nn.Linear(3 * R, n_dec).cuda()
+        with torch.no_grad():
+            lin.weight.copy_(dec_w); lin.bias.copy_(dec_b)
+        y0g = y0.cuda().requires_grad_(True)
+        y, reg = ude_b200.odeint_decoded(mod, lin, y0g, t, options=opts)
+        ((y * Gd.cuda()).sum() + 0.5 * reg + tail(mod)).backward()
+        assert abs(float(reg) - float(regr)) <= 1e-5 * max(1.0, abs(float(regr)))
+        assert rel_err(lin.weight.grad, wr.grad) <= RTOL_PARITY
+        # the bias gradient is a plain sum of the (random, cancelling) cotangents: judged at the scale of its terms
+        assert float((lin.bias.grad.cpu().double() - br.grad).abs().max()) <= RTOL_PARITY * float(Gd.abs().sum(dim=(0, 1)).max())
+        assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
+    else:
+        y0g = y0.cuda().requires_grad_(True)
+        if mode == "bayes":
+            opts["bayes_z"] = z.cuda()
+        try:
+            y = ude_b200.odeint(mod, y0g, t, method="rk4", options=opts)
+        except ude_b200.UdeError as e:
+            if mode == "bayes" and e.status == -2:      # UDE_ERR_UNSUPPORTED: Bayes funcs need the all-resident plans
+                pytest.skip("model too large for the Bayes mode's all-resident plans: explicit UDE_ERR_UNSUPPORTED")
+            raise
+        ((y * G.cuda()).sum() + tail(mod)).backward()
+        assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
+    assert rel_err(y, yr) <= RTOL_PARITY
+    if mode == "bayes":
+        gm = torch.cat([p.grad.reshape(-1) for l in layers for p in (l.w_mean, l.b_mean)])
+        gs = torch.cat([p.grad.reshape(-1) for l in layers for p in (l.w_std, l.b_std)])
+        assert rel_err(gm, f.theta.grad) <= RTOL_PARITY and rel_err(gs, f.std.grad) <= RTOL_PARITY
+    else:
+        assert rel_err(flat_grad(mod), f.theta.grad) <= RTOL_PARITY
