@@ -159,3 +159,44 @@ def test_random_configuration_matches_oracle(seed):
         assert rel_err(gm, f.theta.grad) <= RTOL_PARITY and rel_err(gs, f.std.grad) <= RTOL_PARITY
     else:
         assert rel_err(flat_grad(mod), f.theta.grad) <= RTOL_PARITY
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("UDE_FUZZ_N_DOPRI", "24"))))
+def test_random_configuration_dopri5(seed):
+    """Dopri5 over random shapes, both controllers.  A controller whose arithmetic does not depend on the data (tolerances so loose
+    that the error ratio is ~0: every step accepted and grown by exactly ifactor; given first step) makes the fused solve and its
+    frozen-step adjoint comparable with autograd through the oracle, outputs AND gradients: dt = 0.02 * 2^k in both."""
+    import ude_b200
+    from oracle import odeint_ref
+    from oracle.ude_rhs import OracleFunc, UdeSpec, init_theta, synth_y0
+    rng = random.Random(10_000 + seed)
+    kind = rng.choice(["Fp", "Fa", "FaFp"])
+    R = rng.choice([1, 2, 3, 5, 10])
+    L = rng.choice([3, 4, 8, 16])
+    depth = rng.choice([1, 2, 3])
+    widths = lambda: tuple(rng.choice([12, 20, 32, 64]) for _ in range(depth))
+    net = widths() if kind != "Fa" else ()
+    aug = widths() if kind != "Fp" else ()
+    B = rng.choice([1, 9, 64, 130])
+    shared = rng.choice([True, False])
+    spec = UdeSpec(kind, R, L, net, aug)
+    theta = init_theta(spec, seed=seed)
+    y0 = synth_y0(B, R, L, seed=seed + 3)
+    t = torch.tensor([0.0, 0.7, 1.5, 3.0])
+    G = torch.randn(4, B, R, L, generator=torch.Generator().manual_seed(seed))
+    print(f"seed {seed}: {kind} R={R} L={L} net={net} aug={aug} B={B} shared={shared}")
+    kw = dict(rtol=1e3, atol=1e3)
+    f = OracleFunc(spec, theta)
+    st = odeint_ref.Dopri5Stats()
+    y0r = y0.clone().requires_grad_(True)
+    yr = odeint_ref.odeint(f, y0r, t, options=dict(first_step=0.02, ifactor=2.0, per_trajectory=not shared, stats=st), **kw)
+    (yr * G).sum().backward()
+    mod = module_from_spec(spec, theta, 1.0, "cuda")
+    y0g = y0.cuda().requires_grad_(True)
+    y, stats = ude_b200.odeint(mod, y0g, t, options=dict(first_step=0.02, ifactor=2.0, per_trajectory=not shared, return_stats=True), **kw)
+    (y * G.cuda()).sum().backward()
+    ref_acc = st.n_accept if shared else st.n_accept.tolist()
+    assert stats.n_accept.cpu().tolist() == ([int(ref_acc)] * B if shared else ref_acc)
+    assert rel_err(y, yr) <= RTOL_PARITY
+    assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
+    assert rel_err(flat_grad(mod), f.theta.grad) <= RTOL_PARITY
