@@ -12,9 +12,11 @@ from oracle.ude_rhs import UdeSpec, init_theta, synth_y0
 from tests.util import module_from_spec
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 64 * 4
-spec = UdeSpec("FaFp", 1, 8, (64, 64, 32), (64, 64))
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+TILE = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+spec = UdeSpec("FaFp", R, 8, (64, 64, 32), (64, 64))
 mod = module_from_spec(spec, init_theta(spec, 0), 1.0, "cuda")
-y0 = synth_y0(B, 1, 8, seed=1).cuda()
+y0 = synth_y0(B, R, 8, seed=1).cuda()
 t = torch.arange(9.)
 L = ude_b200.lib()
 nw = 8
@@ -39,9 +41,9 @@ def dump(title, n_evals):
     print(f"  sum of phase spans {tot:8.0f}")
 
 
-tiles_cta0 = (B // 64 + 147) // 148
+tiles_cta0 = (B // TILE + 147) // 148
 y0g = y0.clone().requires_grad_(True)
-y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=1.0))
+y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
 torch.cuda.synchronize()
 dump("forward kernel", tiles_cta0 * 32)
 (y[..., :3] ** 2).sum().backward()
