@@ -412,6 +412,23 @@ def secondary_configs(dev, ffma_peak_tflops: float, with_cpu: bool) -> dict:
         rec["cuda_graph_error"] = f"{type(e).__name__}: {e}"
     out["training shape B=2048 FaFp R=1, 7 weekly RK4 steps, fwd+backprop"] = rec
 
+    # ---- configs[3] variants of SURVEY 8d: the headline model on the 56-step daily grid, and the rate-only Fp([64, 64]) model
+    B3 = 1 << 20
+    y0 = synth_y0(B3, 1, 8, seed=7).to(dev)
+    t = torch.arange(57.) / 7
+    ms = _cuda_timed(fwd_bwd(mod1, y0, t, method="rk4", options=dict(step_size=t[1] - t[0])), reps=2, warm=1)
+    ts = B3 * 56 / (ms * 1e-3)
+    out["configs[3] variant: FaFp R=1, B=2^20, 56 daily RK4 steps (t = arange(57)/7, h = t[1]-t[0]) fwd+adjoint"] = {
+        "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * spec1.macs_per_eval() / peak}
+    specp = UdeSpec("Fp", 1, 8, (64, 64), ())
+    modp = _module(specp, init_theta(specp, 0), dev)
+    t = torch.arange(9.)
+    ms = _cuda_timed(fwd_bwd(modp, y0, t, method="rk4", options=dict(step_size=1.0)))
+    ts = B3 * 8 / (ms * 1e-3)
+    out["configs[3] variant: Fp([64, 64]) R=1, B=2^20, 8 weekly RK4 steps fwd+adjoint"] = {
+        "ms_per_iter": ms, "trajectory_steps_per_s": ts, "frac_ffma": ts * 24 * specp.macs_per_eval() / peak}
+    del y0, modp
+
     # ---- configs[2]: 49 states x 256 latent samples (x b), 28 daily RK4 steps
     spec49 = UdeSpec("FaFp", 49, 8, (64, 64, 32), (64, 64))
     mod49 = _module(spec49, init_theta(spec49, 0), dev)
