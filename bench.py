@@ -240,6 +240,20 @@ def _loss(y, y_ili, func, dec=None):
     return _loss_tail(pred, y_ili if dec is None else y_ili.reshape(-1, 1, 1), reg, y.shape[1], func)
 
 
+_PRIORS = {}
+
+
+def _prior(device):
+    """N([0.8, 0.55], [0.2, 0.2]) (lib/VAE.py:42-43), built once per device: creating tensors from python lists is a host -> device
+    copy, which a CUDA-graph capture of the iteration must not contain."""
+    import torch
+    from torch.distributions import Normal
+    key = str(device)
+    if key not in _PRIORS:
+        _PRIORS[key] = Normal(torch.tensor([0.8, 0.55], device=device), torch.tensor([0.2, 0.2], device=device), validate_args=False)
+    return _PRIORS[key]
+
+
 def _loss_tail(pred, y_ili, reg_sum, B, func):
     """mse(pred, y_ili) + 0.1 * reg_sum / B + kl_p + 0.1 * Fa_norm / sqrt(B): shared by the plain path (pred / reg from torch ops on
     the trajectories) and the fused-consumer path (pred / reg straight from ude_b200.odeint_decoded)."""
@@ -250,8 +264,7 @@ def _loss_tail(pred, y_ili, reg_sum, B, func):
     loss = mse + 0.1 * reg_sum / B
     if getattr(func, "params", None):
         post = func.posterior()
-        prior = Normal(torch.tensor([0.8, 0.55], device=y.device), torch.tensor([0.2, 0.2], device=y.device))
-        loss = loss + kl_divergence(prior, post).mean()
+        loss = loss + kl_divergence(_prior(pred.device), post).mean()
     if getattr(func, "tracker", None):
         loss = loss + 0.1 * torch.norm(torch.stack(func.tracker)) / (B ** 0.5)
     return loss
@@ -704,9 +717,62 @@ def run_ours(args):
         return float(te.item()), r
 
     plain_sec, res_plain = time_e2e(False)
-    e2e_sec, res = time_e2e(True)
-    e2e_value = world * B * n_steps / e2e_sec
+    fused_sec, res = time_e2e(True)
     e2e_agree = float((res - res_plain).abs().max() / res_plain.abs().max())      # both legs compute the same loss and gradients
+    e2e_api = ("ude_b200.odeint_decoded (solve + Decoder + latent_init_loss fused, SURVEY 8f2), loss tail in torch, backward, "
+               "gradients to host")
+    e2e_sec = fused_sec
+    graphed = None
+    if not args.no_graph_e2e:
+        # the same iteration through the package's iteration driver: H2D copy of y0 from pinned memory, ONE CUDA-graph
+        # replay (fused solve, loss tail, adjoint, gradient all-reduce), D2H read of [loss | gradients].  Fresh modules: their
+        # gradient accumulators must be created on the capture's stream.
+        try:
+            mod_g = _module(spec, init_theta(spec, seed=0), dev)
+            dec_g = _decoder(dev)
+            params_g = [*mod_g.parameters(), *dec_g.parameters()]
+            opts_g = dict(step_size=t[1] - t[0])
+            if world > 1:
+                opts_g["process_group"] = True
+
+            def step_fn(y0d):
+                mod_g.clear_tracking()
+                yp, reg = ude_b200.odeint_decoded(mod_g, dec_g, y0d, t, options=opts_g)
+                return _loss_tail(yp, y_ili, reg, yp.shape[1], mod_g)
+
+            def after(loss):
+                flat = torch.cat([p.grad.reshape(-1) for p in params_g])
+                if world > 1:
+                    dist.all_reduce(flat)
+                return torch.cat([loss.reshape(1), flat])
+
+            it = ude_b200.GraphedIteration(step_fn, params_g, after_backward=after, device=dev)
+            y0_req = y0_host.requires_grad_(True)
+
+            def step_graph():
+                it(y0_req)
+                return it.last_extra.to("cpu")
+
+            step_graph()
+            barrier()
+            g_steps = max(1, min(args.steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(g_steps):
+                res_g = step_graph()
+            barrier()
+            sec = (time.perf_counter() - t0) / g_steps
+            tg = torch.tensor([sec], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            graphed = {"sec": float(tg.item()), "max_rel_diff_vs_eager": float((res_g - res).abs().max() / res.abs().max())}
+            if graphed["max_rel_diff_vs_eager"] <= 1e-4:
+                e2e_sec, res = graphed["sec"], res_g
+                e2e_api = ("ude_b200.GraphedIteration (SURVEY 8f4) over ude_b200.odeint_decoded (8f2): pinned-host y0 -> H2D -> one CUDA-graph "
+                           "replay (fused solve + Decoder + latent_init_loss, loss tail, adjoint" + (", NCCL all-reduces" if world > 1 else "") +
+                           ") -> D2H of [loss | gradients]")
+        except Exception as e:
+            graphed = {"error": f"{type(e).__name__}: {e}"[:300]}
+    e2e_value = world * B * n_steps / e2e_sec
 
     if rank == 0:
         peak = C.c_double(0.0)
@@ -794,7 +860,9 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(y0_host.numel() * 4),
                     "d2h_bytes_per_step": int(res.numel() * 4), "ms_per_step": e2e_sec * 1e3,
-                    "api": "ude_b200.odeint_decoded (solve + Decoder + latent_init_loss fused, SURVEY 8f2), loss tail in torch, backward, gradients to host",
+                    "api": e2e_api,
+                    "eager_odeint_decoded": {"value": world * B * n_steps / fused_sec, "ms_per_step": fused_sec * 1e3},
+                    "cuda_graph": graphed,
                     "plain_odeint": {"value": world * B * n_steps / plain_sec, "ms_per_step": plain_sec * 1e3,
                                      "api": "ude_b200.odeint, then Decoder + losses as torch ops on the [T,B,R,L] trajectories (lib/VAE.py:137-138,186)"},
                     "fused_vs_plain_max_rel_diff": e2e_agree},
@@ -807,9 +875,16 @@ def run_ours(args):
             line["dist_check"] = check
         if secondary is not None:
             line["secondary"] = secondary
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The graphed end-to-end leg captured NCCL kernels; tearing the communicator down while such graphs exist can wait forever
+        # (observed: the line above printed, then destroy_process_group() never returned).  Everything is measured and printed:
+        # meet at a barrier, then leave without the teardown.
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -821,6 +896,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="trajectories PER GPU (default: 2**20 in total, sharded)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-graph-e2e", action="store_true", help="time the end-to-end leg eagerly only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -36,15 +36,24 @@ class GraphedIteration:
       below it -- here as a device-side blend, so a gated iteration leaves the parameters AND the optimizer state of the
       previous iteration in place without a host decision.
     tag: anything hashable that changes the captured work without changing input shapes (e.g. the time grid's bytes).
+    after_backward: optional ``fn(loss) -> tensor | None`` run INSIDE the captured iteration once the gradients sit in
+      ``p.grad`` and before the optimizer: the place for the gradient all-reduce of a sharded run (NCCL collectives are
+      capturable); what it returns is kept as ``it.last_extra`` (a static tensor: e.g. the flat reduced gradient to read back).
+    device: where the captured work runs when the inputs are HOST tensors (pinned memory): every call then starts with the
+      asynchronous host -> device copy of the inputs into the graph's static buffers.
     """
 
     def __init__(self, step_fn: Callable[..., torch.Tensor], params: Iterable[torch.nn.Parameter],
-                 optimizer: Optional[torch.optim.Optimizer] = None, grad_lim: Optional[float] = None, warmup: int = 3):
+                 optimizer: Optional[torch.optim.Optimizer] = None, grad_lim: Optional[float] = None, warmup: int = 3,
+                 after_backward: Optional[Callable[[torch.Tensor], Optional[torch.Tensor]]] = None, device=None):
         self.step_fn = step_fn
         self.params = [p for p in params]
         self.optimizer = optimizer
         self.grad_lim = grad_lim
         self.warmup = warmup
+        self.after_backward = after_backward
+        self.device = torch.device(device) if device is not None else None
+        self.last_extra = None
         self._graphs: Dict[tuple, Tuple[torch.cuda.CUDAGraph, list, torch.Tensor, torch.Tensor, torch.Tensor]] = {}
 
     # ---- one eager iteration (also the warm-up and the body that is captured)
@@ -63,6 +72,7 @@ class GraphedIteration:
                     p.grad = g.detach().clone()
                 else:
                     p.grad.copy_(g)
+        extra = self.after_backward(loss.detach()) if self.after_backward is not None else None
         grads = [p.grad for p in self.params if p.grad is not None]
         norm = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads])) if grads else loss.new_zeros(())
         ok = torch.ones((), device=loss.device)
@@ -86,20 +96,20 @@ class GraphedIteration:
                                 cur = self.optimizer.state[p][k]
                                 cur.copy_(torch.lerp(v.to(cur.dtype), cur, ok.to(cur.dtype)))
                             i += 1
-        return loss.detach(), norm.detach(), ok
+        return loss.detach(), norm.detach(), ok, extra
 
     def __call__(self, *inputs: torch.Tensor, tag=None):
         key = _key(inputs, tag)
         entry = self._graphs.get(key)
         if entry is None:
             entry = self._capture(inputs, key)
-        graph, static_in, loss, norm, ok = entry
+        graph, static_in, loss, norm, ok, extra = entry
         with torch.no_grad():       # static inputs may be leaves that require grad (dL/dy0 wanted)
             for s, x in zip(static_in, inputs):
                 if s.data_ptr() != x.data_ptr():
-                    s.copy_(x, non_blocking=True)
+                    s.copy_(x, non_blocking=True)          # host inputs: the H2D copy of this iteration, on the replay's stream
         graph.replay()
-        self.last_norm, self.last_ok = norm, ok
+        self.last_norm, self.last_ok, self.last_extra = norm, ok, extra
         return loss
 
     def _capture(self, inputs, key):
@@ -108,8 +118,8 @@ class GraphedIteration:
         # stream must not synchronise with.  Collect them so that the warm-up below re-creates the nodes on its own stream.
         import gc
         gc.collect()
-        dev = inputs[0].device
-        static_in = [x.detach().clone().requires_grad_(x.requires_grad) for x in inputs]
+        dev = self.device if self.device is not None else inputs[0].device
+        static_in = [x.detach().to(dev, copy=True).requires_grad_(x.requires_grad) for x in inputs]
         # optimizer state must exist before capture (lazy init), grads must be allocated: warm up on a side stream
         snapshot = [p.detach().clone() for p in self.params]
         opt_state = {}
@@ -135,8 +145,8 @@ class GraphedIteration:
                             v.copy_(old) if old is not None else v.zero_()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss, norm, ok = self._iteration(static_in)
-        entry = (graph, static_in, loss, norm, ok)
+            loss, norm, ok, extra = self._iteration(static_in)
+        entry = (graph, static_in, loss, norm, ok, extra)
         self._graphs[key] = entry
         return entry
 
