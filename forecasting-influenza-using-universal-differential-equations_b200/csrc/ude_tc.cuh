@@ -17,8 +17,9 @@
 //   * operands are 3-way bf16 splits (ude_tc_model.h); accumulators are fp32 in TMEM;
 //   * epilogues (bias, ELU, ELU', splits) run thread-per-trajectory straight out of TMEM with
 //     tcgen05.ld 32x32b; the 8 warps split the columns (warp w: lane quarter w&3, column chunks w>>2);
-//   * weight gradients leave TMEM once per RHS evaluation as vector reductions (red.global.add.v4.f32)
-//     into a per-CTA slab; slabs are summed in a fixed order afterwards (deterministic).
+//   * weight gradients leave TMEM once per RHS evaluation through per-warp staging slices and bulk reductions
+//     (cp.reduce.async.bulk.add.f32) into a per-CTA slab (per tile with weight-set groups); slabs are summed in a
+//     fixed order afterwards (deterministic).
 // Descriptor conventions (LBO/SBO of un-swizzled K-major and MN-major operands, M = 64 lane mapping)
 // are pinned on hardware by tools/umma_probe.cu.
 #pragma once

@@ -8,7 +8,8 @@ first then the augmentation net, ``W`` row-major ``[out, in]`` followed by
 ``b``.
 
 Checked bit-for-bit against the real reference classes by
-``tests/test_oracle_vs_reference.py`` (runs wherever /root/reference exists)
+``tests/test_oracle.py::test_rhs_restatement_matches_real_reference_modules`` and, for the Bayesian variants,
+``tests/test_bayes.py::test_oracle_matches_real_reference_bayes_classes`` (both run wherever /root/reference exists)
 and through the committed fixtures in ``tests/golden`` (everywhere).
 """
 from __future__ import annotations
