@@ -438,6 +438,12 @@ int& decoded_ctas() {
 // tensor-core path, defined in ude_tc_host.cu
 int tc_choose(const UdeDesc* d, TcModel& M);
 void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas);
+long long tc_bayes_workspace(const UdeDesc* d, const TcModel& M, int n_steps, int* n_ctas);
+int tc_bayes_forward(const UdeDesc* desc, const TcModel& M, const float* theta_evals, const float* y0, const GridTables& g,
+                     float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int tc_bayes_backward(const UdeDesc* desc, const TcModel& M, const float* theta_evals, const float* z_evals, const float* y0,
+                      const GridTables& g, const float* tape, const float* g_out, const float* g_side, float* g_y0,
+                      float* g_mean_zsum, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int tc_forward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
                float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const float* y0, const GridTables& g,
@@ -596,8 +602,25 @@ int ude_plan(const UdeDesc* desc, int method, int n_steps, UdePlan* plan) {
     // rk4: [n_steps][4 stages][Dn][B] stage inputs + ONE record for the final state (read by the decoded adjoint only)
     if (method == UDE_METHOD_RK4) plan->tape_bytes = align_up(((long long)n_steps * 4 + 1) * Pf.Dn * desc->batch * 4, 256);
     else plan->tape_bytes = dopri_tape_x_bytes(Pf, desc->batch, n_steps) + align_up((long long)n_steps * desc->batch * 16, 256);
-    if (desc->flags & UDE_FLAG_BAYES) {       // per-evaluation weight sets (ude_rk4_*_bayes): FFMA engine, all-resident plans
-        if (method != UDE_METHOD_RK4 || (desc->flags & UDE_FLAG_FORCE_TENSOR)) return UDE_ERR_UNSUPPORTED;
+    if (desc->flags & UDE_FLAG_BAYES) {       // per-evaluation weight sets (ude_rk4_*_bayes)
+        if (method != UDE_METHOD_RK4) return UDE_ERR_UNSUPPORTED;
+        UdeDesc db = *desc;
+        db.flags &= ~UDE_FLAG_BAYES;
+        TcModel Mb;
+        const int pb = tc_choose(&db, Mb);       // tcgen05 engine where it covers the model, else the FFMA engine's all-resident plans
+        if (pb < 0) return pb;
+        if (pb == 1) {
+            int tc_ctas = 0;
+            plan->workspace_bytes = tc_bayes_workspace(desc, Mb, n_steps, &tc_ctas);
+            plan->tape_bytes = align_up(((long long)n_steps * 4 + 1) * Pf.Dn * desc->batch * 4, 256);
+            plan->tile_traj = kTcTile;
+            plan->n_ctas = tc_ctas;
+            plan->smem_bytes_fwd = Mb.smem_bytes_fwd;
+            plan->smem_bytes_bwd = Mb.smem_bytes_bwd;
+            plan->weights_in_smem = 1;
+            plan->path = 1;
+            return UDE_OK;
+        }
         if (!Pf.w_in_smem || Pf.cold_global || !Pb.w_in_smem || !Pb.g_in_smem || Pb.cold_global) return UDE_ERR_UNSUPPORTED;
         plan->workspace_bytes = bayes_carve(nullptr, w.bytes, Pf, n_steps, n_ctas).bytes;
     }
@@ -1046,6 +1069,23 @@ int ude_rk4_forward_bayes(const UdeDesc* desc, const float* theta_evals, const f
                           int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w, float* y_out,
                           float* tape, double* side, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!theta_evals || !y0 || !dt || !out_step || !out_kind || !out_w || !y_out || !side || n_out < 1) return UDE_ERR_INVALID;
+    {   // the tcgen05 engine where it covers the model (R = 1, nets up to 64 wide), else the FFMA engine's all-resident plans
+        int st0 = check_desc(desc);
+        if (st0 != UDE_OK) return st0;
+        if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+        if (n_steps < 1 || !workspace) return UDE_ERR_INVALID;
+        if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+        UdeDesc db = *desc;
+        db.flags &= ~UDE_FLAG_BAYES;
+        TcModel Mt;
+        const int path = tc_choose(&db, Mt);
+        if (path < 0) return path;
+        if (path == 1) {
+            if (pending_reparam().mean || pending_decoded().n_dec > 0) return UDE_ERR_UNSUPPORTED;
+            return tc_bayes_forward(desc, Mt, theta_evals, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, y_out, tape, side,
+                                    workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+        }
+    }
     UdeDesc d;
     ModelP Pf, Pb;
     Workspace w;
@@ -1084,6 +1124,23 @@ int ude_rk4_backward_bayes(const UdeDesc* desc, const float* theta_evals, const 
                            void* workspace, int64_t workspace_bytes, void* stream) {
     if (!theta_evals || !z_evals || !y0 || !dt || !out_step || !out_kind || !out_w || !tape || !g_out || !g_y0 || !g_mean_zsum || n_out < 1)
         return UDE_ERR_INVALID;
+    {
+        int st0 = check_desc(desc);
+        if (st0 != UDE_OK) return st0;
+        if (desc->n_groups != 1) return UDE_ERR_UNSUPPORTED;
+        if (n_steps < 1 || !workspace) return UDE_ERR_INVALID;
+        if (!device_info().ok) return UDE_ERR_NO_DEVICE;
+        UdeDesc db = *desc;
+        db.flags &= ~UDE_FLAG_BAYES;
+        TcModel Mt;
+        const int path = tc_choose(&db, Mt);
+        if (path < 0) return path;
+        if (path == 1) {
+            if (pending_reparam().mean || pending_decoded().n_dec > 0) return UDE_ERR_UNSUPPORTED;
+            return tc_bayes_backward(desc, Mt, theta_evals, z_evals, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, tape,
+                                     g_out, g_side, g_y0, g_mean_zsum, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+        }
+    }
     UdeDesc d;
     ModelP Pf, Pb;
     Workspace w;

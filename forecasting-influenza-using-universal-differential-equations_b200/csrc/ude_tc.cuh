@@ -46,6 +46,7 @@ struct TcFwdArgs {
     int n_groups;
     long long blob_stride;          // bytes between the packed blobs of two groups
     long long tape_group_floats;    // floats between the tapes of two groups
+    int bayes;                      // 1: `blob` holds one packed weight set per RHS evaluation (ude_engine.cuh BayesArgs), blob_stride apart
 };
 
 struct TcBwdArgs {
@@ -63,6 +64,11 @@ struct TcBwdArgs {
     int n_groups;           // see TcFwdArgs; slabs are then per TILE: [n_tiles][slab_floats], g_side [G][5]
     long long blob_stride;
     long long tape_group_floats;
+    // Bayes funcs: `blob` holds one weight set per evaluation; the gradients of evaluation e are reduced twice, as they are into
+    // `slabs` (-> dL/dw_mean) and multiplied by the evaluation's noise into `bz_slabs` (-> dL/dw_std); bayes_z is the noise in SLAB
+    // layout, [4 * n_steps][slab_floats]
+    const float* bayes_z;
+    float* bz_slabs;        // [gridDim.x][slab_floats]
 };
 
 // ----------------------------------------------------------------------------------
@@ -437,6 +443,8 @@ struct TcCtx {
     uint32_t phase_b, phase2;
     uint32_t phase_h[2];    // head hand-off barriers (trajectory warps)
     uint8_t* stage_p;       // backward: gradient staging buffer of the bulk reductions
+    const float* bz_z;      // Bayes funcs: this evaluation's noise in slab layout (nullptr: off) and the second slab
+    float* bz_slab;
     uint32_t sweep_par;     // sweep buffer of the current backward phase
     uint32_t sweep_buf_bytes;
     uint32_t smem_base16;   // dynamic shared-memory base >> 4 (MMA table addresses are relative)
@@ -944,7 +952,7 @@ __device__ __forceinline__ void tc_decode_vjp(const DecArgs& d, float g_reg, int
     if (lane < 4) acc4[lane] += (lane == 0 ? p[0] : (lane == 1 ? p[1] : (lane == 2 ? p[2] : p[3])));
 }
 
-template <int R, int L>
+template <int R, int L, bool BAYES = false>
 __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcFwdArgs a_in) {
     const TcFwdArgs& a = a_in;
     constexpr int D0 = R * L, DN = 3 * R;
@@ -993,6 +1001,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
     c.phase2 = 0;
     c.phase_h[0] = c.phase_h[1] = 0;
     c.stage_p = smem + M.off_stage;
+    c.bz_z = nullptr;
+    c.bz_slab = nullptr;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -1077,6 +1087,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_fwd_tc_kernel(const __grid_
             const float dt = __ldg(a.g.dt + n);
 #pragma unroll 1
             for (int stage = 0; stage < 4; ++stage) {
+                if (BAYES) {        // this evaluation's weight set: every product and head loop of the previous one is consumed
+                    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarTile), "n"(32 * kTcEpiWarps) : "memory");
+                    tc_stage_blob(smem + M.off_w, a_in.blob + (long long)(n * 4 + stage) * a_in.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
+                }
                 float o_r[2 * R], o_a[3 * R];
 #pragma unroll
                 for (int i = 0; i < 2 * R; ++i) o_r[i] = 0.f;
@@ -1240,6 +1254,7 @@ __device__ __forceinline__ void tc_flush_grad(const TcModel& M, const TcLayer& L
     }
 }
 // second half: hand the staged gradients to the copy engine (call after tc_drained)
+template <bool BAYES>
 __device__ __forceinline__ void tc_flush_commit(const TcLayer& Lp, TcCtx& c, float* slab) {
     if (16 * c.q >= Lp.out) return;
     tc_proxy_fence();
@@ -1263,6 +1278,54 @@ __device__ __forceinline__ void tc_flush_commit(const TcLayer& Lp, TcCtx& c, flo
                          "r"(slice + kTcChunksPerWarp * 1024), "n"(64)
                          : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (BAYES) {
+        // Bayes funcs: the same staged gradients, multiplied by this evaluation's noise, reduced into the second slab.  The first
+        // reductions must have READ the slice before it is scaled in place.
+        if (c.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        const int n_chunks = Lp.in_p >> 4;
+        uint8_t* slice_p = c.stage_p + (size_t)c.warp * kTcStageSlice;
+        if (c.lane < 16) {
+#pragma unroll
+            for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                const int ch = c.h + kTcSlots * j;
+                if (ch < n_chunks) {
+                    float4* st = reinterpret_cast<float4*>(slice_p + j * 1024);
+                    const float4* zz = reinterpret_cast<const float4*>(c.bz_z + Lp.slab_off + (size_t)(c.q * n_chunks + ch) * 256);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 v = st[i * 16 + c.lane];
+                        const float4 z = __ldg(zz + i * 16 + c.lane);
+                        v.x *= z.x; v.y *= z.y; v.z *= z.z; v.w *= z.w;
+                        st[i * 16 + c.lane] = v;
+                    }
+                }
+            }
+            if (c.h == 0)
+                reinterpret_cast<float*>(slice_p + kTcChunksPerWarp * 1024)[c.lane] *= __ldg(c.bz_z + Lp.slab_off + 64 * Lp.in_p + 16 * c.q + c.lane);
+        }
+        tc_proxy_fence();
+        __syncwarp();
+        if (c.lane == 0) {
+            float* base = c.bz_slab + Lp.slab_off;
+            const uint32_t slice = smem_u32(slice_p);
+#pragma unroll
+            for (int j = 0; j < kTcChunksPerWarp; ++j) {
+                const int ch = c.h + kTcSlots * j;
+                if (ch < n_chunks)
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                                     base + (size_t)(c.q * n_chunks + ch) * 256),
+                                 "r"(slice + j * 1024), "n"(1024)
+                                 : "memory");
+            }
+            if (c.h == 0)
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(
+                                 base + 64 * Lp.in_p + 16 * c.q),
+                             "r"(slice + kTcChunksPerWarp * 1024), "n"(64)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
 }
 __device__ __forceinline__ void tc_drained(TcCtx& c) {
@@ -1288,7 +1351,7 @@ __device__ __forceinline__ void tc_sweep_image(const TcLayer* Ls, int li, uint32
         tc_store_sweep_ones(c, buf, 16);
     }
 }
-template <int D0, int NH>
+template <int D0, int NH, bool BAYES>
 __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer* Ls, int n, int chain, TcCtx& c,
                                                 const float (&g_head)[NH], const float (&x)[D0], float* slab,
                                                 float (&dx)[D0], bool is_traj) {
@@ -1376,7 +1439,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         TCP_T1();
         tc_flush_grad(M, Lh, c, slab);
         tc_drained(c);
-        tc_flush_commit(Lh, c, slab);
+        tc_flush_commit<BAYES>(Lh, c, slab);
         TCP_ADD1(c, TCP_TAIL);
     }
     // ---------------- steps l = n-2 .. 1
@@ -1442,7 +1505,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
         TCP_T1();
         tc_flush_grad(M, Lp, c, slab);
         tc_drained(c);
-        tc_flush_commit(Lp, c, slab);
+        tc_flush_commit<BAYES>(Lp, c, slab);
         TCP_ADD1(c, TCP_TAIL);
     }
     // ---------------- step 0
@@ -1451,7 +1514,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
     {
         TCP_T1();
         tc_flush_grad(M, Ls[0], c, slab);
-        tc_flush_commit(Ls[0], c, slab);
+        tc_flush_commit<BAYES>(Ls[0], c, slab);
         if (kTcSlots > 1) {
             if (!is_traj) {
                 tc_st16(tm_x + 16 * (c.h - 1), pdx);
@@ -1478,7 +1541,7 @@ __device__ __forceinline__ void tc_net_backward(const TcModel& M, const TcLayer*
     c.sweep_par = par ^ 1u;
 }
 
-template <int R, int L>
+template <int R, int L, bool BAYES = false>
 __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_constant__ TcModel M, const __grid_constant__ TcTable tab, const TcBwdArgs a_in) {
     const TcBwdArgs& a = a_in;
     constexpr int D0 = R * L, DN = 3 * R;
@@ -1528,6 +1591,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
     c.phase2 = 0;
     c.phase_h[0] = c.phase_h[1] = 0;
     c.stage_p = smem + M.off_stage;
+    c.bz_z = nullptr;
+    c.bz_slab = nullptr;
     c.sweep_par = 0;
     c.sweep_buf_bytes = (uint32_t)M.sweep_buf_bytes;
     c.smem_base16 = smem_u32(smem) >> 4;
@@ -1553,6 +1618,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
         for (int i = 0; i < 5; ++i) gs[i] = __ldg(a.g_side + i);
     }
     float* slab = a.slabs + (long long)blockIdx.x * M.slab_floats;
+    if (BAYES) c.bz_slab = a.bz_slabs + (long long)blockIdx.x * M.slab_floats;
     const bool decoded = a.dec.n_dec > 0;
     const float g_reg = (decoded && a.g_side) ? __ldg(a.g_side + 5) : 0.f;
 
@@ -1683,6 +1749,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
             }
 #pragma unroll 1
             for (int stage = 3; stage >= 0; --stage) {
+                if (BAYES) {        // this evaluation's weight set and noise: every product of the previous one is consumed
+                    asm volatile("bar.sync %0, %1;" ::"n"(kTcBarTile), "n"(32 * kTcEpiWarps) : "memory");
+                    tc_stage_blob(smem + M.off_w, a_in.blob + (long long)(n * 4 + stage) * a_in.blob_stride, (uint32_t)M.blob_bytes, &wbar, wphase);
+                    c.bz_z = a.bayes_z + (size_t)(n * 4 + stage) * M.slab_floats;
+                }
                 // ---- stage input from the tape (loaded one evaluation ahead: the latency hides behind the sweep)
 #pragma unroll
                 for (int r = 0; r < R; ++r)
@@ -1718,8 +1789,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) rk4_bwd_tc_kernel(const __grid_
                     for (int i = 0; i < DN; ++i) g[i] = stage == 3 ? kb[3][i] : (stage == 2 ? kb[2][i] : (stage == 1 ? kb[1][i] : kb[0][i]));
                     tc_rhs_tail_vjp<R, L>(M, x, o_r, o_a, valid, gs, g, d_r, d_a, xb);
                 }
-                if (M.n_rate > 0) tc_net_backward<D0, 2 * R>(M, M.rate, M.n_rate, 0, c, d_r, x, slab, dx, is_traj);
-                if (M.n_aug > 0) tc_net_backward<D0, 3 * R>(M, M.aug, M.n_aug, 1, c, d_a, x, slab, dx, is_traj);
+                if (M.n_rate > 0) tc_net_backward<D0, 2 * R, BAYES>(M, M.rate, M.n_rate, 0, c, d_r, x, slab, dx, is_traj);
+                if (M.n_aug > 0) tc_net_backward<D0, 3 * R, BAYES>(M, M.aug, M.n_aug, 1, c, d_a, x, slab, dx, is_traj);
                 // ---- combine: xbar = direct + W0^T delta0 (both nets); propagate through the tableau
                 if (is_traj) {
 #pragma unroll
@@ -1831,6 +1902,29 @@ __global__ void tc_reduce_side_kernel(const double* __restrict__ partial_all, in
     for (int cidx = 0; cidx < n_parts; ++cidx) s += partial[cidx * 8 + i];
     if (i == 6) s = partial[6];   // RHS evaluations per trajectory: identical in every CTA
     side[i] = s;
+}
+
+// Bayes funcs: the noise of every evaluation from theta layout into SLAB layout (same index map as tc_reduce_dtheta_kernel);
+// z_slab must be zero-filled beforehand (padding entries).  grid (ceil(n_theta / 256), n_evals)
+__global__ void tc_pack_z_kernel(const __grid_constant__ TcModel M, const float* __restrict__ z_all, float* __restrict__ z_slab_all) {
+    const float* __restrict__ z = z_all + (size_t)blockIdx.y * M.n_theta;
+    float* __restrict__ zs = z_slab_all + (size_t)blockIdx.y * M.slab_floats;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M.n_theta) return;
+    const int nl = M.n_rate + M.n_aug;
+    for (int li = 0; li < nl; ++li) {
+        const TcLayer& Lp = li < M.n_rate ? M.rate[li] : M.aug[li - M.n_rate];
+        if (e >= Lp.th_w && e < Lp.th_w + Lp.in * Lp.out) {
+            const int k = e - Lp.th_w;
+            const int row = k / Lp.in, col = k - row * Lp.in;
+            zs[Lp.slab_off + (((((row >> 4) * (Lp.in_p >> 4) + (col >> 4)) * 4 + ((col & 15) >> 2)) * 16 + (row & 15)) * 4 + (col & 3))] = z[e];
+            return;
+        }
+        if (e >= Lp.th_b && e < Lp.th_b + Lp.out) {
+            zs[Lp.slab_off + 64 * Lp.in_p + (e - Lp.th_b)] = z[e];
+            return;
+        }
+    }
 }
 
 // g_theta[e] = sum over CTA slabs (fixed order => deterministic)

@@ -285,6 +285,117 @@ int tc_backward(const UdeDesc* desc, const TcModel& M, const float* theta, const
     return UDE_OK;
 }
 
+// ---- Bayes funcs on the tensor path: one blob per RHS evaluation, gradients folded into two slab sets -------------------------
+struct TcBayesWs {
+    uint8_t* blobs;         // [n_evals][blob_stride]
+    double* side_partial;   // [n_ctas][8]
+    float* slabs;           // [2][n_ctas][slab_floats]: sum_e G_e, then sum_e G_e * z_e
+    float* z_slab;          // [n_evals][slab_floats]
+    long long bytes;
+};
+static TcBayesWs tc_bayes_carve(void* base, const TcModel& M, int n_ctas, int n_evals) {
+    TcBayesWs w;
+    long long off = 0;
+    w.blobs = reinterpret_cast<uint8_t*>(base) + off;
+    off = align_up(off + tc_blob_stride(M) * n_evals, 256);
+    w.side_partial = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_ctas * 8 * 8, 256);
+    w.slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)2 * n_ctas * M.slab_floats * 4, 256);
+    w.z_slab = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off);
+    off = align_up(off + (long long)n_evals * M.slab_floats * 4, 256);
+    w.bytes = off;
+    return w;
+}
+long long tc_bayes_workspace(const UdeDesc* d, const TcModel& M, int n_steps, int* n_ctas) {
+    *n_ctas = tc_grid(d->batch);
+    return tc_bayes_carve(nullptr, M, *n_ctas, 4 * n_steps).bytes;
+}
+
+int tc_bayes_forward(const UdeDesc* desc, const TcModel& M, const float* theta_evals, const float* y0, const GridTables& g,
+                     float* y_out, float* tape, double* side, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    const int n_ctas = tc_grid(desc->batch), n_evals = 4 * g.n_steps;
+    TcBayesWs w = tc_bayes_carve(workspace, M, n_ctas, n_evals);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    tc_pack_kernel<<<dim3(M.n_rate + M.n_aug, n_evals), 256, 0, s>>>(M, theta_evals, w.blobs, tc_blob_stride(M));
+    UDE_CUDA(cudaGetLastError());
+    static thread_local TcTable tab_storage;
+    TcTable* tab = &tab_storage;
+    tc_build_table(M, *tab, false);
+    TcFwdArgs a{};
+    a.blob = w.blobs;
+    a.y0 = y0;
+    a.g = g;
+    a.y_out = y_out;
+    a.tape = tape;
+    a.side_partial = w.side_partial;
+    a.B = desc->batch;
+    a.n_groups = 1;
+    a.blob_stride = tc_blob_stride(M);
+    a.bayes = 1;
+    int st;
+#define UDE_TC_FWD(RR, LL)                                                                     \
+    do {                                                                                       \
+        if ((st = set_smem(rk4_fwd_tc_kernel<RR, LL, true>, M.smem_bytes_fwd)) != UDE_OK) return st; \
+        rk4_fwd_tc_kernel<RR, LL, true><<<n_ctas, kTcThreads, M.smem_bytes_fwd, s>>>(M, *tab, a);          \
+    } while (0)
+    if (M.L == 8) UDE_TC_FWD(1, 8);
+    else if (M.L == 4) UDE_TC_FWD(1, 4);
+    else UDE_TC_FWD(1, 16);
+#undef UDE_TC_FWD
+    UDE_CUDA(cudaGetLastError());
+    tc_reduce_side_kernel<<<1, 32, 0, s>>>(w.side_partial, n_ctas, side);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+int tc_bayes_backward(const UdeDesc* desc, const TcModel& M, const float* theta_evals, const float* z_evals, const float* y0,
+                      const GridTables& g, const float* tape, const float* g_out, const float* g_side, float* g_y0,
+                      float* g_mean_zsum, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+    const int n_ctas = tc_grid(desc->batch), n_evals = 4 * g.n_steps;
+    TcBayesWs w = tc_bayes_carve(workspace, M, n_ctas, n_evals);
+    if (w.bytes > workspace_bytes) return UDE_ERR_WORKSPACE;
+    if (!(desc->flags & UDE_FLAG_WEIGHTS_PACKED)) {
+        tc_pack_kernel<<<dim3(M.n_rate + M.n_aug, n_evals), 256, 0, s>>>(M, theta_evals, w.blobs, tc_blob_stride(M));
+        UDE_CUDA(cudaGetLastError());
+    }
+    UDE_CUDA(cudaMemsetAsync(w.z_slab, 0, (size_t)n_evals * M.slab_floats * 4, s));
+    tc_pack_z_kernel<<<dim3((M.n_theta + 255) / 256, n_evals), 256, 0, s>>>(M, z_evals, w.z_slab);
+    UDE_CUDA(cudaGetLastError());
+    UDE_CUDA(cudaMemsetAsync(w.slabs, 0, (size_t)2 * n_ctas * M.slab_floats * 4, s));
+    static thread_local TcTable tab_storage;
+    TcTable* tab = &tab_storage;
+    tc_build_table(M, *tab, true);
+    TcBwdArgs a{};
+    a.blob = w.blobs;
+    a.y0 = y0;
+    a.g = g;
+    a.tape = tape;
+    a.g_out = g_out;
+    a.g_side = g_side;
+    a.g_y0 = g_y0;
+    a.slabs = w.slabs;
+    a.B = desc->batch;
+    a.n_groups = 1;
+    a.blob_stride = tc_blob_stride(M);
+    a.bayes_z = w.z_slab;
+    a.bz_slabs = w.slabs + (size_t)n_ctas * M.slab_floats;
+    int st;
+#define UDE_TC_BWD(RR, LL)                                                                     \
+    do {                                                                                       \
+        if ((st = set_smem(rk4_bwd_tc_kernel<RR, LL, true>, M.smem_bytes_bwd)) != UDE_OK) return st; \
+        rk4_bwd_tc_kernel<RR, LL, true><<<n_ctas, kTcThreads, M.smem_bytes_bwd, s>>>(M, *tab, a);          \
+    } while (0)
+    if (M.L == 8) UDE_TC_BWD(1, 8);
+    else if (M.L == 4) UDE_TC_BWD(1, 4);
+    else UDE_TC_BWD(1, 16);
+#undef UDE_TC_BWD
+    UDE_CUDA(cudaGetLastError());
+    tc_reduce_dtheta_kernel<<<dim3((M.n_theta + 255) / 256, 2), 256, 0, s>>>(M, w.slabs, n_ctas, g_mean_zsum);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
 void tc_plan_info(const UdeDesc* d, const TcModel& M, long long* workspace_bytes, int* n_ctas) {
     *n_ctas = tc_grid(d->batch, d->n_groups);
     *workspace_bytes = tc_carve(nullptr, M, *n_ctas, d->batch, d->n_groups).bytes;

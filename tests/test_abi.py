@@ -165,10 +165,11 @@ def test_plan_paths_and_modes_host_only(built_lib):
     assert p1.tape_bytes >= (8 * 4 + 1) * 3 * (1 << 20) * 4          # stage inputs + ONE record for the final state
     st, p = plan(us, 4096, kernels="ffma")
     assert st == 0 and p.path == 0
-    st, pb = plan(us, 4096, flags=_lib.FLAG_BAYES)
+    st, pb = plan(us, 4096, flags=_lib.FLAG_BAYES, kernels="ffma")
     assert st == 0 and pb.path == 0 and pb.workspace_bytes > p.workspace_bytes + 2 * 32 * 11813 * 4     # weight sets + noise of 32 evaluations
-    assert plan(us, 4096, flags=_lib.FLAG_BAYES | 8)[0] == -2          # Bayes funcs: FFMA engine only
-    assert plan(us, 4096, flags=_lib.FLAG_BAYES, method=1)[0] == -2   # ... and rk4 only
+    st, pt = plan(us, 4096, flags=_lib.FLAG_BAYES)
+    assert st == 0 and pt.path == 1 and pt.workspace_bytes > 32 * 80_000                                # one weight image per evaluation
+    assert plan(us, 4096, flags=_lib.FLAG_BAYES, method=1)[0] == -2   # Bayes funcs: rk4 only
     states = ude_b200.FaFp(49, 8, net_sizes=[64, 64, 32], aug_net_sizes=[64, 64])
     st, p = plan(states, 8192, n_steps=28)
     assert st == 0 and p.path == 0 and p.tile_traj == 32 and p.weights_in_smem == 0     # ring plan: weights stream through shared memory

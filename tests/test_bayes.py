@@ -114,15 +114,19 @@ def test_mirror_classes_interchange_checkpoints_and_kl(cls, kind, R, L, net, aug
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cls,kind,R,L,net,aug,B,grid", [
-    ("Bayes_Fp", "Fp", 1, 8, (20, 20), (), 300, "weekly"),
-    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 200, "weekly"),
-    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 150, "interp"),
-    ("Bayes_Fa", "Fa", 2, 4, (), (32, 32), 97, "weekly"),
-    ("Bayes_FaFp", "FaFp", 3, 8, (20, 20), (32, 32), 120, "daily"),
-    ("Bayes_Fp", "Fp", 2, 3, (20, 20), (), 64, "weekly"),
+@pytest.mark.parametrize("cls,kind,R,L,net,aug,B,grid,kernels", [
+    ("Bayes_Fp", "Fp", 1, 8, (20, 20), (), 300, "weekly", None),            # None: the library's pick (tcgen05 engine where it covers the model)
+    ("Bayes_Fp", "Fp", 1, 8, (20, 20), (), 300, "weekly", "ffma"),
+    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 200, "weekly", "tensor"),
+    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 200, "weekly", "ffma"),
+    ("Bayes_FaFp", "FaFp", 1, 8, (64, 64, 32), (64, 64), 150, "interp", "tensor"),
+    ("Bayes_FaFp", "FaFp", 1, 16, (64, 64, 32), (64, 32), 131, "daily", "tensor"),
+    ("Bayes_Fa", "Fa", 1, 4, (), (32, 32), 260, "weekly", "tensor"),
+    ("Bayes_Fa", "Fa", 2, 4, (), (32, 32), 97, "weekly", None),
+    ("Bayes_FaFp", "FaFp", 3, 8, (20, 20), (32, 32), 120, "daily", None),
+    ("Bayes_Fp", "Fp", 2, 3, (20, 20), (), 64, "weekly", None),
 ])
-def test_fused_bayes_solve_matches_oracle(cls, kind, R, L, net, aug, B, grid):
+def test_fused_bayes_solve_matches_oracle(cls, kind, R, L, net, aug, B, grid, kernels):
     import ude_b200
     mod = _build(ude_b200, cls, R, L, net, aug, seed=7)
     with torch.no_grad():
@@ -142,6 +146,8 @@ def test_fused_bayes_solve_matches_oracle(cls, kind, R, L, net, aug, B, grid):
     else:
         t, h = torch.linspace(1, 21, 21) / 7, 1.0
     n_steps = {"weekly": 4, "daily": 14, "interp": 3}[grid]
+    if kernels == "tensor":
+        assert ude_b200.describe_func(mod).bayes
     z = torch.randn(4 * n_steps, mean.numel(), generator=torch.Generator().manual_seed(11))
     y0 = synth_y0(B, R, L, seed=2)
     G = torch.randn(t.numel(), B, R, L, generator=torch.Generator().manual_seed(12))
@@ -165,7 +171,7 @@ def test_fused_bayes_solve_matches_oracle(cls, kind, R, L, net, aug, B, grid):
     mod = mod.cuda()
     y0g = y0.cuda().requires_grad_(True)
     mod.clear_tracking()
-    y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=h, bayes_z=z.cuda()))
+    y = ude_b200.odeint(mod, y0g, t, method="rk4", options=dict(step_size=h, bayes_z=z.cuda(), kernels=kernels))
     loss(y, mod).backward()
     ls = _var_layers(mod)
     gm = torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)])
@@ -188,16 +194,18 @@ def test_bayes_default_noise_and_rejections():
     yb = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0))
     yc = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0))
     assert torch.equal(ya, yb) and not torch.equal(ya, yc)          # noise from the CUDA generator: reproducible, re-drawn per call
-    with pytest.raises(ude_b200.UdeError):
-        ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0, kernels="tensor"))
+    wide = _build(ude_b200, "Bayes_FaFp", 3, 8, (20, 20), (32, 32)).cuda()
+    with pytest.raises(ude_b200.UdeError):          # the tensor engine covers R = 1 only: pinned on an uncovered model it is an error
+        ude_b200.odeint(wide, synth_y0(64, 3, 8, seed=3).cuda(), t, method="rk4", options=dict(step_size=1.0, kernels="tensor"))
     with pytest.raises(NotImplementedError):
         ude_b200.odeint(mod, y0, t, method="dopri5", options=dict(per_trajectory=True))
 
 
 @pytest.mark.gpu
-def test_bayes_with_zero_noise_equals_the_deterministic_func_over_many_tiles():
+@pytest.mark.parametrize("kernels", ["ffma", "tensor"])
+def test_bayes_with_zero_noise_equals_the_deterministic_func_over_many_tiles(kernels):
     """z = 0 makes every evaluation's weight set the mean: several tiles per CTA, ragged last tile -- the per-evaluation
-    re-staging, the per-evaluation constant products and the fold must reproduce the plain FFMA-engine solve of an FaFp module
+    re-staging, the per-evaluation constant products and the fold must reproduce the plain solve (same engine) of an FaFp module
     that holds the means (trajectories bit for bit, gradients to summation round-off; dL/dw_std is exactly zero)."""
     import ude_b200
     B = 148 * 64 * 2 + 37
@@ -214,10 +222,10 @@ def test_bayes_with_zero_noise_equals_the_deterministic_func_over_many_tiles():
     G = torch.randn(4, B, 1, 8, generator=torch.Generator().manual_seed(3)).cuda()
     n_theta = sum(p.numel() for l in _var_layers(mod) for p in (l.w_mean, l.b_mean))
     ya0 = y0.clone().requires_grad_(True)
-    ya = ude_b200.odeint(mod, ya0, t, method="rk4", options=dict(step_size=1.0, bayes_z=torch.zeros(12, n_theta, device="cuda")))
+    ya = ude_b200.odeint(mod, ya0, t, method="rk4", options=dict(step_size=1.0, bayes_z=torch.zeros(12, n_theta, device="cuda"), kernels=kernels))
     (ya * G).sum().backward()
     yb0 = y0.clone().requires_grad_(True)
-    yb = ude_b200.odeint(plain, yb0, t, method="rk4", options=dict(step_size=1.0, kernels="ffma"))
+    yb = ude_b200.odeint(plain, yb0, t, method="rk4", options=dict(step_size=1.0, kernels=kernels))
     (yb * G).sum().backward()
     assert torch.equal(ya, yb)
     assert rel_err(ya0.grad, yb0.grad) <= 1e-6
