@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
     __shared__ double s_t0[kMaxTB], s_t1[kMaxTB], s_dt[kMaxTB];
     __shared__ float s_dtold[kMaxTB], s_h0[kMaxTB];
     __shared__ int s_j[kMaxTB], s_nacc[kMaxTB], s_nrej[kMaxTB], s_natt[kMaxTB], s_status[kMaxTB], s_acc[kMaxTB];
+    __shared__ int s_nint[kMaxTB];          // attempts since the last emitted output: torchdiffeq's max_num_steps is per output interval
     __shared__ __align__(8) uint64_t rbar[2];
 
     copy_model_to_smem(&P, Pg);
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
             s_j[b] = b < nvalid ? 1 : a.n_out;
             s_nacc[b] = s_nrej[b] = s_natt[b] = s_status[b] = 0;
             s_acc[b] = 0;
+            s_nint[b] = 0;
         }
         __syncthreads();
         if (ring) hoist_c0_ring(P, a.wpacked, smem, warp, lane, 0u);
@@ -363,8 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                 const int b = threadIdx.x;
                 int jj = s_j[b];
                 while (jj < a.n_out && !(a.t_out[jj] > s_t1[b])) ++jj;
+                if (jj != s_j[b]) s_nint[b] = 0;          // an output was reached: the step budget of the next interval starts over
                 if (jj < a.n_out) {
-                    if (s_natt[b] >= a.o.max_attempts) { s_status[b] = 2; }
+                    if (s_nint[b] >= a.o.max_attempts) { s_status[b] = 2; }
                     else if (a.tape_x && s_nacc[b] >= a.o.max_steps) { s_status[b] = 1; }
                     else if (!(s_t1[b] + s_dt[b] > s_t1[b]) || !isfinite(s_dt[b])) { s_status[b] = 3; }
                     if (s_status[b] != 0) {
@@ -374,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) dopri5_fwd_kernel(const __grid_co
                     } else {
                         pending = 1;
                         s_natt[b] += 1;
+                        s_nint[b] += 1;
                     }
                 }
                 s_j[b] = jj;

@@ -285,7 +285,7 @@ typedef struct UdeDopri5Opts {
     double  first_step;          /* <= 0: torchdiffeq's _select_initial_step      */
     double  safety, ifactor, dfactor;   /* 0.9, 10, 0.2                            */
     int32_t max_steps;           /* cap on ACCEPTED steps per trajectory (tape)   */
-    int32_t max_attempts;        /* cap on attempted steps per trajectory         */
+    int32_t max_attempts;        /* torchdiffeq's max_num_steps: cap on attempted steps per trajectory and OUTPUT INTERVAL */
     int32_t shared_step;         /* 0: one controller per trajectory.  1: torchdiffeq's batch semantics -- ONE RMS error norm
                                   * over the whole [B,R,L] tensor, one dt, one accept / reject for all trajectories (cooperative
                                   * launch, norms summed across CTAs); side sums then cover EVERY evaluation (initial-step probe

@@ -211,3 +211,26 @@ def test_shared_step_backward_deterministic_controller():
     assert rel_err(y, yr) <= RTOL_PARITY
     assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
     assert rel_err(flat_grad(mod), f.theta.grad) <= RTOL_PARITY
+
+
+def test_max_num_steps_is_per_output_interval():
+    """torchdiffeq counts max_num_steps per _advance(next_t), i.e. per output interval: a solve whose intervals need 2 attempts
+    each passes with max_num_steps = 2 over 4 intervals (8 attempts in total) and fails with 1."""
+    import ude_b200
+    from oracle import odeint_ref
+    from oracle.ude_rhs import OracleFunc, UdeSpec, init_theta, synth_y0
+    spec = UdeSpec("FaFp", 1, 8, (64, 64, 32), (64, 64))
+    theta = init_theta(spec, seed=5)
+    y0 = synth_y0(40, 1, 8, seed=6)
+    t = torch.arange(5.)
+    kw = dict(rtol=1e3, atol=1e3)             # every step accepted and grown by exactly ifactor: dt = 0.6, 0.6, ... with ifactor = 1
+    opts = dict(first_step=0.6, ifactor=1.0, per_trajectory=False)
+    mod = module_from_spec(spec, theta, 1.0, "cuda")
+    with torch.no_grad():
+        ref = odeint_ref.odeint(OracleFunc(spec, theta), y0, t, options=dict(max_num_steps=2, **opts), **kw)
+        y, stats = ude_b200.odeint(mod, y0.cuda(), t, options=dict(max_num_steps=2, return_stats=True, **opts), **kw)
+        assert int(stats.n_attempts[0]) == 7 and rel_err(y, ref) <= RTOL_PARITY
+        with pytest.raises(ude_b200.UdeError, match="max_num_steps"):
+            ude_b200.odeint(mod, y0.cuda(), t, options=dict(max_num_steps=1, **opts), **kw)
+        with pytest.raises(AssertionError):
+            odeint_ref.odeint(OracleFunc(spec, theta), y0, t, options=dict(max_num_steps=1, **opts), **kw)
