@@ -151,6 +151,7 @@ EXPORTS = [
     "ude_rk4_grid", "ude_rk4_forward", "ude_rk4_backward", "ude_dopri5_forward", "ude_dopri5_backward",
     "ude_measure_ffma_tflops", "ude_rk4_path", "ude_rk4_forward_reparam", "ude_rk4_backward_reparam",
     "ude_rk4_forward_decoded", "ude_rk4_backward_decoded", "ude_rk4_forward_bayes", "ude_rk4_backward_bayes",
+    "ude_rk4_forward_bayes_decoded", "ude_rk4_backward_bayes_decoded",
 ]
 
 
@@ -201,6 +202,12 @@ def lib() -> C.CDLL:
         L.ude_rk4_forward_bayes.argtypes = [C.POINTER(UdeDesc), vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         L.ude_rk4_backward_bayes.restype = C.c_int
         L.ude_rk4_backward_bayes.argtypes = [C.POINTER(UdeDesc), vp, vp, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_forward_bayes_decoded.restype = C.c_int
+        L.ude_rk4_forward_bayes_decoded.argtypes = [C.POINTER(UdeDesc), vp, vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp,
+                                                    C.POINTER(UdeDecoder), vp, vp, vp, vp, vp, vp, i64, vp]
+        L.ude_rk4_backward_bayes_decoded.restype = C.c_int
+        L.ude_rk4_backward_bayes_decoded.argtypes = [C.POINTER(UdeDesc), vp, vp, vp, C.POINTER(UdeReparam), i32, vp, i32, vp, vp, vp,
+                                                     C.POINTER(UdeDecoder), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
         L.ude_dopri5_forward.restype = C.c_int
         L.ude_dopri5_forward.argtypes = [C.POINTER(UdeDesc), C.POINTER(UdeDopri5Opts), vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, i64, vp]

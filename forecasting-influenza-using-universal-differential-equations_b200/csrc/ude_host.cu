@@ -1081,7 +1081,6 @@ int ude_rk4_forward_bayes(const UdeDesc* desc, const float* theta_evals, const f
         const int path = tc_choose(&db, Mt);
         if (path < 0) return path;
         if (path == 1) {
-            if (pending_reparam().mean || pending_decoded().n_dec > 0) return UDE_ERR_UNSUPPORTED;
             return tc_bayes_forward(desc, Mt, theta_evals, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, y_out, tape, side,
                                     workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
         }
@@ -1136,7 +1135,6 @@ int ude_rk4_backward_bayes(const UdeDesc* desc, const float* theta_evals, const 
         const int path = tc_choose(&db, Mt);
         if (path < 0) return path;
         if (path == 1) {
-            if (pending_reparam().mean || pending_decoded().n_dec > 0) return UDE_ERR_UNSUPPORTED;
             return tc_bayes_backward(desc, Mt, theta_evals, z_evals, y0, GridTables{n_steps, dt, n_out, out_step, out_kind, out_w}, tape,
                                      g_out, g_side, g_y0, g_mean_zsum, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
         }
@@ -1236,6 +1234,53 @@ int ude_rk4_backward_decoded(const UdeDesc* desc, const float* theta, const floa
         st = ude_rk4_backward(&d, theta, y0, n_steps, dt, n_out, out_step, out_kind, out_w, tape, /*g_out unused*/ g_pred, g_side,
                               g_y0, g_theta, workspace, workspace_bytes, stream);
     pending_decoded() = DecArgs{};
+    if (st != UDE_OK) return st;
+    const int n = dec->n_out * (3 * desc->n_regions + 1);
+    reduce_dec_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dec_partial, decoded_ctas(), n, g_dec);
+    UDE_CUDA(cudaGetLastError());
+    return UDE_OK;
+}
+
+// Bayes funcs with the fused consumers (and, optionally, the fused reparam producer): the decoded entry points over
+// ude_rk4_*_bayes.  theta_evals / z_evals / g_mean_zsum as there, everything else as in ude_rk4_*_decoded.
+int ude_rk4_forward_bayes_decoded(const UdeDesc* desc, const float* theta_evals, const float* y0, const UdeReparam* rp, int32_t n_steps,
+                                  const float* dt, int32_t n_out, const int32_t* out_step, const int32_t* out_kind, const float* out_w,
+                                  const UdeDecoder* dec, float* y_pred, uint8_t* out_mask, float* y0_out, float* tape, double* side,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
+    int st = check_decoder(desc, dec);
+    if (st != UDE_OK) return st;
+    if (!y_pred || !out_mask || (rp ? !y0_out : !y0)) return UDE_ERR_INVALID;
+    if (rp && (st = check_reparam(desc, rp)) != UDE_OK) return st;
+    UdeDesc d;
+    if ((st = decoded_desc(desc, dec, &d)) != UDE_OK) return st;
+    pending_decoded() = DecArgs{dec->weight, dec->bias, dec->n_out, y_pred, out_mask, nullptr, nullptr};
+    if (rp) pending_reparam() = ReparamArgs{rp->eps, rp->mean, rp->std, nullptr, rp->batch};
+    st = ude_rk4_forward_bayes(&d, theta_evals, rp ? y0_out : y0, n_steps, dt, n_out, out_step, out_kind, out_w,
+                               rp ? y0_out : const_cast<float*>(y0), tape, side, workspace, workspace_bytes, stream);
+    pending_decoded() = DecArgs{};
+    pending_reparam() = ReparamArgs{};
+    return st;
+}
+
+int ude_rk4_backward_bayes_decoded(const UdeDesc* desc, const float* theta_evals, const float* z_evals, const float* y0,
+                                   const UdeReparam* rp, int32_t n_steps, const float* dt, int32_t n_out, const int32_t* out_step,
+                                   const int32_t* out_kind, const float* out_w, const UdeDecoder* dec, const float* tape,
+                                   const uint8_t* out_mask, const float* g_pred, const float* g_side, float* g_y0, float* g_z,
+                                   float* g_mean_zsum, float* g_dec, float* dec_partial, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+    int st = check_decoder(desc, dec);
+    if (st != UDE_OK) return st;
+    if (!out_mask || !g_pred || !g_dec || !dec_partial || !y0 || (rp && !g_z)) return UDE_ERR_INVALID;
+    if (rp && (st = check_reparam(desc, rp)) != UDE_OK) return st;
+    UdeDesc d;
+    if ((st = decoded_desc(desc, dec, &d)) != UDE_OK) return st;
+    pending_decoded() = DecArgs{dec->weight, dec->bias, dec->n_out, nullptr, const_cast<uint8_t*>(out_mask), g_pred, dec_partial};
+    if (rp) pending_reparam() = ReparamArgs{rp->eps, rp->mean, rp->std, g_z, rp->batch};
+    decoded_ctas() = 0;
+    st = ude_rk4_backward_bayes(&d, theta_evals, z_evals, y0, n_steps, dt, n_out, out_step, out_kind, out_w, tape, /*g_out unused*/ g_pred,
+                                g_side, g_y0, g_mean_zsum, workspace, workspace_bytes, stream);
+    pending_decoded() = DecArgs{};
+    pending_reparam() = ReparamArgs{};
     if (st != UDE_OK) return st;
     const int n = dec->n_out * (3 * desc->n_regions + 1);
     reduce_dec_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dec_partial, decoded_ctas(), n, g_dec);

@@ -333,6 +333,8 @@ int tc_bayes_forward(const UdeDesc* desc, const TcModel& M, const float* theta_e
     a.n_groups = 1;
     a.blob_stride = tc_blob_stride(M);
     a.bayes = 1;
+    a.rp = pending_reparam();
+    a.dec = pending_decoded();
     int st;
 #define UDE_TC_FWD(RR, LL)                                                                     \
     do {                                                                                       \
@@ -380,6 +382,9 @@ int tc_bayes_backward(const UdeDesc* desc, const TcModel& M, const float* theta_
     a.blob_stride = tc_blob_stride(M);
     a.bayes_z = w.z_slab;
     a.bz_slabs = w.slabs + (size_t)n_ctas * M.slab_floats;
+    a.rp = pending_reparam();
+    a.dec = pending_decoded();
+    decoded_ctas() = n_ctas;
     int st;
 #define UDE_TC_BWD(RR, LL)                                                                     \
     do {                                                                                       \

@@ -340,9 +340,12 @@ class _Rk4SolveDecoded(torch.autograd.Function):
     never written (include/ude_b200.h UdeDecoder)."""
 
     @staticmethod
-    def forward(ctx, y0, eps, std, mean, dec_w, dec_b, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool, *params):
+    def forward(ctx, y0, eps, std, mean, dec_w, dec_b, info: FuncInfo, tables, n_steps: int, n_out: int, need_tape: bool,
+                bayes_z, n_par: int, *params):
+        # Bayes funcs (bayes_z given): params = (*means, *stds), n_par of each; evaluation e runs with mean + z_e * |std|
         L = _lib.lib()
         reparam = y0 is None
+        bayes = bayes_z is not None
         dev = dec_w.device
         if reparam:
             S, b, R, Lm1 = eps.shape
@@ -351,10 +354,20 @@ class _Rk4SolveDecoded(torch.autograd.Function):
             B, R, Ld = y0.shape
         n_dec = dec_w.shape[0]
         desc = info.desc(B)
+        if bayes:
+            desc.flags |= _lib.FLAG_BAYES
+        if n_dec != 1 and not (desc.flags & 8):
+            desc.flags |= 4                          # wider decoders run the FFMA engine: size the plan for it
         plan = _lib.UdePlan()
         with torch.cuda.device(dev):
             _lib.check(L.ude_plan(C.byref(desc), _lib.METHOD["rk4"], n_steps, C.byref(plan)), "ude_plan")
-            theta_c = flat_theta(params)
+            if bayes:
+                std_flat = torch.cat([p.detach().reshape(-1) for p in params[n_par:]])
+                z_c = bayes_z.detach().contiguous()
+                theta_c = torch.addcmul(torch.cat([p.detach().reshape(-1) for p in params[:n_par]]), z_c, std_flat.abs())
+            else:
+                std_flat = z_c = torch.empty(0, device=dev)
+                theta_c = flat_theta(params)
             w_c, b_c = dec_w.detach().contiguous(), dec_b.detach().contiguous()
             dec = _lib.UdeDecoder(w_c.data_ptr(), b_c.data_ptr(), n_dec)
             rp = None
@@ -371,19 +384,20 @@ class _Rk4SolveDecoded(torch.autograd.Function):
             ws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device=dev)
             tape = torch.empty(int(plan.tape_bytes), dtype=torch.uint8, device=dev) if need_tape else None
             dt, out_step, out_kind, out_w = tables
-            st = L.ude_rk4_forward_decoded(C.byref(desc), _ptr(theta_c), _ptr(None if reparam else y0_c),
-                                           C.byref(rp) if reparam else None, n_steps, _ptr(dt), n_out, _ptr(out_step),
-                                           _ptr(out_kind), _ptr(out_w), C.byref(dec), _ptr(y_pred), _ptr(mask),
-                                           _ptr(y0_c if reparam else None), _ptr(tape), _ptr(side), _ptr(ws),
-                                           int(plan.workspace_bytes), _stream_ptr(dev))
-            _lib.check(st, "ude_rk4_forward_decoded")
-        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out, ctx.reparam = info, tables, n_steps, n_out, reparam
-        ctx.plan_ws, ctx.n_ctas = int(plan.workspace_bytes), int(plan.n_ctas)
+            fwd = L.ude_rk4_forward_bayes_decoded if bayes else L.ude_rk4_forward_decoded
+            st = fwd(C.byref(desc), _ptr(theta_c), _ptr(None if reparam else y0_c),
+                     C.byref(rp) if reparam else None, n_steps, _ptr(dt), n_out, _ptr(out_step),
+                     _ptr(out_kind), _ptr(out_w), C.byref(dec), _ptr(y_pred), _ptr(mask),
+                     _ptr(y0_c if reparam else None), _ptr(tape), _ptr(side), _ptr(ws),
+                     int(plan.workspace_bytes), _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_forward_bayes_decoded" if bayes else "ude_rk4_forward_decoded")
+        ctx.info, ctx.tables, ctx.n_steps, ctx.n_out, ctx.reparam, ctx.bayes = info, tables, n_steps, n_out, reparam, bayes
+        ctx.plan_ws, ctx.n_ctas, ctx.desc_flags = int(plan.workspace_bytes), int(plan.n_ctas), int(desc.flags)
         empty = torch.empty(0, device=dev)
-        ctx.save_for_backward(theta_c, y0_c, eps_c, std_c, mean_c, w_c, b_c, mask if need_tape else empty,
-                              tape if need_tape else empty, ws if need_tape else empty)
+        ctx.save_for_backward(theta_c if (need_tape or not bayes) else empty, y0_c, eps_c, std_c, mean_c, w_c, b_c,
+                              mask if need_tape else empty, tape if need_tape else empty, ws if need_tape else empty, z_c, std_flat)
         ctx.has_tape = need_tape
-        ctx.param_meta = [(p.shape, p.numel()) for p in params]
+        ctx.param_meta = [(p.shape, p.numel()) for p in (params[:n_par] if bayes else params)]
         return y_pred, side
 
     @staticmethod
@@ -391,12 +405,12 @@ class _Rk4SolveDecoded(torch.autograd.Function):
         if not ctx.has_tape:
             raise RuntimeError("fused odeint was run without a tape (no input required grad)")
         L = _lib.lib()
-        theta_c, y0_c, eps_c, std_c, mean_c, w_c, b_c, mask, tape, ws = ctx.saved_tensors
+        theta_c, y0_c, eps_c, std_c, mean_c, w_c, b_c, mask, tape, ws, z_c, std_flat = ctx.saved_tensors
         dev = w_c.device
         B, R, Ld = y0_c.shape
         n_dec = w_c.shape[0]
         desc = ctx.info.desc(B)
-        desc.flags |= _lib.FLAG_WEIGHTS_PACKED
+        desc.flags = ctx.desc_flags | _lib.FLAG_WEIGHTS_PACKED
         with torch.cuda.device(dev):
             if g_pred is None:
                 g_pred = torch.zeros((ctx.n_out, B, n_dec), dtype=torch.float32, device=dev)
@@ -405,7 +419,7 @@ class _Rk4SolveDecoded(torch.autograd.Function):
             if g_side is not None:      # [0..4]: the usual side sums, [5]: dL/d(reg sum) = dL/dside[7]
                 gs = torch.cat([g_side[:5], g_side[7:8]]).to(torch.float32).contiguous()
             g_y0 = torch.empty_like(y0_c)
-            g_theta = torch.empty(theta_c.numel(), dtype=torch.float32, device=dev)
+            g_theta = torch.empty((2, std_flat.numel()) if ctx.bayes else theta_c.numel(), dtype=torch.float32, device=dev)
             n_d = n_dec * (3 * R + 1)
             g_dec = torch.empty(n_d, dtype=torch.float32, device=dev)
             partial = torch.empty(ctx.n_ctas * n_d, dtype=torch.float32, device=dev)
@@ -416,11 +430,18 @@ class _Rk4SolveDecoded(torch.autograd.Function):
                 rp = _lib.UdeReparam(eps_c.data_ptr(), mean_c.data_ptr(), std_c.data_ptr(), S, b)
                 g_z = torch.empty((S, b, R, Ld - 1), dtype=torch.float32, device=dev)
             dt, out_step, out_kind, out_w = ctx.tables
-            st = L.ude_rk4_backward_decoded(C.byref(desc), _ptr(theta_c), _ptr(y0_c), C.byref(rp) if rp is not None else None,
-                                            ctx.n_steps, _ptr(dt), ctx.n_out, _ptr(out_step), _ptr(out_kind), _ptr(out_w),
-                                            C.byref(dec), _ptr(tape), _ptr(mask), _ptr(g_pred), _ptr(gs), _ptr(g_y0), _ptr(g_z),
-                                            _ptr(g_theta), _ptr(g_dec), _ptr(partial), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
-            _lib.check(st, "ude_rk4_backward_decoded")
+            if ctx.bayes:
+                st = L.ude_rk4_backward_bayes_decoded(C.byref(desc), _ptr(theta_c), _ptr(z_c), _ptr(y0_c),
+                                                      C.byref(rp) if rp is not None else None, ctx.n_steps, _ptr(dt), ctx.n_out,
+                                                      _ptr(out_step), _ptr(out_kind), _ptr(out_w), C.byref(dec), _ptr(tape), _ptr(mask),
+                                                      _ptr(g_pred), _ptr(gs), _ptr(g_y0), _ptr(g_z), _ptr(g_theta), _ptr(g_dec),
+                                                      _ptr(partial), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            else:
+                st = L.ude_rk4_backward_decoded(C.byref(desc), _ptr(theta_c), _ptr(y0_c), C.byref(rp) if rp is not None else None,
+                                                ctx.n_steps, _ptr(dt), ctx.n_out, _ptr(out_step), _ptr(out_kind), _ptr(out_w),
+                                                C.byref(dec), _ptr(tape), _ptr(mask), _ptr(g_pred), _ptr(gs), _ptr(g_y0), _ptr(g_z),
+                                                _ptr(g_theta), _ptr(g_dec), _ptr(partial), _ptr(ws), ctx.plan_ws, _stream_ptr(dev))
+            _lib.check(st, "ude_rk4_backward_bayes_decoded" if ctx.bayes else "ude_rk4_backward_decoded")
         g_in = [None, None, None, None]
         if ctx.reparam:
             g_in[1] = g_z * std_c if ctx.needs_input_grad[1] else None
@@ -429,10 +450,19 @@ class _Rk4SolveDecoded(torch.autograd.Function):
         else:
             g_in[0] = g_y0
         grads, off = [], 0
-        for shape, n in ctx.param_meta:
-            grads.append(g_theta[off:off + n].view(shape))
-            off += n
-        return (*g_in, g_dec[:n_dec * 3 * R].view(n_dec, 3 * R), g_dec[n_dec * 3 * R:], None, None, None, None, None, *grads)
+        if ctx.bayes:       # dL/dmean = sum_e dL/dtheta_e, dL/dstd = sign(std) * sum_e dL/dtheta_e * z_e
+            g_std = g_theta[1] * torch.sign(std_flat)
+            g_stds = []
+            for shape, n in ctx.param_meta:
+                grads.append(g_theta[0, off:off + n].view(shape))
+                g_stds.append(g_std[off:off + n].view(shape))
+                off += n
+            grads += g_stds
+        else:
+            for shape, n in ctx.param_meta:
+                grads.append(g_theta[off:off + n].view(shape))
+                off += n
+        return (*g_in, g_dec[:n_dec * 3 * R].view(n_dec, 3 * R), g_dec[n_dec * 3 * R:], None, None, None, None, None, None, None, *grads)
 
 
 class _Rk4SolveGroups(torch.autograd.Function):
@@ -684,8 +714,6 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
     if method != "rk4":
         raise NotImplementedError("the fused decoder epilogue implements the reference's method, rk4")
     info = describe_func(func)
-    if info.bayes:
-        raise NotImplementedError("Bayes_* funcs go through ude_b200.odeint (method='rk4')")
     lin = _decoder_linear(decoder)
     R, Ld = info.n_regions, info.latent_dim
     if lin.in_features != 3 * R or lin.bias is None:
@@ -708,6 +736,7 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
     options = {} if options is None else dict(options)
     group = options.pop("process_group", None)
     info.kernels = options.pop("kernels", os.environ.get("UDE_B200_KERNELS") or None)
+    bayes_z = options.pop("bayes_z", None)
     unknown = set(options) - {"step_size"}
     if unknown:
         raise ValueError(f"unexpected rk4 options {sorted(unknown)}")
@@ -716,9 +745,19 @@ def odeint_decoded(func, decoder, y0, t, *, method="rk4", options=None, reparam=
         raise ValueError("t must be a one dimensional, strictly increasing tensor")
     (tables, n_steps) = _grid_on_device(t_cpu, options.get("step_size", None), lin.weight.device)
     params = [p for l in info.linears() for p in (l.weight, l.bias)]
+    n_par = len(params)
+    if info.bayes:      # weights re-drawn at every RHS evaluation (see odeint): params = means, then stds
+        n_theta = sum(p.numel() for p in params)
+        if bayes_z is None:
+            bayes_z = torch.randn(4 * n_steps, n_theta, dtype=torch.float32, device=lin.weight.device)
+        elif tuple(bayes_z.shape) != (4 * n_steps, n_theta) or bayes_z.device != lin.weight.device or bayes_z.dtype != torch.float32:
+            raise ValueError(f"bayes_z must be a float32 [{4 * n_steps}, {n_theta}] tensor on the func's device")
+        params = [*params, *[p for l in info.linears() for p in (l.w_std, l.b_std)]]
+    elif bayes_z is not None:
+        raise ValueError("options['bayes_z'] goes with a Bayes_* func")
     need_tape = torch.is_grad_enabled() and any(x.requires_grad for x in (*ins, lin.weight, lin.bias, *params))
     y_pred, side = _Rk4SolveDecoded.apply(y0, eps, std, mean, lin.weight, lin.bias, info, tables, n_steps, int(t.numel()),
-                                          need_tape, *params)
+                                          need_tape, bayes_z, n_par, *params)
     reg = side[7].to(torch.float32)          # this rank's trajectories only (a per-trajectory sum, like y_pred): a sharded trainer adds
     if group is not None:                    # its local terms and all-reduces gradients; posterior() / tracker need GLOBAL sums
         from .dist import all_reduce_side

@@ -279,6 +279,24 @@ int ude_rk4_backward_bayes(const UdeDesc* desc, const float* theta_evals /*dev*/
                            const float* g_out /*dev*/, const float* g_side /*dev | NULL*/, float* g_y0 /*dev*/,
                            float* g_mean_zsum /*dev [2, n_theta]*/, void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
 
+/* Bayes funcs with the fused consumers (and optionally the fused producer): ude_rk4_*_decoded over ude_rk4_*_bayes --
+ * theta_evals / z_evals / g_mean_zsum as in the bayes pair, every other argument as in the decoded pair. */
+int ude_rk4_forward_bayes_decoded(const UdeDesc* desc, const float* theta_evals /*dev*/, const float* y0 /*dev | NULL with rp*/,
+                                  const UdeReparam* rp /*NULL*/, int32_t n_steps, const float* dt /*dev*/, int32_t n_out,
+                                  const int32_t* out_step /*dev*/, const int32_t* out_kind /*dev*/, const float* out_w /*dev*/,
+                                  const UdeDecoder* dec, float* y_pred /*dev*/, uint8_t* out_mask /*dev*/, float* y0_out /*dev | NULL*/,
+                                  float* tape /*dev | NULL*/, double* side /*dev [8]*/,
+                                  void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
+int ude_rk4_backward_bayes_decoded(const UdeDesc* desc, const float* theta_evals /*dev*/, const float* z_evals /*dev*/,
+                                   const float* y0 /*dev*/, const UdeReparam* rp /*NULL*/, int32_t n_steps, const float* dt /*dev*/,
+                                   int32_t n_out, const int32_t* out_step /*dev*/, const int32_t* out_kind /*dev*/,
+                                   const float* out_w /*dev*/, const UdeDecoder* dec, const float* tape /*dev*/,
+                                   const uint8_t* out_mask /*dev*/, const float* g_pred /*dev*/, const float* g_side /*dev [6] | NULL*/,
+                                   float* g_y0 /*dev*/, float* g_z /*dev | NULL*/, float* g_mean_zsum /*dev [2, n_theta]*/,
+                                   float* g_dec /*dev*/, float* dec_partial /*dev scratch*/,
+                                   void* workspace /*dev*/, int64_t workspace_bytes, void* stream);
+
 /* Controller options of torchdiffeq's RKAdaptiveStepsizeODESolver. */
 typedef struct UdeDopri5Opts {
     double  rtol, atol;

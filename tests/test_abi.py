@@ -198,7 +198,7 @@ def test_front_end_argument_checks_need_no_gpu():
         ude_b200.odeint_decoded(us, ude_b200.Decoder(1, 8, 1, Fp=False), torch.zeros(4, 1, 8), t)
     bayes = ude_b200.Bayes_FaFp(1, 8)
     assert ude_b200.describe_func(bayes).bayes
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         ude_b200.odeint_decoded(bayes, dec, torch.zeros(4, 1, 8), t)
     with pytest.raises(ude_b200.UnsupportedFunc):
         ude_b200.describe_func(torch.nn.Linear(3, 3))

@@ -235,3 +235,52 @@ def test_bayes_with_zero_noise_equals_the_deterministic_func_over_many_tiles(ker
     gp = torch.cat([p.grad.reshape(-1) for net in (plain.net, plain.aug_net) for m in net if isinstance(m, torch.nn.Linear) for p in (m.weight, m.bias)])
     assert rel_err(gm, gp) <= 3e-6
     assert float(gs.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["ffma", "tensor"])
+def test_bayes_func_with_fused_reparam_and_decoder(kernels):
+    """All three fusions around a Bayesian ODE func in one call (f1 + f2 + f3): (eps, std, mean) in, (y_pred, reg) out, gradients
+    of mean / std (encoder side), of the variational means and stds and of the decoder -- against the same pieces run separately
+    through torch (reparam, decoder, latent_init_loss) around the Bayes solve."""
+    import ude_b200
+    S, b, L = 24, 7, 8
+    mod = _build(ude_b200, "Bayes_FaFp", 1, L, (64, 64, 32), (64, 64), seed=12).cuda()
+    with torch.no_grad():
+        for l in _var_layers(mod):
+            l.w_std.mul_(0.3); l.b_std.mul_(0.3)
+        for p in (mod.aug_net[-1].w_mean, mod.aug_net[-1].b_mean, mod.aug_net[-1].w_std, mod.aug_net[-1].b_std):
+            p.mul_(0.05)
+    g = torch.Generator().manual_seed(3)
+    mean = (torch.tensor([0.9, 0.02] + [0.0] * (L - 3)).expand(b, 1, L - 1) + 0.01 * torch.randn(b, 1, L - 1, generator=g)).cuda()
+    std = (torch.tensor([0.1, 0.05] + [1.0] * (L - 3)) * 0.3).expand(b, 1, L - 1).clone().cuda()
+    eps = torch.randn(S, b, 1, L - 1, generator=g).cuda()
+    t = torch.arange(5.)
+    n_theta = sum(p.numel() for l in _var_layers(mod) for p in (l.w_mean, l.b_mean))
+    z = torch.randn(16, n_theta, generator=g).cuda()
+    dec = ude_b200.Decoder(1, L, 1).cuda()
+    target = torch.rand(5, 1, 1, generator=g).cuda()
+    res = {}
+    for mode in ("fused", "pieces"):
+        mod.zero_grad(set_to_none=True); dec.zero_grad(set_to_none=True); mod.clear_tracking()
+        s_, m_ = std.clone().requires_grad_(True), mean.clone().requires_grad_(True)
+        if mode == "fused":
+            yp, reg = ude_b200.odeint_decoded(mod, dec, None, t, options=dict(step_size=1.0, kernels=kernels, bayes_z=z), reparam=(eps, s_, m_))
+        else:
+            zz = eps * s_ + m_
+            y0 = torch.cat([zz[..., :2].abs(), (1 - zz[..., :2].abs().sum(-1)).unsqueeze(-1), zz[..., 2:]], -1).reshape(S * b, 1, L) + 1e-5
+            lat = ude_b200.odeint(mod, y0, t, method="rk4", options=dict(step_size=1.0, kernels=kernels, bayes_z=z))
+            x3 = lat[..., :3]
+            yp = dec(x3)
+            reg = (torch.where(x3 < 0, x3.abs(), torch.zeros_like(x3)) + torch.where(x3 > 1, (1 - x3).abs(), torch.zeros_like(x3))).sum()
+        post = mod.posterior()
+        loss = ((yp - target) ** 2).mean() + 0.1 * reg / (S * b) + 0.01 * (post.mean ** 2).sum() + 0.01 * torch.norm(torch.stack(mod.tracker)) / (S * b) ** 0.5
+        loss.backward()
+        ls = _var_layers(mod)
+        res[mode] = (yp.detach(), s_.grad, m_.grad,
+                     torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_mean, l.b_mean)]),
+                     torch.cat([p.grad.reshape(-1) for l in ls for p in (l.w_std, l.b_std)]),
+                     dec.decoder[1].weight.grad.clone(), dec.decoder[1].bias.grad.clone())
+    assert rel_err(res["fused"][0], res["pieces"][0]) <= 1e-6
+    for i in range(1, 7):
+        assert rel_err(res["fused"][i], res["pieces"][i]) <= 5e-6, i

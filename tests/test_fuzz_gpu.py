@@ -26,7 +26,7 @@ def _case(seed):
     aug = widths() if kind != "Fp" else ()
     B = rng.choice([1, 7, 33, 64, 100, 257])
     grid = rng.choice(["weekly", "daily", "interp"])
-    mode = rng.choice(["plain", "plain", "decoded", "reparam", "bayes"])
+    mode = rng.choice(["plain", "plain", "decoded", "reparam", "bayes", "bayes_decoded"])
     return kind, R, L, net, aug, B, grid, mode
 
 
@@ -54,7 +54,9 @@ def test_random_configuration_matches_oracle(seed):
     fa_w = 0.7 if kind == "FaFp" else 1.0
     print(f"seed {seed}: {kind} R={R} L={L} net={net} aug={aug} B={B} {grid} {mode}")
 
-    if mode == "bayes":
+    bayes = mode in ("bayes", "bayes_decoded")
+    decoded = mode in ("decoded", "bayes_decoded")
+    if bayes:
         cls = {"Fp": "Bayes_Fp", "Fa": "Bayes_Fa", "FaFp": "Bayes_FaFp"}[kind]
         kw = {}
         if net:
@@ -110,7 +112,7 @@ def test_random_configuration_matches_oracle(seed):
     # fp64 solve on the SAME fp32-built grid (the grid arithmetic is part of the path: ude_rk4_grid restates it bit for bit)
     grid64 = odeint_ref.rk4_grid(t, h).double()
     lat = odeint_ref.odeint(f, y0r, t.double(), method="rk4", options=dict(grid_constructor=lambda *_: grid64))
-    if mode == "decoded":
+    if decoded:
         wr, br = dec_w.double().clone().requires_grad_(True), dec_b.double().clone().requires_grad_(True)
         x3 = lat[..., :3]
         yr = torch.nn.functional.linear(x3.reshape(t.numel(), B, 3 * R), wr, br)
@@ -128,12 +130,19 @@ def test_random_configuration_matches_oracle(seed):
         y = ude_b200.odeint_reparam(mod, e2, s2, m2, t, options=opts)
         ((y * G.cuda()).sum() + tail(mod)).backward()
         assert rel_err(s2.grad, s_.grad) <= RTOL_PARITY and rel_err(m2.grad, m_.grad) <= RTOL_PARITY
-    elif mode == "decoded":
+    elif decoded:
         lin = torch.nn.Linear(3 * R, n_dec).cuda()
         with torch.no_grad():
             lin.weight.copy_(dec_w); lin.bias.copy_(dec_b)
         y0g = y0.cuda().requires_grad_(True)
-        y, reg = ude_b200.odeint_decoded(mod, lin, y0g, t, options=opts)
+        if bayes:
+            opts["bayes_z"] = z.cuda()
+        try:
+            y, reg = ude_b200.odeint_decoded(mod, lin, y0g, t, options=opts)
+        except ude_b200.UdeError as e:
+            if bayes and e.status == -2:
+                pytest.skip("model too large for the Bayes mode's all-resident plans: explicit UDE_ERR_UNSUPPORTED")
+            raise
         ((y * Gd.cuda()).sum() + 0.5 * reg + tail(mod)).backward()
         assert abs(float(reg) - float(regr)) <= 1e-5 * max(1.0, abs(float(regr)))
         assert rel_err(lin.weight.grad, wr.grad) <= RTOL_PARITY
@@ -142,18 +151,18 @@ def test_random_configuration_matches_oracle(seed):
         assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
     else:
         y0g = y0.cuda().requires_grad_(True)
-        if mode == "bayes":
+        if bayes:
             opts["bayes_z"] = z.cuda()
         try:
             y = ude_b200.odeint(mod, y0g, t, method="rk4", options=opts)
         except ude_b200.UdeError as e:
-            if mode == "bayes" and e.status == -2:      # UDE_ERR_UNSUPPORTED: Bayes funcs need the all-resident plans
+            if bayes and e.status == -2:      # UDE_ERR_UNSUPPORTED: Bayes funcs need the all-resident plans
                 pytest.skip("model too large for the Bayes mode's all-resident plans: explicit UDE_ERR_UNSUPPORTED")
             raise
         ((y * G.cuda()).sum() + tail(mod)).backward()
         assert rel_err(y0g.grad, y0r.grad) <= RTOL_PARITY
     assert rel_err(y, yr) <= RTOL_PARITY
-    if mode == "bayes":
+    if bayes:
         gm = torch.cat([p.grad.reshape(-1) for l in layers for p in (l.w_mean, l.b_mean)])
         gs = torch.cat([p.grad.reshape(-1) for l in layers for p in (l.w_std, l.b_std)])
         assert rel_err(gm, f.theta.grad) <= RTOL_PARITY and rel_err(gs, f.std.grad) <= RTOL_PARITY
